@@ -1,0 +1,84 @@
+/* mgs_b200.h - C ABI of libmgs_b200.so, the B200-native replacement for the grasp-evaluation
+ * rollout hot path of freiberg-roman/mj-grasp-sim.
+ *
+ * What each entry point replaces in the reference (paths under /root/reference):
+ *   mgs_model_create          MjModel.from_xml_string + MjData  (mgs/env/gravityless_object_grasping.py:67-70)
+ *                             - the MJCF itself is compiled on the host (mj_grasp_sim_b200/compiler);
+ *                             this call uploads the flat result to the GPU.
+ *   mgs_grasp_collision_mask  the per-candidate loop of GravitylessObjectGrasping.grasp_collision_mask
+ *                             (mgs/env/gravityless_object_grasping.py:112-122: mj_resetData, set_qpos, set_pose,
+ *                             mj_forward, ncon != 0)
+ *   mgs_grasp_stability       the per-candidate loop of grasp_stability_evaluation_from_joints
+ *                             (mgs/env/gravityless_object_grasping.py:158-277) including close_gripper_at
+ *                             (mgs/gripper/panda.py:225-241 and siblings): up to 8000 mj_step per candidate
+ *   mgs_step_*                mujoco.mj_step(model, data, nstep) / mj_forward on a batch of explicit states
+ *                             (mgs/core/simualtion.py:45-61 state get/set + mj_step) - used by parity tests
+ *
+ * Conventions: every function returns 0 on success, <0 on error (message via mgs_last_error(),
+ * thread-local).  No torch types; plain pointers and sizes.  "_device" variants take CUDA device
+ * pointers (e.g. torch tensor .data_ptr()) and a cudaStream_t passed as void*; the plain variants
+ * take host pointers and perform the host<->device copies themselves (pinned staging).
+ * Buffers are owned by the caller; the model handle owns only the model constants and scratch.
+ * One host thread per model handle.  There is no CPU fallback: without a CUDA device every call
+ * fails with an error.
+ */
+#ifndef MGS_B200_H
+#define MGS_B200_H
+#include <stdint.h>
+
+#include "mgs_model_desc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct MgsModel MgsModel;
+
+/* rollout schedule: defaults of grasp_stability_evaluation_from_joints (:131-135) are
+ * {3000, 3000, 500, 0, 0.1, 0.02}; repose_on_close=1 for Allegro/LEAP (their close_gripper_at
+ * calls set_pose again, allegro.py:354-357). */
+typedef struct MgsRolloutCfg {
+  int nstep_close, nstep_lift, shake_steps, repose_on_close;
+  double lift_dist, shake_dist;
+} MgsRolloutCfg;
+
+typedef struct MgsModelInfo {
+  int nq, nv, nu, nmocap, state_stride, diag_stride, ncon_max, nefc_max, smem_bytes_per_env, warps_per_block,
+      blocks_per_sm, num_sms, real_bytes;
+} MgsModelInfo;
+
+int mgs_model_create(const MgsModelDesc *desc, int device, MgsModel **out);
+void mgs_model_destroy(MgsModel *model);
+int mgs_model_info(const MgsModel *model, MgsModelInfo *info);
+
+/* pose7: [n][7] processed base pose (pos xyz, quat wxyz) in float32 exactly as SE3Pose holds it;
+ * joints: [n][nj] float32; joint_qposadr: [nj] qpos addresses of the actuated joints
+ * (MjSimulation.get_joint_idxs); base_qposadr: qpos address of the gripper's free joint. */
+int mgs_grasp_collision_mask(MgsModel *model, int n, const float *pose7, const float *joints, int nj,
+                             const int *joint_qposadr, int base_qposadr, uint8_t *collision_free_out);
+int mgs_grasp_stability(MgsModel *model, int n, const float *pose7, const float *joints, int nj,
+                        const int *joint_qposadr, int base_qposadr, const double *close_ctrl,
+                        const MgsRolloutCfg *cfg, uint8_t *stable_out, int *steps_out);
+/* mode: 1 = collision mask, 2 = stability.  d_* are device pointers; steps may be NULL. */
+int mgs_rollout_device(MgsModel *model, int mode, int n, const float *d_pose7, const float *d_joints, int nj,
+                       const int *joint_qposadr, int base_qposadr, const double *close_ctrl,
+                       const MgsRolloutCfg *cfg, uint8_t *d_labels, int *d_steps, void *stream);
+
+/* Batched mj_step on explicit states.  State record (state_stride reals, env-major):
+ * qpos[nq] qvel[nv] qacc_warmstart[nv] ctrl[nu] mocap_pos[3] mocap_quat[4].  nstep = 0 runs
+ * mj_forward only.  diag (may be NULL) receives diag_stride reals per env: header
+ * {ncon, nefc, niter, bad, overflow, ne, nf, nl}, qacc, qacc_smooth, qfrc_smooth, M, xpos, xquat,
+ * contacts {dist,pos3,pair} x ncon_max, rows {aref,D,force,jar} x nefc_max.  Reals are float
+ * (double in the -DMGS_REAL_DOUBLE ablation build; see MgsModelInfo.real_bytes). */
+int mgs_step_host(MgsModel *model, int n, int nstep, const void *state_in, void *state_out, void *diag_out);
+int mgs_step_device(MgsModel *model, int n, int nstep, const void *d_state_in, void *d_state_out, void *d_diag_out,
+                    void *stream);
+
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+long long mgs_launch_count(void);
+const char *mgs_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

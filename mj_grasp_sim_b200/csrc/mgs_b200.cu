@@ -1,0 +1,250 @@
+// mgs_b200.cu - persistent warp-per-environment rollout kernel + the C ABI (include/mgs_b200.h).
+//
+// Launch shape: a persistent grid of (blocks_per_sm x 148) CTAs, each WARPS warps; every warp pulls
+// candidate indices from a global atomic work queue, so warps that finish early (most candidates
+// fail the post-close contact test after 3000 of 8000 steps) immediately start the next candidate
+// instead of idling until the slowest lane of a fixed assignment finishes.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <string>
+
+#include "../../include/mgs_b200.h"
+#include "mgs_model_build.h"
+#include "mgs_rollout.cuh"
+
+#ifndef MGS_WARPS_PER_BLOCK
+#define MGS_WARPS_PER_BLOCK 4
+#endif
+
+extern __shared__ __align__(16) unsigned char mgs_smem_raw[];
+
+__global__ void __launch_bounds__(MGS_WARPS_PER_BLOCK * 32)
+mgs_rollout_kernel(const DevModel m, const Layout L, const RolloutParams prm, const BatchIO io) {
+  real *base = reinterpret_cast<real *>(mgs_smem_raw) + (size_t)(threadIdx.x >> 5) * L.total;
+  const int lane = threadIdx.x & 31;
+  Env e;
+  for (;;) {
+    unsigned int env = 0;
+    if (lane == 0) env = atomicAdd(io.work_counter, 1u);
+    env = __shfl_sync(0xffffffffu, env, 0);
+    if (env >= (unsigned int)prm.n) break;
+    env_bind(e, base, L);
+    run_env_w(m, e, prm, io, (int)env);
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+static thread_local std::string g_err;
+static long long g_launches = 0;
+
+static int fail(const std::string &msg) { g_err = msg; return -1; }
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+
+struct MgsModel {
+  int device;
+  DevModel dm;
+  Layout L;
+  char *d_blob;
+  unsigned int *d_counter;
+  int num_sms, blocks_per_sm, smem_per_block;
+  int state_stride, diag_stride;
+  // staging for the host-pointer entry points (grown on demand)
+  void *d_stage, *h_stage;
+  size_t stage_bytes;
+  cudaStream_t stream;
+};
+
+extern "C" const char *mgs_last_error(void) { return g_err.c_str(); }
+extern "C" long long mgs_launch_count(void) { return g_launches; }
+
+extern "C" int mgs_model_create(const MgsModelDesc *desc, int device, MgsModel **out) {
+  if (!desc || !out) return fail("null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device: libmgs_b200 has no CPU path");
+  if (device < 0 || device >= ndev) return fail("bad device index");
+  CU(cudaSetDevice(device));
+  ModelBlob blob;
+  std::string err;
+  if (!build_model_blob(desc, blob, err)) return fail("model: " + err);
+  MgsModel *M = new MgsModel();
+  memset(M, 0, sizeof(*M));
+  M->device = device;
+  CU(cudaMalloc(&M->d_blob, blob.bytes.size()));
+  CU(cudaMemcpy(M->d_blob, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice));
+  M->dm = blob.dm;
+  rebase_model(M->dm, M->d_blob);
+  CU(cudaMalloc(&M->d_counter, sizeof(unsigned int)));
+  layout_compute(&M->L, desc->nq, desc->nv, desc->nu, desc->nbody, desc->njnt, desc->nmocap, desc->ntendon, desc->ncgeom, blob.ncon_max,
+                 blob.nefc_max);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  M->num_sms = prop.multiProcessorCount;
+  M->smem_per_block = (int)(M->L.total * sizeof(real)) * MGS_WARPS_PER_BLOCK;
+  if ((size_t)M->smem_per_block > prop.sharedMemPerBlockOptin) {
+    delete M;
+    return fail("model needs more shared memory per block than the device offers (env-per-block variant not built yet)");
+  }
+  CU(cudaFuncSetAttribute(mgs_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, M->smem_per_block));
+  int occ = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgs_rollout_kernel, MGS_WARPS_PER_BLOCK * 32, M->smem_per_block));
+  M->blocks_per_sm = occ > 0 ? occ : 1;
+  M->state_stride = desc->nq + 2 * desc->nv + desc->nu + 7 * desc->nmocap;
+  M->diag_stride = mgs_diag_stride(desc->nv, desc->nbody, blob.ncon_max, blob.nefc_max);
+  CU(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+  *out = M;
+  return 0;
+}
+
+extern "C" void mgs_model_destroy(MgsModel *M) {
+  if (!M) return;
+  cudaSetDevice(M->device);
+  cudaFree(M->d_blob);
+  cudaFree(M->d_counter);
+  if (M->d_stage) cudaFree(M->d_stage);
+  if (M->h_stage) cudaFreeHost(M->h_stage);
+  if (M->stream) cudaStreamDestroy(M->stream);
+  delete M;
+}
+
+extern "C" int mgs_model_info(const MgsModel *M, MgsModelInfo *info) {
+  if (!M || !info) return fail("null argument");
+  info->nq = M->dm.nq; info->nv = M->dm.nv; info->nu = M->dm.nu; info->nmocap = M->dm.nmocap;
+  info->state_stride = M->state_stride; info->diag_stride = M->diag_stride;
+  info->ncon_max = M->L.ncon_max; info->nefc_max = M->L.nefc_max;
+  info->smem_bytes_per_env = (int)(M->L.total * sizeof(real));
+  info->warps_per_block = MGS_WARPS_PER_BLOCK; info->blocks_per_sm = M->blocks_per_sm; info->num_sms = M->num_sms;
+  info->real_bytes = (int)sizeof(real);
+  return 0;
+}
+
+static int launch(MgsModel *M, const RolloutParams &prm, const BatchIO &io_in, cudaStream_t st) {
+  if (prm.n <= 0) return 0;
+  BatchIO io = io_in;
+  io.work_counter = M->d_counter;
+  CU(cudaMemsetAsync(M->d_counter, 0, sizeof(unsigned int), st));
+  int blocks_needed = (prm.n + MGS_WARPS_PER_BLOCK - 1) / MGS_WARPS_PER_BLOCK;
+  int grid = M->num_sms * M->blocks_per_sm;
+  if (grid > blocks_needed) grid = blocks_needed;
+  mgs_rollout_kernel<<<grid, MGS_WARPS_PER_BLOCK * 32, M->smem_per_block, st>>>(M->dm, M->L, prm, io);
+  g_launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int fill_params(const MgsModel *M, RolloutParams &prm, int mode, int n, int nj, const int *joint_qposadr, int base_qposadr,
+                       const double *close_ctrl, const MgsRolloutCfg *cfg) {
+  memset(&prm, 0, sizeof(prm));
+  if (nj > MGS_MAX_NJ) return fail("too many actuated joints");
+  if (base_qposadr < 0 || base_qposadr + 7 > M->dm.nq) return fail("bad base_qposadr");
+  prm.mode = mode; prm.n = n; prm.nj = nj; prm.base_qposadr = base_qposadr;
+  for (int k = 0; k < nj; k++) {
+    if (joint_qposadr[k] < 0 || joint_qposadr[k] >= M->dm.nq) return fail("bad joint_qposadr");
+    prm.joint_qposadr[k] = joint_qposadr[k];
+  }
+  if (mode == MGS_MODE_STABILITY) {
+    if (!cfg || !close_ctrl) return fail("stability rollout needs cfg and close_ctrl");
+    prm.nstep_close = cfg->nstep_close; prm.nstep_lift = cfg->nstep_lift; prm.shake_steps = cfg->shake_steps;
+    prm.repose_on_close = cfg->repose_on_close; prm.lift_dist = (real)cfg->lift_dist; prm.shake_dist = (real)cfg->shake_dist;
+    for (int u = 0; u < M->dm.nu; u++) prm.close_ctrl[u] = (real)close_ctrl[u];
+  }
+  return 0;
+}
+
+extern "C" int mgs_rollout_device(MgsModel *M, int mode, int n, const float *d_pose7, const float *d_joints, int nj,
+                                  const int *joint_qposadr, int base_qposadr, const double *close_ctrl, const MgsRolloutCfg *cfg,
+                                  uint8_t *d_labels, int *d_steps, void *stream) {
+  if (!M) return fail("null model");
+  if (mode != MGS_MODE_COLLISION && mode != MGS_MODE_STABILITY) return fail("bad mode");
+  CU(cudaSetDevice(M->device));
+  RolloutParams prm;
+  if (fill_params(M, prm, mode, n, nj, joint_qposadr, base_qposadr, close_ctrl, cfg)) return -1;
+  BatchIO io;
+  memset(&io, 0, sizeof(io));
+  io.pose7 = d_pose7; io.joints = d_joints; io.labels = d_labels; io.steps = d_steps;
+  return launch(M, prm, io, (cudaStream_t)stream);
+}
+
+static int ensure_stage(MgsModel *M, size_t bytes) {
+  if (bytes <= M->stage_bytes) return 0;
+  if (M->d_stage) cudaFree(M->d_stage);
+  if (M->h_stage) cudaFreeHost(M->h_stage);
+  M->d_stage = M->h_stage = nullptr;
+  M->stage_bytes = 0;
+  CU(cudaMalloc(&M->d_stage, bytes));
+  CU(cudaMallocHost(&M->h_stage, bytes));
+  M->stage_bytes = bytes;
+  return 0;
+}
+
+static size_t up256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static int rollout_host(MgsModel *M, int mode, int n, const float *pose7, const float *joints, int nj, const int *joint_qposadr,
+                        int base_qposadr, const double *close_ctrl, const MgsRolloutCfg *cfg, uint8_t *labels, int *steps) {
+  if (!M) return fail("null model");
+  if (n <= 0) return 0;
+  CU(cudaSetDevice(M->device));
+  size_t o_pose = 0, o_joint = up256(o_pose + (size_t)n * 7 * 4), o_lab = up256(o_joint + (size_t)n * (nj > 0 ? nj : 1) * 4),
+         o_steps = up256(o_lab + (size_t)n), total = up256(o_steps + (size_t)n * 4);
+  if (ensure_stage(M, total)) return -1;
+  char *h = (char *)M->h_stage, *d = (char *)M->d_stage;
+  memcpy(h + o_pose, pose7, (size_t)n * 7 * 4);
+  memcpy(h + o_joint, joints, (size_t)n * nj * 4);
+  CU(cudaMemcpyAsync(d + o_pose, h + o_pose, o_lab, cudaMemcpyHostToDevice, M->stream));
+  int rc = mgs_rollout_device(M, mode, n, (const float *)(d + o_pose), (const float *)(d + o_joint), nj, joint_qposadr, base_qposadr,
+                              close_ctrl, cfg, (uint8_t *)(d + o_lab), (int *)(d + o_steps), M->stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h + o_lab, d + o_lab, total - o_lab, cudaMemcpyDeviceToHost, M->stream));
+  CU(cudaStreamSynchronize(M->stream));
+  memcpy(labels, h + o_lab, (size_t)n);
+  if (steps) memcpy(steps, h + o_steps, (size_t)n * 4);
+  return 0;
+}
+
+extern "C" int mgs_grasp_collision_mask(MgsModel *M, int n, const float *pose7, const float *joints, int nj, const int *joint_qposadr,
+                                        int base_qposadr, uint8_t *collision_free_out) {
+  return rollout_host(M, MGS_MODE_COLLISION, n, pose7, joints, nj, joint_qposadr, base_qposadr, nullptr, nullptr, collision_free_out, nullptr);
+}
+
+extern "C" int mgs_grasp_stability(MgsModel *M, int n, const float *pose7, const float *joints, int nj, const int *joint_qposadr,
+                                   int base_qposadr, const double *close_ctrl, const MgsRolloutCfg *cfg, uint8_t *stable_out,
+                                   int *steps_out) {
+  return rollout_host(M, MGS_MODE_STABILITY, n, pose7, joints, nj, joint_qposadr, base_qposadr, close_ctrl, cfg, stable_out, steps_out);
+}
+
+extern "C" int mgs_step_device(MgsModel *M, int n, int nstep, const void *d_state_in, void *d_state_out, void *d_diag_out, void *stream) {
+  if (!M) return fail("null model");
+  CU(cudaSetDevice(M->device));
+  RolloutParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.mode = MGS_MODE_STEP; prm.n = n; prm.nstep = nstep;
+  BatchIO io;
+  memset(&io, 0, sizeof(io));
+  io.state_in = (const real *)d_state_in; io.state_out = (real *)d_state_out; io.diag_out = (real *)d_diag_out;
+  io.state_stride = M->state_stride; io.diag_stride = M->diag_stride;
+  return launch(M, prm, io, (cudaStream_t)stream);
+}
+
+extern "C" int mgs_step_host(MgsModel *M, int n, int nstep, const void *state_in, void *state_out, void *diag_out) {
+  if (!M) return fail("null model");
+  if (n <= 0) return 0;
+  CU(cudaSetDevice(M->device));
+  size_t sb = (size_t)n * M->state_stride * sizeof(real), db = diag_out ? (size_t)n * M->diag_stride * sizeof(real) : 0;
+  size_t o_in = 0, o_out = up256(sb), o_diag = up256(o_out + sb), total = up256(o_diag + db);
+  if (ensure_stage(M, total)) return -1;
+  char *h = (char *)M->h_stage, *d = (char *)M->d_stage;
+  memcpy(h + o_in, state_in, sb);
+  CU(cudaMemcpyAsync(d + o_in, h + o_in, sb, cudaMemcpyHostToDevice, M->stream));
+  int rc = mgs_step_device(M, n, nstep, d + o_in, d + o_out, diag_out ? d + o_diag : nullptr, M->stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h + o_out, d + o_out, total - o_out, cudaMemcpyDeviceToHost, M->stream));
+  CU(cudaStreamSynchronize(M->stream));
+  memcpy(state_out, h + o_out, sb);
+  if (diag_out) memcpy(diag_out, h + o_diag, db);
+  return 0;
+}

@@ -1,0 +1,373 @@
+// mgs_collide.cuh - broadphase + convex narrowphase, ONE GEOM PAIR PER LANE.
+//
+// The candidate pair list is static (filtered on the host: contype/conaffinity, <exclude>,
+// parent-child, same body) and its contact parameters are pre-mixed, so the device does a
+// bounding-sphere cull, then Minkowski Portal Refinement (the algorithm MuJoCo 3.2.2 reaches
+// through libccd for mesh pairs) with analytic box supports and hill-climbing hull supports, then
+// clips the two most-aligned polytope faces against each other for a <=4 point manifold.
+// Contact slots are assigned with a warp prefix sum so the contact order is deterministic
+// (pair order), which keeps the Gauss-Seidel noslip pass reproducible.
+#pragma once
+#include "mgs_sim.cuh"
+
+#define MGS_MAXPOLY 8
+#define MGS_MAXCLIP 12
+#define MGS_FACE_ALIGN_MIN R_(0.9990)
+
+struct SupPt { real v[3], v1[3], v2[3]; };
+
+struct GeomRef {
+  int type, hull, nvert, vadr;
+  const real *R, *p;
+  real size[3];
+  int cur;  // hill-climbing start vertex (persists across support calls of one query)
+};
+
+MGS_DEV void geomref_init(GeomRef &g, const DevModel &m, const Env &e, int cg) {
+  g.type = LDG(m.cgeom_type + cg);
+  g.hull = LDG(m.cgeom_hullid + cg);
+  g.R = e.gxmat + 9 * cg;
+  g.p = e.gxpos + 3 * cg;
+  ld3(g.size, m.cgeom_size + 3 * cg);
+  g.cur = 0;
+  g.nvert = 0; g.vadr = 0;
+  if (g.type == GEOM_MESH) { g.nvert = LDG(m.hull_vertnum + g.hull); g.vadr = LDG(m.hull_vertadr + g.hull); }
+}
+
+// support point (world) of a geom in world direction d
+MGS_DEV void geom_support(const DevModel &m, GeomRef &g, const real *d, real *out) {
+  real dl[3], p[3] = {0, 0, 0};
+  mulmatTvec3(dl, g.R, d);
+  if (g.type == GEOM_BOX) {
+    p[0] = dl[0] >= 0 ? g.size[0] : -g.size[0];
+    p[1] = dl[1] >= 0 ? g.size[1] : -g.size[1];
+    p[2] = dl[2] >= 0 ? g.size[2] : -g.size[2];
+  } else if (g.type == GEOM_MESH) {
+    // hill climbing on the hull's vertex graph from the previous answer
+    const real *V = m.hull_vert + 3 * g.vadr;
+    int cur = g.cur;
+    real best = LDG(V + 3 * cur) * dl[0] + LDG(V + 3 * cur + 1) * dl[1] + LDG(V + 3 * cur + 2) * dl[2];
+    for (int guard = 0; guard < g.nvert; guard++) {
+      int na = LDG(m.hull_nbradr + g.vadr + cur), nn = LDG(m.hull_nbrnum + g.vadr + cur), nxt = cur;
+      for (int k = 0; k < nn; k++) {
+        int v = LDG(m.hull_nbr + na + k);
+        real t = LDG(V + 3 * v) * dl[0] + LDG(V + 3 * v + 1) * dl[1] + LDG(V + 3 * v + 2) * dl[2];
+        if (t > best) { best = t; nxt = v; }
+      }
+      if (nxt == cur) break;
+      cur = nxt;
+    }
+    g.cur = cur;
+    ld3(p, V + 3 * cur);
+  } else if (g.type == GEOM_SPHERE) {
+    scl3(p, dl, g.size[0]);
+  } else if (g.type == GEOM_CAPSULE) {
+    scl3(p, dl, g.size[0]);
+    p[2] += dl[2] >= 0 ? g.size[1] : -g.size[1];
+  } else if (g.type == GEOM_CYLINDER) {
+    real n = sqrt(dl[0] * dl[0] + dl[1] * dl[1]);
+    if (n > MGS_MINVAL) { p[0] = dl[0] / n * g.size[0]; p[1] = dl[1] / n * g.size[0]; }
+    p[2] = dl[2] >= 0 ? g.size[1] : -g.size[1];
+  }
+  mulmatvec3(out, g.R, p);
+  add3(out, out, g.p);
+}
+
+MGS_DEV void mink_support(const DevModel &m, GeomRef &g1, GeomRef &g2, const real *d, SupPt &o) {
+  real nd[3] = {-d[0], -d[1], -d[2]};
+  geom_support(m, g1, d, o.v1);
+  geom_support(m, g2, nd, o.v2);
+  sub3(o.v, o.v1, o.v2);
+}
+
+MGS_DEV void portal_dir(const SupPt &p1, const SupPt &p2, const SupPt &p3, real *dir) {
+  real a[3], b[3];
+  sub3(a, p2.v, p1.v);
+  sub3(b, p3.v, p1.v);
+  cross3(dir, a, b);
+  normalize3(dir);
+}
+
+MGS_DEV void expand_portal(const SupPt &p0, SupPt &p1, SupPt &p2, SupPt &p3, const SupPt &v4) {
+  real v4v0[3];
+  cross3(v4v0, v4.v, p0.v);
+  if (dot3(p1.v, v4v0) > 0) {
+    if (dot3(p2.v, v4v0) > 0) p1 = v4; else p3 = v4;
+  } else {
+    if (dot3(p3.v, v4v0) > 0) p2 = v4; else p1 = v4;
+  }
+}
+
+MGS_DEV int reach_tolerance(const SupPt &p1, const SupPt &p2, const SupPt &p3, const SupPt &v4, const real *dir, real tol) {
+  real d4 = dot3(v4.v, dir);
+  real mn = fmin(d4 - dot3(p1.v, dir), fmin(d4 - dot3(p2.v, dir), d4 - dot3(p3.v, dir)));
+  return mn <= tol;
+}
+
+MGS_DEV void closest_on_triangle(const real *a, const real *b, const real *c, real *out) {
+  real ab[3], ac[3], ap[3] = {-a[0], -a[1], -a[2]};
+  sub3(ab, b, a); sub3(ac, c, a);
+  real d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+  if (d1 <= 0 && d2 <= 0) { copy3(out, a); return; }
+  real bp[3] = {-b[0], -b[1], -b[2]};
+  real d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+  if (d3 >= 0 && d4 <= d3) { copy3(out, b); return; }
+  real vc = d1 * d4 - d3 * d2;
+  if (vc <= 0 && d1 >= 0 && d3 <= 0) { real v = d1 / (d1 - d3); copy3(out, a); addscl3(out, ab, v); return; }
+  real cp[3] = {-c[0], -c[1], -c[2]};
+  real d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+  if (d6 >= 0 && d5 <= d6) { copy3(out, c); return; }
+  real vb = d5 * d2 - d1 * d6;
+  if (vb <= 0 && d2 >= 0 && d6 <= 0) { real w = d2 / (d2 - d6); copy3(out, a); addscl3(out, ac, w); return; }
+  real va = d3 * d6 - d5 * d4;
+  if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+    real w = (d4 - d3) / ((d4 - d3) + (d5 - d6)), bc[3];
+    sub3(bc, c, b); copy3(out, b); addscl3(out, bc, w); return;
+  }
+  real den = R_(1.0) / (va + vb + vc), v = vb * den, w = vc * den;
+  copy3(out, a); addscl3(out, ab, v); addscl3(out, ac, w);
+}
+
+// returns 1 when penetrating: depth > 0, dir from g1 to g2 (unit), pos
+MGS_DEVN int mpr_penetration(const DevModel &m, GeomRef &g1, GeomRef &g2, real *depth, real *dir, real *pos) {
+  const real tol = m.mpr_tolerance;
+  SupPt p0, p1, p2, p3, v4;
+  real d[3], va[3], vb[3];
+  copy3(p0.v1, g1.p); copy3(p0.v2, g2.p);
+  sub3(p0.v, p0.v1, p0.v2);
+  if (dot3(p0.v, p0.v) < R_(1e-28)) p0.v[0] += R_(1e-10);
+  scl3(d, p0.v, -1); normalize3(d);
+  mink_support(m, g1, g2, d, p1);
+  if (dot3(p1.v, d) <= 0) return 0;
+  cross3(d, p0.v, p1.v);
+  if (dot3(d, d) < R_(1e-28) * fmax(R_(1e-30), dot3(p0.v, p0.v) * dot3(p1.v, p1.v))) {
+    *depth = sqrt(dot3(p1.v, p1.v));
+    copy3(dir, p1.v); normalize3(dir);
+    for (int k = 0; k < 3; k++) pos[k] = R_(0.5) * (p1.v1[k] + p1.v2[k]);
+    return *depth > 0;
+  }
+  normalize3(d);
+  mink_support(m, g1, g2, d, p2);
+  if (dot3(p2.v, d) <= 0) return 0;
+  sub3(va, p1.v, p0.v); sub3(vb, p2.v, p0.v);
+  cross3(d, va, vb); normalize3(d);
+  if (dot3(d, p0.v) > 0) { SupPt t = p1; p1 = p2; p2 = t; scl3(d, d, -1); }
+  for (int it = 0;; it++) {
+    if (it > 100) return 0;
+    mink_support(m, g1, g2, d, p3);
+    if (dot3(p3.v, d) <= 0) return 0;
+    int cont = 0;
+    cross3(va, p1.v, p3.v);
+    if (dot3(va, p0.v) < R_(-1e-30)) { p2 = p3; cont = 1; }
+    if (!cont) {
+      cross3(va, p3.v, p2.v);
+      if (dot3(va, p0.v) < R_(-1e-30)) { p1 = p3; cont = 1; }
+    }
+    if (!cont) break;
+    sub3(va, p1.v, p0.v); sub3(vb, p2.v, p0.v);
+    cross3(d, va, vb); normalize3(d);
+  }
+  for (int it = 0;; it++) {
+    portal_dir(p1, p2, p3, d);
+    if (dot3(d, p1.v) >= 0) break;
+    mink_support(m, g1, g2, d, v4);
+    if (dot3(v4.v, d) < 0 || reach_tolerance(p1, p2, p3, v4, d, tol) || it > m.mpr_iterations) return 0;
+    expand_portal(p0, p1, p2, p3, v4);
+  }
+  for (int it = 0;; it++) {
+    portal_dir(p1, p2, p3, d);
+    mink_support(m, g1, g2, d, v4);
+    if (reach_tolerance(p1, p2, p3, v4, d, tol) || it > m.mpr_iterations) {
+      real c[3];
+      closest_on_triangle(p1.v, p2.v, p3.v, c);
+      *depth = sqrt(dot3(c, c));
+      if (*depth < MGS_MINVAL) copy3(dir, d); else scl3(dir, c, R_(1.0) / *depth);
+      real b0, b1, b2, b3, t[3], sum;
+      cross3(t, p1.v, p2.v); b0 = dot3(t, p3.v);
+      cross3(t, p3.v, p2.v); b1 = dot3(t, p0.v);
+      cross3(t, p0.v, p1.v); b2 = dot3(t, p3.v);
+      cross3(t, p2.v, p1.v); b3 = dot3(t, p0.v);
+      sum = b0 + b1 + b2 + b3;
+      if (sum <= 0) {
+        b0 = 0;
+        cross3(t, p2.v, p3.v); b1 = dot3(t, d);
+        cross3(t, p3.v, p1.v); b2 = dot3(t, d);
+        cross3(t, p1.v, p2.v); b3 = dot3(t, d);
+        sum = b1 + b2 + b3;
+      }
+      real is = R_(0.5) / sum;
+      for (int k = 0; k < 3; k++)
+        pos[k] = (b0 * (p0.v1[k] + p0.v2[k]) + b1 * (p1.v1[k] + p1.v2[k]) + b2 * (p2.v1[k] + p2.v2[k]) + b3 * (p3.v1[k] + p3.v2[k])) * is;
+      return 1;
+    }
+    expand_portal(p0, p1, p2, p3, v4);
+  }
+}
+
+MGS_DEV int best_face(const DevModel &m, const GeomRef &g, const real *n, real *align) {
+  real nl[3], bd = R_(-1e30);
+  mulmatTvec3(nl, g.R, n);
+  int fa = LDG(m.hull_faceadr + g.hull), fn = LDG(m.hull_facenum + g.hull), best = 0;
+  const real *FN = m.hull_facenormal + 3 * fa;
+  for (int f = 0; f < fn; f++) {
+    real t = LDG(FN + 3 * f) * nl[0] + LDG(FN + 3 * f + 1) * nl[1] + LDG(FN + 3 * f + 2) * nl[2];
+    if (t > bd) { bd = t; best = f; }
+  }
+  *align = bd;
+  return best;
+}
+MGS_DEV int face_polygon(const DevModel &m, const GeomRef &g, int f, real (*poly)[3], real *nw) {
+  int gf = LDG(m.hull_faceadr + g.hull) + f;
+  int n = LDG(m.hull_facevertnum + gf), fva = LDG(m.hull_facevertadr + gf), va = LDG(m.hull_vertadr + g.hull);
+  for (int i = 0; i < n; i++) {
+    real v[3];
+    ld3(v, m.hull_vert + 3 * (va + LDG(m.hull_facevert + fva + i)));
+    mulmatvec3(poly[i], g.R, v);
+    add3(poly[i], poly[i], g.p);
+  }
+  real fnl[3];
+  ld3(fnl, m.hull_facenormal + 3 * gf);
+  mulmatvec3(nw, g.R, fnl);
+  return n;
+}
+
+struct PairContacts { int n; real normal[3], pos[4][3], dist[4]; };
+
+// narrowphase for candidate pair `pair`; fills up to 4 contacts
+MGS_DEVN void collide_pair(const DevModel &m, const Env &e, int pair, PairContacts &out) {
+  out.n = 0;
+  int c1 = LDG(m.pair_geom1 + pair), c2 = LDG(m.pair_geom2 + pair);
+  real dc[3];
+  sub3(dc, e.gxpos + 3 * c1, e.gxpos + 3 * c2);
+  real rr = LDG(m.cgeom_rbound + c1) + LDG(m.cgeom_rbound + c2) + LDG(m.pair_margin + pair);
+  if (dot3(dc, dc) > rr * rr) return;
+  GeomRef g1, g2;
+  geomref_init(g1, m, e, c1);
+  geomref_init(g2, m, e, c2);
+  real depth, n[3], pos[3];
+  if (!mpr_penetration(m, g1, g2, &depth, n, pos)) return;
+  if (!(depth > 0)) return;
+  int poly1 = (g1.type == GEOM_BOX || g1.type == GEOM_MESH), poly2 = (g2.type == GEOM_BOX || g2.type == GEOM_MESH);
+  if (poly1 && poly2) {
+    real a1, a2, nn[3] = {-n[0], -n[1], -n[2]};
+    int f1 = best_face(m, g1, n, &a1), f2 = best_face(m, g2, nn, &a2);
+    if (fmax(a1, a2) >= MGS_FACE_ALIGN_MIN) {
+      const int ref_is_1 = a1 >= a2;
+      const GeomRef &rg = ref_is_1 ? g1 : g2;
+      const GeomRef &ig = ref_is_1 ? g2 : g1;
+      real ref[MGS_MAXPOLY][3], nref[3], ninc[3], A[MGS_MAXCLIP][3], B[MGS_MAXCLIP][3], dist[MGS_MAXCLIP];
+      int nr = face_polygon(m, rg, ref_is_1 ? f1 : f2, ref, nref);
+      real mn[3] = {-nref[0], -nref[1], -nref[2]}, al;
+      int incf = best_face(m, ig, mn, &al);
+      int na = face_polygon(m, ig, incf, A, ninc);
+      for (int ed = 0; ed < nr && na > 0; ed++) {
+        real edge[3], sn[3];
+        int e2 = (ed + 1 == nr) ? 0 : ed + 1;
+        sub3(edge, ref[e2], ref[ed]);
+        cross3(sn, edge, nref);
+        int nb2 = 0;
+        for (int i = 0; i < na; i++) {
+          const real *P = A[i], *Q = A[(i + 1 == na) ? 0 : i + 1];
+          real t0[3], t1[3];
+          sub3(t0, P, ref[ed]); sub3(t1, Q, ref[ed]);
+          real dp = dot3(t0, sn), dq = dot3(t1, sn);
+          if (dp <= 0 && nb2 < MGS_MAXCLIP) { copy3(B[nb2], P); nb2++; }
+          if ((dp <= 0) != (dq <= 0) && nb2 < MGS_MAXCLIP) {
+            real t = dp / (dp - dq);
+            for (int k = 0; k < 3; k++) B[nb2][k] = P[k] + t * (Q[k] - P[k]);
+            nb2++;
+          }
+        }
+        na = nb2;
+        for (int i = 0; i < na; i++) copy3(A[i], B[i]);
+      }
+      int np = 0;
+      for (int i = 0; i < na; i++) {
+        real t[3];
+        sub3(t, A[i], ref[0]);
+        real dd = dot3(t, nref);
+        if (dd < 0) { copy3(A[np], A[i]); dist[np] = dd; np++; }
+      }
+      if (np > 0) {
+        int sel[4], ns = 0, i0 = 0;
+        for (int i = 1; i < np; i++) if (dist[i] < dist[i0]) i0 = i;
+        sel[ns++] = i0;
+        if (np > 1) {
+          int i1 = -1; real bd = -1;
+          for (int i = 0; i < np; i++) { real t[3]; sub3(t, A[i], A[i0]); real d2 = dot3(t, t); if (i != i0 && d2 > bd) { bd = d2; i1 = i; } }
+          if (i1 >= 0 && bd > R_(1e-12)) {
+            sel[ns++] = i1;
+            real e01[3]; sub3(e01, A[i1], A[i0]);
+            int i2 = -1, i3 = -1; real mx = R_(1e-12), mnv = R_(-1e-12);
+            for (int i = 0; i < np; i++) {
+              if (i == i0 || i == i1) continue;
+              real t[3], c[3]; sub3(t, A[i], A[i0]); cross3(c, e01, t);
+              real sa = dot3(c, nref);
+              if (sa > mx) { mx = sa; i2 = i; }
+              if (sa < mnv) { mnv = sa; i3 = i; }
+            }
+            if (i2 >= 0) sel[ns++] = i2;
+            if (i3 >= 0) sel[ns++] = i3;
+          }
+        }
+        if (ref_is_1) copy3(out.normal, nref); else scl3(out.normal, nref, -1);
+        for (int k = 0; k < ns; k++) {
+          copy3(out.pos[k], A[sel[k]]);
+          addscl3(out.pos[k], nref, R_(-0.5) * dist[sel[k]]);
+          out.dist[k] = dist[sel[k]];
+        }
+        out.n = ns;
+        return;
+      }
+    }
+  }
+  out.n = 1;
+  copy3(out.normal, n);
+  copy3(out.pos[0], pos);
+  out.dist[0] = -depth;
+}
+
+MGS_DEV void make_frame(real *frame) {
+  real *x = frame, *y = frame + 3, *z = frame + 6;
+  if (fabs(x[1]) < R_(0.5)) { y[0] = 0; y[1] = 1; y[2] = 0; } else { y[0] = 0; y[1] = 0; y[2] = 1; }
+  real d = dot3(x, y);
+  addscl3(y, x, -d);
+  normalize3(y);
+  cross3(z, x, y);
+}
+
+MGS_DEVN void collision_w(const DevModel &m, Env &e) {
+  int base = 0;
+  for (int p0 = 0; p0 < m.npair; p0 += LANES) {
+    int p = p0 + MGS_LANE;
+    PairContacts pc;
+    pc.n = 0;
+    if (p < m.npair) collide_pair(m, e, p, pc);
+    int total, off = wscan_excl(pc.n, &total);
+    for (int k = 0; k < pc.n; k++) {
+      int c = base + off + k;
+      if (c >= e.ncon_max) break;
+      copy3(e.con_pos + 3 * c, pc.pos[k]);
+      copy3(e.con_frame + 9 * c, pc.normal);
+      make_frame(e.con_frame + 9 * c);
+      e.con_dist[c] = pc.dist[k];
+      IARR(e.con_pair)[c] = p;
+    }
+    base += total;
+  }
+  if (base > e.ncon_max) { e.overflow += base - e.ncon_max; base = e.ncon_max; }
+  e.ncon = base;
+  WSYNC();
+}
+
+// gripper <-> object contact test (reference check_contact_with_object,
+// gravityless_object_grasping.py:309-321): a contact whose geom ids straddle the ground geom's id
+MGS_DEV int contact_with_object_w(const DevModel &m, const Env &e) {
+  int hit = 0, g = m.ground_geomid;
+  PFOR(c, e.ncon) {
+    int p = IARR(e.con_pair)[c];
+    int a = LDG(m.cgeom_geomid + LDG(m.pair_geom1 + p)), b = LDG(m.cgeom_geomid + LDG(m.pair_geom2 + p));
+    if ((a < g && b > g) || (a > g && b < g)) hit = 1;
+  }
+  return wany(hit);
+}

@@ -1,0 +1,141 @@
+// mgs_common.cuh - types shared by the sm_100a kernels and the C-ABI glue.
+//
+// Execution model: ONE ENVIRONMENT PER WARP.  All per-environment state lives in that warp's
+// slice of dynamic shared memory for the whole rollout (thousands of steps); HBM is touched only
+// for the read-only model constants (L1/L2 resident, shared by every warp) and for the
+// candidate inputs / labels at the two ends of the rollout.
+//
+// The device code is written against a tiny "lane" abstraction (PFOR / warp reductions).  With
+// -DMGS_HOST the same source builds as a 1-lane scalar program; that build exists ONLY so the
+// CPU-only test tier can check the kernel's arithmetic against the fp64 oracle before GPU time is
+// spent.  It is compiled into tests/hostsim/, never into the product library, which has no CPU
+// path at all.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef MGS_REAL_DOUBLE
+typedef double real;
+#define R_(x) x
+#define REAL_EPS 2.2e-16
+#else
+typedef float real;
+#define R_(x) x##f
+#define REAL_EPS 1.2e-7f
+#endif
+#define MGS_MINVAL R_(1e-15)
+
+#ifdef MGS_HOST
+#define MGS_DEV static inline
+#define MGS_DEVN static
+#define LANES 1
+#define MGS_LANE 0
+#define WSYNC() ((void)0)
+#define LDG(p) (*(p))
+#else
+#include <cuda_runtime.h>
+#define MGS_DEV __device__ __forceinline__
+#define MGS_DEVN __device__ __noinline__
+#define LANES 32
+#define MGS_LANE ((int)(threadIdx.x & 31))
+#define WSYNC() __syncwarp()
+#define LDG(p) __ldg(p)
+#endif
+
+// lane-strided loop: on the GPU lane L handles i = L, L+32, ...; on the host build one lane does all
+#define PFOR(i, n) for (int i = MGS_LANE; i < (n); i += LANES)
+
+enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
+enum { GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_CYLINDER = 5, GEOM_BOX = 6, GEOM_MESH = 7 };
+enum { EQ_CONNECT = 0, EQ_WELD = 1, EQ_JOINT = 2 };
+enum { CT_EQUALITY = 0, CT_FRICTION_DOF = 1, CT_LIMIT = 2, CT_CONTACT = 3 };
+enum { ST_SATISFIED = 0, ST_QUADRATIC = 1, ST_LINEARNEG = 2, ST_LINEARPOS = 3, ST_CONE = 4 };
+enum { MGS_MODE_STEP = 0, MGS_MODE_COLLISION = 1, MGS_MODE_STABILITY = 2 };
+
+// Model constants on the device (all pointers into one read-only blob).
+struct DevModel {
+  int nq, nv, nu, nbody, njnt, neq, nmocap, ntendon, nwrap, ncgeom, npair, nhull;
+  int maxdepth, ne_rows, cone_elliptic, iterations, ls_iterations, noslip_iterations, mpr_iterations, ground_geomid;
+  real timestep, impratio, tolerance, ls_tolerance, noslip_tolerance, mpr_tolerance, meaninertia, gravity[3];
+  const int *body_parentid, *body_rootid, *body_mocapid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_depth;
+  const real *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0, *body_subtreemass;
+  const int *jnt_type, *jnt_bodyid, *jnt_qposadr, *jnt_dofadr, *jnt_limited;
+  const real *jnt_pos, *jnt_axis, *jnt_range, *jnt_stiffness, *jnt_solref, *jnt_solimp, *jnt_margin, *qpos0, *qpos_spring;
+  const int *dof_bodyid, *dof_jntid, *dof_parentid;
+  const real *dof_armature, *dof_damping, *dof_frictionloss, *dof_solref, *dof_solimp, *dof_invweight0;
+  const int *cgeom_geomid, *cgeom_type, *cgeom_bodyid, *cgeom_hullid;
+  const real *cgeom_pos, *cgeom_quat, *cgeom_size, *cgeom_rbound;
+  const int *hull_vertadr, *hull_vertnum, *hull_faceadr, *hull_facenum, *hull_facevertadr, *hull_facevertnum, *hull_facevert;
+  const int *hull_nbradr, *hull_nbrnum, *hull_nbr;
+  const real *hull_vert, *hull_facenormal;
+  const int *pair_geom1, *pair_geom2, *pair_condim;
+  const real *pair_friction, *pair_solref, *pair_solimp, *pair_margin;
+  const int *tendon_adr, *tendon_num, *wrap_dofadr, *wrap_qposadr;
+  const real *wrap_coef;
+  const int *actuator_trntype, *actuator_trnid, *actuator_ctrllimited, *actuator_forcelimited;
+  const real *actuator_gainprm, *actuator_biasprm, *actuator_ctrlrange, *actuator_forcerange, *actuator_gear;
+  const int *eq_type, *eq_obj1id, *eq_obj2id, *eq_active, *eq_rowadr;
+  const real *eq_data, *eq_solref, *eq_solimp;
+  const real *mocap_pos0, *mocap_quat0;
+};
+
+// Per-environment scratch layout (offsets in `real` units into the warp's shared-memory slice).
+#define MGS_LAYOUT_FIELDS(X)                                                                                       \
+  X(qpos, nq) X(qvel, nv) X(qacc_ws, nv) X(ctrl, nu) X(mocap, 7 * nmocap)                                          \
+  X(xpos, 3 * nbody) X(xquat, 4 * nbody) X(xmat, 9 * nbody) X(xipos, 3 * nbody) X(ximat, 9 * nbody)                \
+  X(xanchor, 3 * njnt) X(xaxis, 3 * njnt) X(gxpos, 3 * ncgeom) X(gxmat, 9 * ncgeom) X(rootcom, 3 * nbody)          \
+  X(cinert, 10 * nbody) X(crb, 10 * nbody) X(cdof, 6 * nv) X(cdof_dot, 6 * nv) X(cvel, 6 * nbody)                  \
+  X(cacc, 6 * nbody) X(cfrc, 6 * nbody) X(M, nv * nv) X(Minv, nv * nv) X(H, nv * nv)                               \
+  X(ten_length, ntendon) X(ten_J, ntendon * nv) X(act_moment, nu * nv) X(act_force, nu) X(act_length, nu)          \
+  X(qfrc_smooth, nv) X(qacc_smooth, nv) X(qacc, nv) X(qfrc_constraint, nv) X(Ma, nv) X(grad, nv) X(search, nv)     \
+  X(Mv, nv) X(wvec, nv) X(con_pos, 3 * ncon_max) X(con_frame, 9 * ncon_max) X(con_dist, ncon_max)                  \
+  X(con_mu, ncon_max) X(con_pair, ncon_max) X(con_efc, ncon_max) X(hcone, 16 * ncon_max) X(J, nefc_max * nv)       \
+  X(efc_pos, nefc_max) X(efc_D, nefc_max) X(efc_R, nefc_max) X(efc_aref, nefc_max) X(efc_floss, nefc_max)          \
+  X(efc_force, nefc_max) X(efc_jar, nefc_max) X(efc_jv, nefc_max) X(efc_imp, nefc_max) X(efc_type, nefc_max)       \
+  X(efc_id, nefc_max) X(efc_state, nefc_max) X(nsB, 3 * nv) X(nsS, 32)
+
+struct Layout {
+#define X(name, cnt) int name;
+  MGS_LAYOUT_FIELDS(X)
+#undef X
+  int total, ncon_max, nefc_max;
+};
+
+static inline void layout_compute(Layout *L, int nq, int nv, int nu, int nbody, int njnt, int nmocap, int ntendon, int ncgeom,
+                                  int ncon_max, int nefc_max) {
+  int off = 0;
+#define X(name, cnt) L->name = off; off += ((cnt) + 3) & ~3;
+  MGS_LAYOUT_FIELDS(X)
+#undef X
+  L->total = off;
+  L->ncon_max = ncon_max;
+  L->nefc_max = nefc_max;
+}
+
+// Rollout parameters (reference: gravityless_object_grasping.py:127-137 defaults and the
+// per-gripper close_gripper_at control vectors).
+#define MGS_MAX_NU 24
+#define MGS_MAX_NJ 24
+struct RolloutParams {
+  int mode, n, nj, base_qposadr, nstep, nstep_close, nstep_lift, shake_steps, repose_on_close;
+  real lift_dist, shake_dist;
+  int joint_qposadr[MGS_MAX_NJ];
+  real close_ctrl[MGS_MAX_NU];
+};
+
+// Per-call device I/O.  All arrays are env-major (one contiguous record per environment): with one
+// warp per environment that is the coalesced layout - lane k reads element k of its env's record.
+struct BatchIO {
+  const float *pose7;   // [n][7]  processed base pose (pos, quat wxyz), fp32 like SE3Pose
+  const float *joints;  // [n][nj]
+  uint8_t *labels;      // [n]
+  int *steps;           // [n] env-steps executed
+  // generic state in/out (MGS_MODE_STEP and diagnostics): [n][state_stride]
+  // record = qpos(nq) qvel(nv) qacc_ws(nv) ctrl(nu) mocap(7*nmocap)
+  const real *state_in;
+  real *state_out;
+  real *diag_out;  // optional [n][diag_stride]: ncon, nefc, niter, then contacts/qacc (tests)
+  int state_stride, diag_stride;
+  unsigned int *work_counter;
+};

@@ -1,0 +1,109 @@
+// mgs_model_build.h - host side: MgsModelDesc (fp64, from the MJCF compiler) -> one contiguous
+// blob of `real`/int arrays + a DevModel whose pointers index into it.  The CUDA library uploads
+// the blob once per model (it is KBs: read-only, shared by every warp, L1/L2 resident).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/mgs_model_desc.h"
+#include "mgs_common.cuh"
+
+struct ModelBlob {
+  std::vector<char> bytes;
+  DevModel dm;  // pointers hold byte OFFSETS until rebase()
+  int ncon_max, nefc_max;
+};
+
+namespace mgs_detail {
+template <typename T, typename S>
+inline const T *put(std::vector<char> &b, const S *src, size_t n) {
+  size_t off = (b.size() + 15) & ~size_t(15);
+  b.resize(off + (n ? n : 1) * sizeof(T));
+  T *dst = reinterpret_cast<T *>(b.data() + off);
+  for (size_t i = 0; i < n; i++) dst[i] = (T)src[i];
+  return reinterpret_cast<const T *>(off);
+}
+}  // namespace mgs_detail
+
+inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string &err) {
+  using mgs_detail::put;
+  DevModel &m = out.dm;
+  std::vector<char> &b = out.bytes;
+  b.clear();
+  b.resize(16);
+  memset(&m, 0, sizeof(m));
+  if (d->nu > MGS_MAX_NU) { err = "too many actuators"; return false; }
+  if (d->nmocap > 1) { err = "at most one mocap body is supported"; return false; }
+  for (int p = 0; p < d->npair; p++)
+    if (d->pair_condim[p] != 1 && d->pair_condim[p] != 3 && d->pair_condim[p] != 4) { err = "condim must be 1, 3 or 4"; return false; }
+  for (int g = 0; g < d->ncgeom; g++) {
+    int t = d->cgeom_type[g];
+    if (t != GEOM_SPHERE && t != GEOM_CAPSULE && t != GEOM_CYLINDER && t != GEOM_BOX && t != GEOM_MESH) { err = "unsupported geom type"; return false; }
+  }
+  m.nq = d->nq; m.nv = d->nv; m.nu = d->nu; m.nbody = d->nbody; m.njnt = d->njnt; m.neq = d->neq; m.nmocap = d->nmocap;
+  m.ntendon = d->ntendon; m.nwrap = d->nwrap; m.ncgeom = d->ncgeom; m.npair = d->npair; m.nhull = d->nhull;
+  m.cone_elliptic = d->cone_elliptic; m.iterations = d->iterations; m.ls_iterations = d->ls_iterations;
+  m.noslip_iterations = d->noslip_iterations; m.mpr_iterations = d->mpr_iterations; m.ground_geomid = d->ground_geomid;
+  m.timestep = (real)d->timestep; m.impratio = (real)d->impratio; m.tolerance = (real)d->tolerance; m.ls_tolerance = (real)d->ls_tolerance;
+  m.noslip_tolerance = (real)d->noslip_tolerance; m.mpr_tolerance = (real)d->mpr_tolerance; m.meaninertia = (real)d->meaninertia;
+  for (int k = 0; k < 3; k++) m.gravity[k] = (real)d->gravity[k];
+  const int nb = d->nbody, nv = d->nv, nq = d->nq, nj = d->njnt, nu = d->nu, ng = d->ncgeom, np = d->npair, nh = d->nhull;
+  // derived: tree depth, subtree mass, static equality row addresses
+  std::vector<int> depth(nb, 0), rowadr(d->neq, 0);
+  std::vector<double> stm(nb, 0.0);
+  int maxdepth = 0;
+  for (int i = 1; i < nb; i++) { depth[i] = depth[d->body_parentid[i]] + 1; if (depth[i] > maxdepth) maxdepth = depth[i]; }
+  for (int i = 0; i < nb; i++) stm[i] = d->body_mass[i];
+  for (int i = nb - 1; i > 0; i--) stm[d->body_parentid[i]] += stm[i];
+  int ne = 0;
+  for (int q = 0; q < d->neq; q++) {
+    rowadr[q] = ne;
+    if (d->eq_active[q]) ne += d->eq_type[q] == EQ_WELD ? 6 : (d->eq_type[q] == EQ_CONNECT ? 3 : 1);
+  }
+  m.maxdepth = maxdepth; m.ne_rows = ne;
+#define PI_(f, n) m.f = put<int>(b, d->f, (size_t)(n))
+#define PR_(f, n) m.f = put<real>(b, d->f, (size_t)(n))
+  PI_(body_parentid, nb); PI_(body_rootid, nb); PI_(body_mocapid, nb); PI_(body_jntadr, nb); PI_(body_jntnum, nb); PI_(body_dofadr, nb);
+  PI_(body_dofnum, nb);
+  m.body_depth = put<int>(b, depth.data(), nb);
+  PR_(body_pos, 3 * nb); PR_(body_quat, 4 * nb); PR_(body_ipos, 3 * nb); PR_(body_iquat, 4 * nb); PR_(body_mass, nb); PR_(body_inertia, 3 * nb);
+  PR_(body_invweight0, 2 * nb);
+  m.body_subtreemass = put<real>(b, stm.data(), nb);
+  PI_(jnt_type, nj); PI_(jnt_bodyid, nj); PI_(jnt_qposadr, nj); PI_(jnt_dofadr, nj); PI_(jnt_limited, nj);
+  PR_(jnt_pos, 3 * nj); PR_(jnt_axis, 3 * nj); PR_(jnt_range, 2 * nj); PR_(jnt_stiffness, nj); PR_(jnt_solref, 2 * nj); PR_(jnt_solimp, 5 * nj);
+  PR_(jnt_margin, nj); PR_(qpos0, nq); PR_(qpos_spring, nq);
+  PI_(dof_bodyid, nv); PI_(dof_jntid, nv); PI_(dof_parentid, nv);
+  PR_(dof_armature, nv); PR_(dof_damping, nv); PR_(dof_frictionloss, nv); PR_(dof_solref, 2 * nv); PR_(dof_solimp, 5 * nv); PR_(dof_invweight0, nv);
+  PI_(cgeom_geomid, ng); PI_(cgeom_type, ng); PI_(cgeom_bodyid, ng); PI_(cgeom_hullid, ng);
+  PR_(cgeom_pos, 3 * ng); PR_(cgeom_quat, 4 * ng); PR_(cgeom_size, 3 * ng); PR_(cgeom_rbound, ng);
+  PI_(hull_vertadr, nh); PI_(hull_vertnum, nh); PI_(hull_faceadr, nh); PI_(hull_facenum, nh); PI_(hull_facevertadr, d->nhullface);
+  PI_(hull_facevertnum, d->nhullface); PI_(hull_facevert, d->nhullfacevert); PI_(hull_nbradr, d->nhullvert); PI_(hull_nbrnum, d->nhullvert);
+  PI_(hull_nbr, d->nhullnbr); PR_(hull_vert, 3 * d->nhullvert); PR_(hull_facenormal, 3 * d->nhullface);
+  PI_(pair_geom1, np); PI_(pair_geom2, np); PI_(pair_condim, np); PR_(pair_friction, 5 * np); PR_(pair_solref, 2 * np); PR_(pair_solimp, 5 * np);
+  PR_(pair_margin, np);
+  PI_(tendon_adr, d->ntendon); PI_(tendon_num, d->ntendon); PI_(wrap_dofadr, d->nwrap); PI_(wrap_qposadr, d->nwrap); PR_(wrap_coef, d->nwrap);
+  PI_(actuator_trntype, nu); PI_(actuator_trnid, nu); PI_(actuator_ctrllimited, nu); PI_(actuator_forcelimited, nu);
+  PR_(actuator_gainprm, 3 * nu); PR_(actuator_biasprm, 3 * nu); PR_(actuator_ctrlrange, 2 * nu); PR_(actuator_forcerange, 2 * nu); PR_(actuator_gear, nu);
+  PI_(eq_type, d->neq); PI_(eq_obj1id, d->neq); PI_(eq_obj2id, d->neq); PI_(eq_active, d->neq);
+  m.eq_rowadr = put<int>(b, rowadr.data(), d->neq);
+  PR_(eq_data, 11 * d->neq); PR_(eq_solref, 2 * d->neq); PR_(eq_solimp, 5 * d->neq);
+  PR_(mocap_pos0, 3 * d->nmocap); PR_(mocap_quat0, 4 * d->nmocap);
+#undef PI_
+#undef PR_
+  // scratch capacities: static rows + limits + a contact budget
+  int nfr = 0, nlim = 0;
+  for (int i = 0; i < nv; i++) nfr += d->dof_frictionloss[i] > 0;
+  for (int j = 0; j < nj; j++) nlim += d->jnt_limited[j] ? 1 : 0;
+  int maxdim = 1;
+  for (int p = 0; p < np; p++) if (d->pair_condim[p] > maxdim) maxdim = d->pair_condim[p];
+  out.ncon_max = 40;
+  out.nefc_max = ne + nfr + nlim + out.ncon_max * maxdim;
+  return true;
+}
+
+// turn offsets into pointers relative to `base`
+inline void rebase_model(DevModel &m, const char *base) {
+  const char **p = reinterpret_cast<const char **>(&m.body_parentid);
+  const char **end = reinterpret_cast<const char **>(&m.mocap_quat0) + 1;
+  for (; p != end; ++p) *p = base + reinterpret_cast<size_t>(*p);
+}

@@ -1,0 +1,488 @@
+// mgs_sim.cuh - warp-per-environment rigid-body step (sm_100a device code).
+//
+// Replaces, for the batched rollout, what the reference gets from mujoco.mj_step / mj_forward
+// (/root/reference/mgs/gripper/panda.py:241, /root/reference/mgs/env/gravityless_object_grasping.py
+// :159-165,214,244,258,273).  Stage list per step:
+//   kinematics -> CoM frames/CRBA mass matrix -> M^-1 -> broadphase+narrowphase (MPR + face
+//   clipping, lane per geom pair) -> constraint rows (weld/connect/joint equality, dof friction,
+//   limits, elliptic contacts) -> smooth forces (RNE bias, passive, actuators) -> primal Newton with
+//   exact line search (warp-cooperative dense Cholesky in shared memory) -> noslip -> implicitfast.
+// Lanes split the work inside one environment (dofs, bodies of one tree level, constraint rows,
+// geom pairs); warp shuffles do the reductions.  No global-memory traffic for state inside a step.
+#pragma once
+#include "mgs_common.cuh"
+
+// ---------------------------------------------------------------------------------- warp helpers
+#ifdef MGS_HOST
+MGS_DEV real wsum(real x) { return x; }
+MGS_DEV int wsumi(int x) { return x; }
+MGS_DEV int wany(int p) { return p; }
+MGS_DEV int wscan_excl(int x, int *total) { *total = x; return 0; }
+#else
+MGS_DEV real wsum(real x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+MGS_DEV int wsumi(int x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+MGS_DEV int wany(int p) { return __any_sync(0xffffffffu, p); }
+MGS_DEV int wscan_excl(int x, int *total) {
+  int lane = MGS_LANE, v = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  *total = __shfl_sync(0xffffffffu, v, 31);
+  return v - x;
+}
+#endif
+
+// ---------------------------------------------------------------------------------- small math
+MGS_DEV real rsqrt_(real x) { return R_(1.0) / sqrt(x); }
+MGS_DEV real dot3(const real *a, const real *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+MGS_DEV void cross3(real *r, const real *a, const real *b) {
+  real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+MGS_DEV void copy3(real *r, const real *a) { r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; }
+MGS_DEV void add3(real *r, const real *a, const real *b) { r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; }
+MGS_DEV void sub3(real *r, const real *a, const real *b) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+MGS_DEV void scl3(real *r, const real *a, real s) { r[0] = a[0] * s; r[1] = a[1] * s; r[2] = a[2] * s; }
+MGS_DEV void addscl3(real *r, const real *a, real s) { r[0] += a[0] * s; r[1] += a[1] * s; r[2] += a[2] * s; }
+MGS_DEV real normalize3(real *a) {
+  real n = sqrt(dot3(a, a));
+  if (n < MGS_MINVAL) { a[0] = 1; a[1] = 0; a[2] = 0; return 0; }
+  real i = R_(1.0) / n;
+  a[0] *= i; a[1] *= i; a[2] *= i;
+  return n;
+}
+MGS_DEV void mulquat(real *r, const real *a, const real *b) {
+  real w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  real x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  real y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  real z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+MGS_DEV void normquat(real *q) {
+  real n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < MGS_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  real i = R_(1.0) / n;
+  q[0] *= i; q[1] *= i; q[2] *= i; q[3] *= i;
+}
+MGS_DEV void quat2mat(real *R, const real *q) {
+  real w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = w * w + x * x - y * y - z * z; R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
+}
+MGS_DEV void mulmatvec3(real *r, const real *R, const real *v) {
+  real x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2], y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2],
+       z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+MGS_DEV void mulmatTvec3(real *r, const real *R, const real *v) {
+  real x = R[0] * v[0] + R[3] * v[1] + R[6] * v[2], y = R[1] * v[0] + R[4] * v[1] + R[7] * v[2],
+       z = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+MGS_DEV void ld3(real *r, const real *g) { r[0] = LDG(g); r[1] = LDG(g + 1); r[2] = LDG(g + 2); }
+MGS_DEV void ld4(real *r, const real *g) { r[0] = LDG(g); r[1] = LDG(g + 1); r[2] = LDG(g + 2); r[3] = LDG(g + 3); }
+
+// ---------------------------------------------------------------------------------- environment
+struct Env {
+#define X(name, cnt) real *name;
+  MGS_LAYOUT_FIELDS(X)
+#undef X
+  int ncon, nefc, ne, nf, nl, niter, bad, ncon_max, nefc_max, overflow;
+};
+MGS_DEV void env_bind(Env &e, real *base, const Layout &L) {
+#define X(name, cnt) e.name = base + L.name;
+  MGS_LAYOUT_FIELDS(X)
+#undef X
+  e.ncon = e.nefc = e.ne = e.nf = e.nl = e.niter = e.bad = e.overflow = 0;
+  e.ncon_max = L.ncon_max;
+  e.nefc_max = L.nefc_max;
+}
+#define IARR(p) ((int *)(p))
+
+// ---------------------------------------------------------------------------------- dense linear algebra (warp)
+// In-place lower Cholesky of the n x n matrix A (row-major, only the lower triangle is read).
+MGS_DEVN void chol_factor_w(real *A, int n) {
+  for (int j = 0; j < n; j++) {
+    WSYNC();
+    real d = A[j * n + j];
+    d = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL);
+    real inv = R_(1.0) / d;
+    WSYNC();
+    PFOR(i, n) {
+      if (i == j) A[j * n + j] = d;
+      else if (i > j) A[i * n + j] *= inv;
+    }
+    WSYNC();
+    PFOR(i, n) {
+      if (i > j) {
+        real lij = A[i * n + j];
+        for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+      }
+    }
+  }
+  WSYNC();
+}
+// x <- (L L')^-1 x, warp-cooperative (column oriented substitution)
+MGS_DEVN void chol_solve_w(const real *L, real *x, int n) {
+  for (int k = 0; k < n; k++) {
+    WSYNC();
+    real xk = x[k] / L[k * n + k];
+    WSYNC();
+    PFOR(i, n) {
+      if (i == k) x[k] = xk;
+      else if (i > k) x[i] -= L[i * n + k] * xk;
+    }
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    WSYNC();
+    real xk = x[k] / L[k * n + k];
+    WSYNC();
+    PFOR(i, n) {
+      if (i == k) x[k] = xk;
+      else if (i < k) x[i] -= L[k * n + i] * xk;
+    }
+  }
+  WSYNC();
+}
+// Ainv <- (L L')^-1, one column per lane (serial substitution inside the lane)
+MGS_DEVN void chol_inverse_w(const real *L, real *Ainv, int n) {
+  PFOR(c, n) {
+    for (int i = 0; i < n; i++) {
+      real s = (i == c) ? R_(1.0) : R_(0.0);
+      for (int k = 0; k < i; k++) s -= L[i * n + k] * Ainv[k * n + c];
+      Ainv[i * n + c] = s / L[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+      real s = Ainv[i * n + c];
+      for (int k = i + 1; k < n; k++) s -= L[k * n + i] * Ainv[k * n + c];
+      Ainv[i * n + c] = s / L[i * n + i];
+    }
+  }
+  WSYNC();
+}
+// y <- A x for a dense n x n A (lane per row)
+MGS_DEV void matvec_w(real *y, const real *A, const real *x, int n) {
+  PFOR(i, n) {
+    real t = 0;
+    for (int j = 0; j < n; j++) t += A[i * n + j] * x[j];
+    y[i] = t;
+  }
+  WSYNC();
+}
+
+// ---------------------------------------------------------------------------------- kinematics
+MGS_DEVN void kinematics_w(const DevModel &m, Env &e) {
+  PFOR(i, 1) {
+    e.xpos[0] = e.xpos[1] = e.xpos[2] = 0;
+    e.xquat[0] = 1; e.xquat[1] = e.xquat[2] = e.xquat[3] = 0;
+    for (int k = 0; k < 9; k++) e.xmat[k] = e.ximat[k] = (k % 4 == 0) ? R_(1.0) : R_(0.0);
+    e.xipos[0] = e.xipos[1] = e.xipos[2] = 0;
+  }
+  WSYNC();
+  for (int lvl = 1; lvl <= m.maxdepth; lvl++) {
+    PFOR(b, m.nbody) {
+      if (LDG(m.body_depth + b) != lvl) continue;
+      int p = LDG(m.body_parentid + b);
+      real xp[3], xq[4], t[3], bq[4];
+      int mid = LDG(m.body_mocapid + b);
+      if (mid >= 0) {
+        copy3(xp, e.mocap + 7 * mid);
+        xq[0] = e.mocap[7 * mid + 3]; xq[1] = e.mocap[7 * mid + 4]; xq[2] = e.mocap[7 * mid + 5]; xq[3] = e.mocap[7 * mid + 6];
+        normquat(xq);
+      } else {
+        ld3(t, m.body_pos + 3 * b);
+        mulmatvec3(xp, e.xmat + 9 * p, t);
+        add3(xp, xp, e.xpos + 3 * p);
+        ld4(bq, m.body_quat + 4 * b);
+        mulquat(xq, e.xquat + 4 * p, bq);
+      }
+      int ja = LDG(m.body_jntadr + b), jn = LDG(m.body_jntnum + b);
+      for (int j = ja; j < ja + jn; j++) {
+        int qa = LDG(m.jnt_qposadr + j), jt = LDG(m.jnt_type + j);
+        real *anchor = e.xanchor + 3 * j, *axis = e.xaxis + 3 * j;
+        if (jt == JNT_FREE) {
+          copy3(xp, e.qpos + qa);
+          normquat(e.qpos + qa + 3);
+          xq[0] = e.qpos[qa + 3]; xq[1] = e.qpos[qa + 4]; xq[2] = e.qpos[qa + 5]; xq[3] = e.qpos[qa + 6];
+          copy3(anchor, xp);
+          axis[0] = 0; axis[1] = 0; axis[2] = 1;
+          continue;
+        }
+        real Rm[9], ja3[3], jp3[3];
+        quat2mat(Rm, xq);
+        ld3(ja3, m.jnt_axis + 3 * j); ld3(jp3, m.jnt_pos + 3 * j);
+        mulmatvec3(axis, Rm, ja3);
+        mulmatvec3(anchor, Rm, jp3);
+        add3(anchor, anchor, xp);
+        real dq = e.qpos[qa] - LDG(m.qpos0 + qa);
+        if (jt == JNT_SLIDE) {
+          addscl3(xp, axis, dq);
+        } else {
+          real sn = sin(R_(0.5) * dq), cs = cos(R_(0.5) * dq);
+          real ql[4] = {cs, sn * ja3[0], sn * ja3[1], sn * ja3[2]};
+          mulquat(xq, xq, ql);
+          quat2mat(Rm, xq);
+          mulmatvec3(t, Rm, jp3);
+          sub3(xp, anchor, t);
+        }
+      }
+      normquat(xq);
+      copy3(e.xpos + 3 * b, xp);
+      e.xquat[4 * b] = xq[0]; e.xquat[4 * b + 1] = xq[1]; e.xquat[4 * b + 2] = xq[2]; e.xquat[4 * b + 3] = xq[3];
+      quat2mat(e.xmat + 9 * b, xq);
+      ld3(t, m.body_ipos + 3 * b);
+      mulmatvec3(t, e.xmat + 9 * b, t);
+      add3(e.xipos + 3 * b, xp, t);
+      ld4(bq, m.body_iquat + 4 * b);
+      real qi[4];
+      mulquat(qi, xq, bq);
+      quat2mat(e.ximat + 9 * b, qi);
+    }
+    WSYNC();
+  }
+  PFOR(g, m.ncgeom) {
+    int b = LDG(m.cgeom_bodyid + g);
+    real t[3], q[4], gq[4];
+    ld3(t, m.cgeom_pos + 3 * g);
+    mulmatvec3(t, e.xmat + 9 * b, t);
+    add3(e.gxpos + 3 * g, e.xpos + 3 * b, t);
+    ld4(gq, m.cgeom_quat + 4 * g);
+    mulquat(q, e.xquat + 4 * b, gq);
+    quat2mat(e.gxmat + 9 * g, q);
+  }
+  WSYNC();
+}
+
+// spatial inertia helpers (CoM-based 10-vector: Ixx Iyy Izz Ixy Ixz Iyz, m*c, m)
+MGS_DEV void mul_inert_vec(real *res, const real *I, const real *v) {
+  real t[3];
+  res[0] = I[0] * v[0] + I[3] * v[1] + I[4] * v[2];
+  res[1] = I[3] * v[0] + I[1] * v[1] + I[5] * v[2];
+  res[2] = I[4] * v[0] + I[5] * v[1] + I[2] * v[2];
+  cross3(t, I + 6, v + 3);
+  add3(res, res, t);
+  cross3(t, I + 6, v);
+  res[3] = I[9] * v[3] - t[0]; res[4] = I[9] * v[4] - t[1]; res[5] = I[9] * v[5] - t[2];
+}
+MGS_DEV void cross_motion(real *res, const real *vel, const real *v) {
+  real t[3];
+  cross3(res, vel, v);
+  cross3(res + 3, vel, v + 3);
+  cross3(t, vel + 3, v);
+  add3(res + 3, res + 3, t);
+}
+MGS_DEV void cross_force(real *res, const real *vel, const real *f) {
+  real t[3];
+  cross3(res, vel, f);
+  cross3(t, vel + 3, f + 3);
+  add3(res, res, t);
+  cross3(res + 3, vel, f + 3);
+}
+
+// CoM frames, composite inertias, motion axes, mass matrix, M^-1
+MGS_DEVN void inertia_w(const DevModel &m, Env &e) {
+  const int nb = m.nbody, nv = m.nv;
+  // centre of mass of every kinematic tree (origin of its spatial quantities)
+  PFOR(b, nb) {
+    if (b == 0 || LDG(m.body_parentid + b) != 0) continue;
+    real c[3] = {0, 0, 0}, mt = LDG(m.body_subtreemass + b);
+    if (mt < MGS_MINVAL) copy3(c, e.xipos + 3 * b);
+    else {
+      for (int k = b; k < nb; k++)
+        if (LDG(m.body_rootid + k) == b) addscl3(c, e.xipos + 3 * k, LDG(m.body_mass + k));
+      scl3(c, c, R_(1.0) / mt);
+    }
+    copy3(e.rootcom + 3 * b, c);
+  }
+  WSYNC();
+  PFOR(b, nb) {
+    real *ci = e.cinert + 10 * b;
+    if (b == 0) { for (int k = 0; k < 10; k++) ci[k] = 0; continue; }
+    real dif[3], diag[3], mass = LDG(m.body_mass + b);
+    const real *Rm = e.ximat + 9 * b;
+    sub3(dif, e.xipos + 3 * b, e.rootcom + 3 * LDG(m.body_rootid + b));
+    ld3(diag, m.body_inertia + 3 * b);
+    real I[6];  // xx yy zz xy xz yz
+    I[0] = Rm[0] * diag[0] * Rm[0] + Rm[1] * diag[1] * Rm[1] + Rm[2] * diag[2] * Rm[2];
+    I[1] = Rm[3] * diag[0] * Rm[3] + Rm[4] * diag[1] * Rm[4] + Rm[5] * diag[2] * Rm[5];
+    I[2] = Rm[6] * diag[0] * Rm[6] + Rm[7] * diag[1] * Rm[7] + Rm[8] * diag[2] * Rm[8];
+    I[3] = Rm[0] * diag[0] * Rm[3] + Rm[1] * diag[1] * Rm[4] + Rm[2] * diag[2] * Rm[5];
+    I[4] = Rm[0] * diag[0] * Rm[6] + Rm[1] * diag[1] * Rm[7] + Rm[2] * diag[2] * Rm[8];
+    I[5] = Rm[3] * diag[0] * Rm[6] + Rm[4] * diag[1] * Rm[7] + Rm[5] * diag[2] * Rm[8];
+    real d2 = dot3(dif, dif);
+    ci[0] = I[0] + mass * (d2 - dif[0] * dif[0]);
+    ci[1] = I[1] + mass * (d2 - dif[1] * dif[1]);
+    ci[2] = I[2] + mass * (d2 - dif[2] * dif[2]);
+    ci[3] = I[3] - mass * dif[0] * dif[1];
+    ci[4] = I[4] - mass * dif[0] * dif[2];
+    ci[5] = I[5] - mass * dif[1] * dif[2];
+    ci[6] = mass * dif[0]; ci[7] = mass * dif[1]; ci[8] = mass * dif[2]; ci[9] = mass;
+    for (int k = 0; k < 10; k++) e.crb[10 * b + k] = ci[k];
+  }
+  PFOR(j, m.njnt) {
+    int b = LDG(m.jnt_bodyid + j), da = LDG(m.jnt_dofadr + j), jt = LDG(m.jnt_type + j);
+    real off[3];
+    sub3(off, e.rootcom + 3 * LDG(m.body_rootid + b), e.xanchor + 3 * j);
+    if (jt == JNT_FREE) {
+      for (int k = 0; k < 36; k++) e.cdof[6 * da + k] = 0;
+      for (int k = 0; k < 3; k++) e.cdof[6 * (da + k) + 3 + k] = 1;
+      for (int k = 0; k < 3; k++) {
+        real ax[3] = {e.xmat[9 * b + k], e.xmat[9 * b + 3 + k], e.xmat[9 * b + 6 + k]};
+        real *c = e.cdof + 6 * (da + 3 + k);
+        copy3(c, ax);
+        cross3(c + 3, ax, off);
+      }
+    } else if (jt == JNT_SLIDE) {
+      real *c = e.cdof + 6 * da;
+      c[0] = c[1] = c[2] = 0;
+      copy3(c + 3, e.xaxis + 3 * j);
+    } else {
+      real *c = e.cdof + 6 * da;
+      copy3(c, e.xaxis + 3 * j);
+      cross3(c + 3, e.xaxis + 3 * j, off);
+    }
+  }
+  PFOR(i, nv * nv) e.M[i] = 0;
+  WSYNC();
+  // composite inertias: parents absorb their children, deepest level first
+  for (int lvl = m.maxdepth - 1; lvl >= 1; lvl--) {
+    PFOR(b, nb) {
+      if (LDG(m.body_depth + b) != lvl) continue;
+      for (int c = b + 1; c < nb; c++)
+        if (LDG(m.body_parentid + c) == b)
+          for (int k = 0; k < 10; k++) e.crb[10 * b + k] += e.crb[10 * c + k];
+    }
+    WSYNC();
+  }
+  PFOR(i, nv) {
+    real buf[6];
+    mul_inert_vec(buf, e.crb + 10 * LDG(m.dof_bodyid + i), e.cdof + 6 * i);
+    for (int j = i; j >= 0; j = LDG(m.dof_parentid + j)) {
+      real v = 0;
+      for (int k = 0; k < 6; k++) v += e.cdof[6 * j + k] * buf[k];
+      if (j == i) v += LDG(m.dof_armature + i);
+      e.M[i * nv + j] = v;
+      e.M[j * nv + i] = v;
+    }
+  }
+  WSYNC();
+  PFOR(i, nv * nv) e.H[i] = e.M[i];
+  chol_factor_w(e.H, nv);
+  chol_inverse_w(e.H, e.Minv, nv);
+}
+
+// fixed tendons + actuator transmission
+MGS_DEVN void transmission_w(const DevModel &m, Env &e) {
+  const int nv = m.nv;
+  PFOR(i, m.ntendon * nv) e.ten_J[i] = 0;
+  PFOR(i, m.nu * nv) e.act_moment[i] = 0;
+  WSYNC();
+  PFOR(t, m.ntendon) {
+    real L = 0;
+    int a = LDG(m.tendon_adr + t), n = LDG(m.tendon_num + t);
+    for (int w = a; w < a + n; w++) {
+      real c = LDG(m.wrap_coef + w);
+      L += c * e.qpos[LDG(m.wrap_qposadr + w)];
+      e.ten_J[t * nv + LDG(m.wrap_dofadr + w)] += c;
+    }
+    e.ten_length[t] = L;
+  }
+  WSYNC();
+  PFOR(a, m.nu) {
+    real gear = LDG(m.actuator_gear + a);
+    int id = LDG(m.actuator_trnid + a);
+    if (LDG(m.actuator_trntype + a) == 0) {
+      e.act_length[a] = gear * e.qpos[LDG(m.jnt_qposadr + id)];
+      e.act_moment[a * nv + LDG(m.jnt_dofadr + id)] = gear;
+    } else {
+      e.act_length[a] = gear * e.ten_length[id];
+      for (int d = 0; d < nv; d++) e.act_moment[a * nv + d] = gear * e.ten_J[id * nv + d];
+    }
+  }
+  WSYNC();
+}
+
+// velocities, bias (RNE without acceleration), passive and actuator forces -> qfrc_smooth, qacc_smooth
+MGS_DEVN void smooth_forces_w(const DevModel &m, Env &e) {
+  const int nb = m.nbody, nv = m.nv;
+  PFOR(k, 6) { e.cvel[k] = 0; e.cfrc[k] = 0; e.cacc[k] = (k < 3) ? R_(0.0) : -m.gravity[k - 3]; }
+  WSYNC();
+  for (int lvl = 1; lvl <= m.maxdepth; lvl++) {
+    PFOR(b, nb) {
+      if (LDG(m.body_depth + b) != lvl) continue;
+      int p = LDG(m.body_parentid + b);
+      real cv[6], ca[6];
+      for (int k = 0; k < 6; k++) { cv[k] = e.cvel[6 * p + k]; ca[k] = e.cacc[6 * p + k]; }
+      int ja = LDG(m.body_jntadr + b), jn = LDG(m.body_jntnum + b);
+      for (int j = ja; j < ja + jn; j++) {
+        int da = LDG(m.jnt_dofadr + j);
+        if (LDG(m.jnt_type + j) == JNT_FREE) {
+          for (int k = 0; k < 18; k++) e.cdof_dot[6 * da + k] = 0;
+          for (int k = 0; k < 3; k++)
+            for (int c = 0; c < 6; c++) cv[c] += e.cdof[6 * (da + k) + c] * e.qvel[da + k];
+          for (int k = 3; k < 6; k++) cross_motion(e.cdof_dot + 6 * (da + k), cv, e.cdof + 6 * (da + k));
+          for (int k = 3; k < 6; k++)
+            for (int c = 0; c < 6; c++) cv[c] += e.cdof[6 * (da + k) + c] * e.qvel[da + k];
+          for (int k = 3; k < 6; k++)
+            for (int c = 0; c < 6; c++) ca[c] += e.cdof_dot[6 * (da + k) + c] * e.qvel[da + k];
+        } else {
+          cross_motion(e.cdof_dot + 6 * da, cv, e.cdof + 6 * da);
+          for (int c = 0; c < 6; c++) { cv[c] += e.cdof[6 * da + c] * e.qvel[da]; ca[c] += e.cdof_dot[6 * da + c] * e.qvel[da]; }
+        }
+      }
+      real t1[6], t2[6];
+      mul_inert_vec(t1, e.cinert + 10 * b, cv);
+      cross_force(t2, cv, t1);
+      mul_inert_vec(t1, e.cinert + 10 * b, ca);
+      for (int k = 0; k < 6; k++) { e.cvel[6 * b + k] = cv[k]; e.cacc[6 * b + k] = ca[k]; e.cfrc[6 * b + k] = t1[k] + t2[k]; }
+    }
+    WSYNC();
+  }
+  for (int lvl = m.maxdepth - 1; lvl >= 1; lvl--) {
+    PFOR(b, nb) {
+      if (LDG(m.body_depth + b) != lvl) continue;
+      for (int c = b + 1; c < nb; c++)
+        if (LDG(m.body_parentid + c) == b)
+          for (int k = 0; k < 6; k++) e.cfrc[6 * b + k] += e.cfrc[6 * c + k];
+    }
+    WSYNC();
+  }
+  // actuator forces (lane per actuator), then per-dof totals
+  PFOR(a, m.nu) {
+    real c = e.ctrl[a], vel = 0;
+    if (LDG(m.actuator_ctrllimited + a)) c = fmax(LDG(m.actuator_ctrlrange + 2 * a), fmin(LDG(m.actuator_ctrlrange + 2 * a + 1), c));
+    for (int d = 0; d < nv; d++) vel += e.act_moment[a * nv + d] * e.qvel[d];
+    real f = LDG(m.actuator_gainprm + 3 * a) * c + LDG(m.actuator_biasprm + 3 * a) + LDG(m.actuator_biasprm + 3 * a + 1) * e.act_length[a] +
+             LDG(m.actuator_biasprm + 3 * a + 2) * vel;
+    if (LDG(m.actuator_forcelimited + a)) f = fmax(LDG(m.actuator_forcerange + 2 * a), fmin(LDG(m.actuator_forcerange + 2 * a + 1), f));
+    e.act_force[a] = f;
+  }
+  WSYNC();
+  PFOR(d, nv) {
+    real bias = 0;
+    int b = LDG(m.dof_bodyid + d);
+    for (int c = 0; c < 6; c++) bias += e.cdof[6 * d + c] * e.cfrc[6 * b + c];
+    real f = -LDG(m.dof_damping + d) * e.qvel[d] - bias;
+    int j = LDG(m.dof_jntid + d);
+    if (LDG(m.jnt_type + j) != JNT_FREE) {
+      real k = LDG(m.jnt_stiffness + j);
+      int qa = LDG(m.jnt_qposadr + j);
+      if (k != 0) f -= k * (e.qpos[qa] - LDG(m.qpos_spring + qa));
+    }
+    for (int a = 0; a < m.nu; a++) f += e.act_moment[a * nv + d] * e.act_force[a];
+    e.qfrc_smooth[d] = f;
+  }
+  WSYNC();
+  matvec_w(e.qacc_smooth, e.Minv, e.qfrc_smooth, nv);
+}

@@ -1,0 +1,188 @@
+"""Scene assembly + synthetic workloads (objects and grasp candidates) for tests and bench.py.
+
+Scene template: same options and body layout as the reference's zero-gravity grasping scene
+(`/root/reference/mgs/env/gravityless_object_grasping.py:34-54`): gripper fragment, then the
+ground body with `geom:ground`, then the object fragment - the geom-id ordering the contact
+labels rely on (`:309-321`).  Synthetic inputs follow SURVEY.md 8(d): YCB/GSO meshes are not
+available offline, so objects are a box primitive or seeded random convex hulls emitted with the
+reference's object recipe (`/root/reference/mgs/obj/ycb.py:138-158`).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+from scipy.spatial import ConvexHull
+from scipy.spatial.transform import Rotation as R
+
+from .compiler import mesh as meshlib
+from .compiler.mjcf import compile_mjcf
+
+ASSET_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+
+GRAVITYLESS_XML = """<mujoco>
+  <compiler angle="radian" autolimits="true" discardvisual="false"/>
+  <option integrator="implicitfast" timestep="0.001" cone="elliptic" impratio="3" noslip_iterations="2"
+          noslip_tolerance="1e-8" tolerance="1e-8" gravity="0 0 0"><flag multiccd="enable"/></option>
+  {gripper}
+  <worldbody>
+    <body name="body:ground" pos="0.0 0 -1.0">
+      <geom name="geom:ground" pos="0 0 0" size="1.0 1.0 0.02" type="box" density="500"/>
+    </body>
+  </worldbody>
+  {object}
+</mujoco>"""
+
+CUBE_XML = """<worldbody><body name="{name}" pos="0 0 0" quat="1 0 0 0"><freejoint name="{name}:joint"/>
+<geom name="geom:{name}" size="{size} {size} {size}" type="box" mass="1.0"/></body></worldbody>"""
+
+# gripper name -> (asset dir, base free joint, actuated joints, close ctrl, b2c pos, b2c quat wxyz, repose_on_close)
+GRIPPERS = {
+    "panda": dict(dir="panda", freejoint="freejoint", joints=["finger_joint1", "finger_joint2"], close_ctrl=[0.0, -0.04],
+                  b2c_pos=[0, 0, -0.102], b2c_quat=[0.707106781, 0.0, 0.0, 0.707106781], repose=0),
+}
+
+
+def gripper_fragment(name: str):
+    g = GRIPPERS[name]
+    d = os.path.join(ASSET_PATH, g["dir"])
+    xml = open(os.path.join(d, "template.xml")).read().format(position="0 0 0", quaternion="1 0 0 0")
+    assets = {f: open(os.path.join(d, f), "rb").read() for f in os.listdir(d) if f != "template.xml"}
+    return xml, assets
+
+
+def cube_fragment(name="cube", size=0.02):
+    return CUBE_XML.format(name=name, size=size), {}
+
+
+def random_hull_points(seed: int, n_v: int = 32):
+    """n_v points on an ellipsoid with semi-axes ~U(0.015, 0.05) m."""
+    rng = np.random.default_rng(1000 + seed)
+    ax = rng.uniform(0.015, 0.05, size=3)
+    p = rng.normal(size=(n_v, 3))
+    p /= np.linalg.norm(p, axis=1, keepdims=True)
+    mass = rng.uniform(0.05, 0.5)
+    return p * ax, mass
+
+
+def hull_object_fragment(seed: int, n_v: int = 32, name="obj"):
+    """Convex-hull object with the reference's object recipe: condim 4, friction 1/.3/.1,
+    solimp .998 .998 .001, solref .001 1, free joint damping 1e-4 (ycb.py:138-157)."""
+    pts, mass = random_hull_points(seed, n_v)
+    h = meshlib.build_hull(pts)
+    fn = f"{name}_hull_{seed}.obj"
+    xml = f"""<asset><mesh name="{name}_coll_0" file="{fn}"/></asset>
+<worldbody><body name="{name}" pos="0 0 0" quat="1 0 0 0">
+<geom mesh="{name}_coll_0" mass="{mass}" group="3" type="mesh" conaffinity="1" contype="1" condim="4"
+      friction="1.0 0.3 0.1" solimp="0.998 0.998 0.001" solref="0.001 1"/>
+<joint damping="0.0001" name="{name}:joint" type="free"/></body></worldbody>"""
+    return xml, {fn: meshlib.write_obj(h.verts, h.tri)}, (h.verts, h.tri)
+
+
+def build_scene(gripper: str, obj_xml: str, obj_assets: dict):
+    gx, ga = gripper_fragment(gripper)
+    model = compile_mjcf(GRAVITYLESS_XML.format(gripper=gx, object=obj_xml), {**ga, **obj_assets})
+    g = GRIPPERS[gripper]
+    info = dict(base_qposadr=int(model.jnt_qposadr[model.names["joint"][g["freejoint"]]]),
+                joint_qposadr=np.array([model.jnt_qposadr[model.names["joint"][j]] for j in g["joints"]], dtype=np.int32),
+                close_ctrl=np.array(g["close_ctrl"], dtype=np.float64), repose=g["repose"], gripper=gripper)
+    return model, info
+
+
+# ---- SE3Pose-compatible pose preprocessing (fp32, like the reference's SE3Pose.__matmul__) -----
+def pose_to_mat32(pos, quat_wxyz):
+    T = np.zeros((4, 4), dtype=np.float32)
+    T[:3, :3] = R.from_quat([quat_wxyz[1], quat_wxyz[2], quat_wxyz[3], quat_wxyz[0]]).as_matrix()
+    T[:3, 3] = pos
+    T[3, 3] = 1
+    return T
+
+
+def process_poses(H: np.ndarray, gripper: str) -> np.ndarray:
+    """candidate 4x4 matrices (f64 [N,4,4]) -> base pose7 float32 [N,7] = SE3Pose.from_mat(H) @ b2c.
+
+    Mirrors /root/reference/mgs/util/geo/transforms.py:78-128: from_mat -> float32 pos/quat,
+    to_mat -> float32 4x4, einsum in float32, from_mat again (scipy), cast float32."""
+    g = GRIPPERS[gripper]
+    b2c = pose_to_mat32(np.asarray(g["b2c_pos"], dtype=np.float32), np.asarray(g["b2c_quat"], dtype=np.float32))
+    H = np.asarray(H)
+    q = R.from_matrix(H[:, :3, :3]).as_quat()  # xyzw
+    q32 = q.astype(np.float32)
+    pos32 = H[:, :3, 3].astype(np.float32)
+    M = np.zeros((len(H), 4, 4), dtype=np.float32)
+    M[:, :3, :3] = R.from_quat(q32).as_matrix()
+    M[:, :3, 3] = pos32
+    M[:, 3, 3] = 1
+    P = np.einsum("nij,jk->nik", M, b2c)
+    q2 = R.from_matrix(P[:, :3, :3]).as_quat()
+    out = np.concatenate([P[:, :3, 3], q2[:, [3, 0, 1, 2]]], axis=1).astype(np.float32)
+    return out
+
+
+def panda_width_to_joints(width):
+    """gen_grasp_candidates.py:62-64 with GripperPanda._clamp_width / width_to_joints (panda.py:217-223,264-266)."""
+    w = np.clip(np.asarray(width) + 0.025, 0.003, 0.08)
+    w = np.clip(w, 0.003, 0.08)
+    return np.stack([np.clip(w / 2, 0, 0.04), np.clip(-0.04 + w / 2, -0.04, 0.0)], axis=-1)
+
+
+def antipodal_candidates(verts, tri, n: int, seed: int):
+    """Antipodal-style candidates on a convex mesh (frames as mgs/sampler/antipodal.py:181-298):
+    x = p2 - p1 normalised, z random perpendicular to x, y = z cross x, origin = midpoint."""
+    rng = np.random.default_rng(2000 + seed)
+    T = verts[tri]
+    area = 0.5 * np.linalg.norm(np.cross(T[:, 1] - T[:, 0], T[:, 2] - T[:, 0]), axis=1)
+    fn = np.cross(T[:, 1] - T[:, 0], T[:, 2] - T[:, 0])
+    fn /= np.linalg.norm(fn, axis=1, keepdims=True)
+    d0 = np.einsum("ij,ij->i", fn, T[:, 0])
+    f = rng.choice(len(tri), size=n, p=area / area.sum())
+    u, v = rng.uniform(size=n), rng.uniform(size=n)
+    flip = u + v > 1
+    u[flip], v[flip] = 1 - u[flip], 1 - v[flip]
+    p1 = T[f, 0] + u[:, None] * (T[f, 1] - T[f, 0]) + v[:, None] * (T[f, 2] - T[f, 0])
+    # inward direction: -normal perturbed (stand-in for the vMF draw, kappa=10)
+    dirs = -fn[f] + rng.normal(size=(n, 3)) * 0.3
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    # exit point of the ray p1 + t*dir through the convex body: min positive t over faces
+    denom = dirs @ fn.T  # [n, nf]
+    num = d0[None, :] - p1 @ fn.T
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.where(denom > 1e-9, num / denom, np.inf)
+    t_exit = t.min(axis=1)
+    p2 = p1 + dirs * t_exit[:, None]
+    # degenerate rays (start on an edge): the reference's fallback - a random second contact inside a
+    # 10 cm cube around the first (antipodal.py:139-144)
+    bad = ~np.isfinite(t_exit) | (t_exit < 1e-5)
+    p2[bad] = p1[bad] + rng.uniform(-0.05, 0.05, size=(int(bad.sum()), 3))
+    x = p2 - p1
+    width = np.linalg.norm(x, axis=1)
+    x /= width[:, None]
+    rv = rng.normal(size=(n, 3))
+    z = np.cross(x, rv)
+    z /= np.linalg.norm(z, axis=1, keepdims=True)
+    y = np.cross(z, x)
+    H = np.zeros((n, 4, 4))
+    H[:, :3, 0], H[:, :3, 1], H[:, :3, 2], H[:, :3, 3], H[:, 3, 3] = x, y, z, 0.5 * (p1 + p2), 1.0
+    return H, width
+
+
+def box_mesh(size):
+    h = meshlib.box_hull([size, size, size])
+    return h.verts, h.tri
+
+
+def workload(gripper: str, kind: str, seed: int, n: int, n_v: int = 32):
+    """(model, info, pose7 float32 [n,7], joints float32 [n,nj]) for one synthetic object."""
+    if kind == "cube":
+        ox, oa = cube_fragment()
+        verts, tri = box_mesh(0.02)
+    else:
+        ox, oa, (verts, tri) = hull_object_fragment(seed, n_v)
+    model, info = build_scene(gripper, ox, oa)
+    H, width = antipodal_candidates(verts, tri, n, seed)
+    pose7 = process_poses(H, gripper)
+    if gripper == "panda":
+        joints = panda_width_to_joints(width)
+    else:
+        raise NotImplementedError(gripper)
+    return model, info, pose7, joints.astype(np.float32)

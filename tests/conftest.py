@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def panda_cube():
+    from mj_grasp_sim_b200 import scenes
+    return scenes.workload("panda", "cube", 0, 64)
+
+
+@pytest.fixture(scope="session")
+def panda_hull():
+    from mj_grasp_sim_b200 import scenes
+    return scenes.workload("panda", "hull", 0, 64)

@@ -1,0 +1,70 @@
+"""The kernel source, built as a 1-lane host program (tests/hostsim), against the fp64 oracle.
+
+This is the CPU-tier differential test: identical algorithmic spec, two independent
+implementations (plain C fp64 oracle vs the warp-cooperative CUDA source).  Tolerances: fp64 build
+1e-8 abs; fp32 build 1e-4 relative on qpos/qvel over the first 50 steps (north_star)."""
+import numpy as np
+import pytest
+
+from hostsim import lane1
+from mj_grasp_sim_b200.lib import MgsRolloutCfg
+from oracle.oracle import OracleSim, RolloutCfg, batch
+
+P7 = np.array([0, 0, -0.102, 0.70710677, 0, 0, 0.70710677])
+
+
+def _start(s, info, joints):
+    s.reset()
+    s.place(P7, info["base_qposadr"], np.array(joints), info["joint_qposadr"])
+    s.ctrl[:] = info["close_ctrl"]
+
+
+@pytest.mark.parametrize("f64,tol", [(True, 1e-8), (False, 2e-4)])
+def test_forward_quantities(panda_cube, f64, tol):
+    m, info = panda_cube[0], panda_cube[1]
+    s = OracleSim(m)
+    L = lane1.sim(m, f64=f64)
+    _start(s, info, [0.0199, -0.0201])  # pads penetrate the cube: contacts present
+    st = L.pack_state(s.qpos.copy(), s.qvel.copy(), ctrl=s.ctrl.copy(), mocap_pos=s.mocap_pos[0].copy(), mocap_quat=s.mocap_quat[0].copy())
+    s.forward()
+    _, d = L.step(st, 0, want_diag=True)
+    assert d["ncon"][0] == s.ncon and d["nefc"][0] == s.nefc and s.ncon > 0
+    assert np.abs(d["M"][0] - s.M).max() < tol
+    assert np.abs(d["xpos"][0] - s.xpos).max() < tol
+    scale = max(1.0, np.abs(s.qacc).max())
+    assert np.abs(d["qacc_smooth"][0] - s.qacc_smooth).max() < tol * scale * 10
+    assert np.abs(d["qacc"][0] - s.qacc).max() < (1e-6 if f64 else 2e-2) * scale
+    con = s.contacts()
+    assert np.abs(d["contact"][0, : s.ncon, 0] - con[:, 12]).max() < max(tol * 1e-2, 1e-7)  # penetration depths
+
+
+@pytest.mark.parametrize("f64,tol", [(True, 1e-8), (False, 1e-4)])
+def test_first_50_steps(panda_cube, f64, tol):
+    m, info = panda_cube[0], panda_cube[1]
+    s = OracleSim(m)
+    L = lane1.sim(m, f64=f64)
+    _start(s, info, [0.0215, -0.0185])  # fingers reach the cube within the window
+    st = L.pack_state(s.qpos.copy(), s.qvel.copy(), ctrl=s.ctrl.copy(), mocap_pos=s.mocap_pos[0].copy(), mocap_quat=s.mocap_quat[0].copy())
+    for k in range(5):
+        s.step(10)
+        st = L.step(st, 10)
+        u = L.unpack_state(st)
+        assert np.abs(u["qpos"][0] - s.qpos).max() <= tol * max(1.0, np.abs(s.qpos).max())
+        assert np.abs(u["qvel"][0] - s.qvel).max() <= tol * max(1.0, np.abs(s.qvel).max()) * 10
+    assert s.ncon > 0
+
+
+def test_rollout_labels_short_schedule(panda_hull):
+    m, info, pose7, joints = panda_hull
+    n = 12
+    sched = (400, 200, 40, 0, 0.03, 0.02)
+    L = lane1.sim(m)
+    free = L.collision_mask(pose7[:n], joints[:n], info["joint_qposadr"], info["base_qposadr"])
+    lab, steps = L.stability(pose7[:n], joints[:n], info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], MgsRolloutCfg(*sched))
+    ofree, _ = batch(m, 0, pose7[:n].astype(np.float64), info["base_qposadr"], joints[:n].astype(np.float64), info["joint_qposadr"],
+                     info["close_ctrl"], RolloutCfg(*sched), 4)
+    olab, osteps = batch(m, 1, pose7[:n].astype(np.float64), info["base_qposadr"], joints[:n].astype(np.float64), info["joint_qposadr"],
+                         info["close_ctrl"], RolloutCfg(*sched), 4)
+    assert (free == ofree).all()
+    assert (lab == olab).mean() >= 11 / 12
+    assert np.array_equal(steps[lab == olab], osteps[lab == olab])

@@ -1,0 +1,148 @@
+"""Oracle pinned by analytic invariants (no MuJoCo available: SURVEY.md 8(c) "known answers" row 4)."""
+import numpy as np
+import pytest
+
+from mj_grasp_sim_b200.compiler.mjcf import compile_mjcf, mass_matrix
+from oracle.oracle import OracleSim
+
+FREE_BODY = """<mujoco><compiler angle="radian" autolimits="true"/>
+<option integrator="implicitfast" timestep="0.001" cone="elliptic" gravity="{g}"/>
+<worldbody><body name="b" pos="0 0 0"><freejoint name="j"/>
+<geom type="box" size="0.02 0.03 0.05" mass="0.7"/></body></worldbody></mujoco>"""
+
+WELD = """<mujoco><compiler angle="radian" autolimits="true"/>
+<option integrator="implicitfast" timestep="0.001" cone="elliptic" gravity="0 0 0"/>
+<worldbody><body name="mocap" mocap="true" pos="0 0 0"/>
+<body name="b" pos="0 0 0"><freejoint name="j"/><geom type="sphere" size="0.02" mass="0.5" contype="0" conaffinity="0"/></body>
+</worldbody><equality><weld body1="mocap" body2="b"/></equality></mujoco>"""
+
+
+def test_crba_matches_jacobian_mass_matrix(panda_cube):
+    m = panda_cube[0]
+    s = OracleSim(m)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        q = m.qpos0.copy()
+        q[0:3] = rng.normal(size=3) * 0.1
+        qq = rng.normal(size=4); q[3:7] = qq / np.linalg.norm(qq)
+        q[7], q[8] = rng.uniform(0, 0.04), rng.uniform(-0.04, 0)
+        q[9:12] = rng.normal(size=3) * 0.1
+        qq = rng.normal(size=4); q[12:16] = qq / np.linalg.norm(qq)
+        s.qpos[:] = q
+        s.kinematics()
+        M2, _ = mass_matrix(m, q)
+        assert np.abs(s.M - M2).max() < 1e-12
+
+
+def test_free_body_momentum_conserved_zero_gravity():
+    m = compile_mjcf(FREE_BODY.format(g="0 0 0"))
+    s = OracleSim(m)
+    s.reset()
+    s.qvel[:] = [0.3, -0.2, 0.1, 2.0, -1.0, 0.5]
+    s.forward()
+    from mj_grasp_sim_b200.compiler.mjcf import quat_to_mat
+
+    def ang_mom():  # world-frame angular momentum; free-joint angular velocity is body-frame
+        R = s.xmat[1].reshape(3, 3)
+        Ri = R @ quat_to_mat(m.body_iquat[1])
+        return Ri @ np.diag(m.body_inertia[1]) @ Ri.T @ (R @ np.array(s.qvel[3:6]))
+
+    L0 = ang_mom()
+    p0 = 0.7 * np.array(s.qvel[0:3])
+    s.step(2000)
+    s.forward()
+    assert np.allclose(0.7 * np.array(s.qvel[0:3]), p0, atol=1e-12)
+    assert np.allclose(ang_mom(), L0, rtol=2e-3, atol=2e-6)  # semi-implicit Euler on a tumbling box: small drift only
+    assert np.allclose(s.qpos[0:3], np.array([0.3, -0.2, 0.1]) * 2.0, atol=1e-9)
+
+
+def test_free_fall_under_gravity():
+    m = compile_mjcf(FREE_BODY.format(g="0 0 -9.81"))
+    s = OracleSim(m)
+    s.reset()
+    s.step(500)
+    t = 0.5
+    assert np.isclose(s.qvel[2], -9.81 * t, rtol=1e-9)
+    assert np.isclose(s.qpos[2], -0.5 * 9.81 * t * (t + 0.001), rtol=1e-9)  # semi-implicit Euler closed form
+
+
+def test_weld_tracks_mocap_like_critically_damped_spring():
+    """Default solref (0.02, 1): the weld pulls the body to the mocap target like a critically damped
+    spring with time constant ~0.02 s: after 0.2 s the error is < 1 %, no overshoot."""
+    m = compile_mjcf(WELD)
+    s = OracleSim(m)
+    s.reset()
+    s.mocap_pos[0] = [0.01, 0, 0]
+    xs = []
+    for _ in range(300):
+        s.step(1)
+        xs.append(s.qpos[0])
+    xs = np.array(xs)
+    assert xs.max() <= 0.01 * 1.001  # no overshoot
+    assert abs(xs[199] - 0.01) < 1e-4
+    # time to reach 1 - 2/e of the step for a critically damped 2nd-order system: t = tau_eff; tau_eff in [0.015, 0.03]
+    t63 = np.argmax(xs > 0.01 * (1 - 2 / np.e)) * 1e-3
+    assert 0.015 < t63 < 0.035
+
+
+def test_panda_closes_on_cube_and_holds(panda_cube):
+    m, info = panda_cube[0], panda_cube[1]
+    s = OracleSim(m)
+    p7 = np.array([0, 0, -0.102, 0.70710677, 0, 0, 0.70710677])
+    s.reset()
+    s.place(p7, info["base_qposadr"], np.array([0.0325, -0.0075]), info["joint_qposadr"])
+    s.ctrl[:] = info["close_ctrl"]
+    s.step(1500)
+    # fingers stop at the cube faces (half width 0.02) with a sub-millimetre penetration
+    assert 0.0195 < s.qpos[7] < 0.02 and -0.0205 < s.qpos[8] < -0.02 + 0.0005 + 1e-9
+    assert s.contact_with_object()
+    con = s.contacts()
+    assert (con[:, 12] < 0).all() and (con[:, 12] > -1e-3).all()
+    # actuator force is clamped to 15 N and the joint's dry friction (frictionloss 1 N) may hold up to
+    # 1 N more or less, so the summed normal force on each side lies in [14, 16] N
+    f = s.efc("force")
+    rows = con[:, 17].astype(int)
+    left = con[:, 13] < 14
+    assert 14.0 - 1e-3 <= f[rows[left]].sum() <= 16.0 + 1e-3 and 14.0 - 1e-3 <= f[rows[~left]].sum() <= 16.0 + 1e-3
+    assert np.isclose(f[rows[left]].sum(), f[rows[~left]].sum(), rtol=1e-3)  # cube in equilibrium
+    # cube stays put (symmetric squeeze)
+    assert np.abs(s.qpos[9:12]).max() < 1e-4
+    # energy: everything at rest after the squeeze
+    assert np.abs(s.qvel).max() < 1e-4
+
+
+def test_static_friction_threshold(panda_cube):
+    """A pinched 1 kg cube on an accelerating gripper: it stays in the fingers while m*a < mu * N_total and
+    slips beyond (pad friction 2.4, 2 x ~15 N normal force -> ~72 N)."""
+    m, info = panda_cube[0], panda_cube[1]
+    p7 = np.array([0, 0, -0.102, 0.70710677, 0, 0, 0.70710677])
+    for acc, holds in ((30.0, True), (160.0, False)):
+        s = OracleSim(m)
+        s.reset()
+        s.place(p7, info["base_qposadr"], np.array([0.0325, -0.0075]), info["joint_qposadr"])
+        s.ctrl[:] = info["close_ctrl"]
+        s.step(1500)
+        rel0 = s.qpos[11] - s.qpos[2]
+        for k in range(60):
+            t = (k + 1) * 1e-3
+            s.mocap_pos[0, 2] = p7[2] + 0.5 * acc * t * t
+            s.step(1)
+        slip = abs((s.qpos[11] - s.qpos[2]) - rel0)
+        if holds:
+            assert slip < 5e-4, slip
+        else:
+            assert slip > 5e-3, slip
+
+
+def test_newton_solution_is_kkt_point(panda_cube):
+    m, info = panda_cube[0], panda_cube[1]
+    s = OracleSim(m)
+    p7 = np.array([0, 0, -0.102, 0.70710677, 0, 0, 0.70710677])
+    s.reset()
+    s.place(p7, info["base_qposadr"], np.array([0.0201, -0.0199]), info["joint_qposadr"])
+    s.ctrl[:] = info["close_ctrl"]
+    s.step(50)
+    # before noslip: M qacc - qfrc_smooth = J' f at the Newton optimum; with noslip the same identity holds by construction
+    J, f = s.efc("J"), s.efc("force")
+    lhs = s.M @ s.qacc - s.qfrc_smooth
+    assert np.allclose(lhs, J.T @ f, atol=1e-6 * max(1.0, np.abs(lhs).max()))
