@@ -14,25 +14,26 @@
 #include "mgs_model_build.h"
 #include "mgs_rollout.cuh"
 
-#ifndef MGS_WARPS_PER_BLOCK
-#define MGS_WARPS_PER_BLOCK 4
+#ifndef MGS_MAX_WARPS_PER_BLOCK
+#define MGS_MAX_WARPS_PER_BLOCK 16
 #endif
 
 extern __shared__ __align__(16) unsigned char mgs_smem_raw[];
 
-__global__ void __launch_bounds__(MGS_WARPS_PER_BLOCK * 32)
-mgs_rollout_kernel(const DevModel m, const Layout L, const RolloutParams prm, const BatchIO io) {
-  real *base = reinterpret_cast<real *>(mgs_smem_raw) + (size_t)(threadIdx.x >> 5) * L.total;
+__global__ void __launch_bounds__(MGS_MAX_WARPS_PER_BLOCK * 32)
+mgs_rollout_kernel() {
+  real *base = reinterpret_cast<real *>(mgs_smem_raw) + (size_t)(threadIdx.x >> 5) * LY.total;
   const int lane = threadIdx.x & 31;
   Env e;
   for (;;) {
     unsigned int env = 0;
-    if (lane == 0) env = atomicAdd(io.work_counter, 1u);
+    if (lane == 0) env = atomicAdd(IO.work_counter, 1u);
     env = __shfl_sync(0xffffffffu, env, 0);
-    if (env >= (unsigned int)prm.n) break;
-    env_bind(e, base, L);
-    run_env_w(m, e, prm, io, (int)env);
+    if (env >= (unsigned int)PRM.n) break;
+    env_bind(e, base);
+    run_env_w(e, (int)env);
   }
+  // a warp that runs out of work leaves; exited warps no longer count towards the CTA barrier
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -52,7 +53,7 @@ struct MgsModel {
   Layout L;
   char *d_blob;
   unsigned int *d_counter;
-  int num_sms, blocks_per_sm, smem_per_block;
+  int num_sms, blocks_per_sm, smem_per_block, warps_per_block;
   int state_stride, diag_stride;
   // staging for the host-pointer entry points (grown on demand)
   void *d_stage, *h_stage;
@@ -85,15 +86,27 @@ extern "C" int mgs_model_create(const MgsModelDesc *desc, int device, MgsModel *
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   M->num_sms = prop.multiProcessorCount;
-  M->smem_per_block = (int)(M->L.total * sizeof(real)) * MGS_WARPS_PER_BLOCK;
-  if ((size_t)M->smem_per_block > prop.sharedMemPerBlockOptin) {
+  const int env_bytes = (int)(M->L.total * sizeof(real));
+  if ((size_t)env_bytes > prop.sharedMemPerBlockOptin) {
     delete M;
-    return fail("model needs more shared memory per block than the device offers (env-per-block variant not built yet)");
+    return fail("model needs more shared memory per environment than one CTA can have (env-per-block variant not built yet)");
   }
+  CU(cudaFuncSetAttribute(mgs_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  // CTA size = the warps-per-block that gives the most resident warps per SM (shared memory per
+  // environment and the per-CTA reservation decide)
+  int best_warps = 0;
+  for (int w = 1; w <= MGS_MAX_WARPS_PER_BLOCK; w++) {
+    if ((size_t)env_bytes * w > prop.sharedMemPerBlockOptin) break;
+    CU(cudaFuncSetAttribute(mgs_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, env_bytes * w));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgs_rollout_kernel, w * 32, (size_t)env_bytes * w));
+    if (occ * w >= best_warps && occ > 0) {  // ties go to the LARGER CTA: one CTA per SM keeps all resident warps stage-aligned
+       best_warps = occ * w; M->warps_per_block = w; M->blocks_per_sm = occ;
+    }
+  }
+  if (best_warps == 0) { delete M; return fail("kernel does not fit on this device"); }
+  M->smem_per_block = env_bytes * M->warps_per_block;
   CU(cudaFuncSetAttribute(mgs_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, M->smem_per_block));
-  int occ = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgs_rollout_kernel, MGS_WARPS_PER_BLOCK * 32, M->smem_per_block));
-  M->blocks_per_sm = occ > 0 ? occ : 1;
   M->state_stride = desc->nq + 2 * desc->nv + desc->nu + 7 * desc->nmocap;
   M->diag_stride = mgs_diag_stride(desc->nv, desc->nbody, blob.ncon_max, blob.nefc_max);
   CU(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
@@ -118,7 +131,7 @@ extern "C" int mgs_model_info(const MgsModel *M, MgsModelInfo *info) {
   info->state_stride = M->state_stride; info->diag_stride = M->diag_stride;
   info->ncon_max = M->L.ncon_max; info->nefc_max = M->L.nefc_max;
   info->smem_bytes_per_env = (int)(M->L.total * sizeof(real));
-  info->warps_per_block = MGS_WARPS_PER_BLOCK; info->blocks_per_sm = M->blocks_per_sm; info->num_sms = M->num_sms;
+  info->warps_per_block = M->warps_per_block; info->blocks_per_sm = M->blocks_per_sm; info->num_sms = M->num_sms;
   info->real_bytes = (int)sizeof(real);
   return 0;
 }
@@ -128,12 +141,23 @@ static int launch(MgsModel *M, const RolloutParams &prm, const BatchIO &io_in, c
   BatchIO io = io_in;
   io.work_counter = M->d_counter;
   CU(cudaMemsetAsync(M->d_counter, 0, sizeof(unsigned int), st));
-  int blocks_needed = (prm.n + MGS_WARPS_PER_BLOCK - 1) / MGS_WARPS_PER_BLOCK;
+  int blocks_needed = (prm.n + M->warps_per_block - 1) / M->warps_per_block;
   int grid = M->num_sms * M->blocks_per_sm;
   if (grid > blocks_needed) grid = blocks_needed;
-  mgs_rollout_kernel<<<grid, MGS_WARPS_PER_BLOCK * 32, M->smem_per_block, st>>>(M->dm, M->L, prm, io);
+  // the constants of this launch (model pointers, layout, parameters, I/O) go to __constant__ memory,
+  // stream-ordered; wait for the previous launch on this device before overwriting them
+  static cudaEvent_t last_done[64];  // one per device, created once, never destroyed
+  static bool have_last[64];
+  if (!have_last[M->device]) CU(cudaEventCreateWithFlags(&last_done[M->device], cudaEventDisableTiming));
+  else CU(cudaStreamWaitEvent(st, last_done[M->device], 0));
+  have_last[M->device] = true;
+  KernelConsts kc;
+  kc.m = M->dm; kc.L = M->L; kc.prm = prm; kc.io = io;
+  CU(cudaMemcpyToSymbolAsync(c_k, &kc, sizeof(kc), 0, cudaMemcpyHostToDevice, st));
+  mgs_rollout_kernel<<<grid, M->warps_per_block * 32, M->smem_per_block, st>>>();
   g_launches++;
   CU(cudaGetLastError());
+  CU(cudaEventRecord(last_done[M->device], st));
   return 0;
 }
 

@@ -17,66 +17,74 @@
 struct SupPt { real v[3], v1[3], v2[3]; };
 
 struct GeomRef {
-  int type, hull, nvert, vadr;
+  int cg, type, hull;
   const real *R, *p;
-  real size[3];
   int cur;  // hill-climbing start vertex (persists across support calls of one query)
 };
 
-MGS_DEV void geomref_init(GeomRef &g, const DevModel &m, const Env &e, int cg) {
-  g.type = LDG(m.cgeom_type + cg);
-  g.hull = LDG(m.cgeom_hullid + cg);
-  g.R = e.gxmat + 9 * cg;
-  g.p = e.gxpos + 3 * cg;
-  ld3(g.size, m.cgeom_size + 3 * cg);
+MGS_DEV void geomref_init(GeomRef &g, const Env &e, int cg) {
+  g.cg = cg;
+  g.type = LDG(MD.cgeom_type + cg);
+  g.hull = LDG(MD.cgeom_hullid + cg);
+  g.R = EF(gxmat) + 9 * cg;
+  g.p = EF(gxpos) + 3 * cg;
   g.cur = 0;
-  g.nvert = 0; g.vadr = 0;
-  if (g.type == GEOM_MESH) { g.nvert = LDG(m.hull_vertnum + g.hull); g.vadr = LDG(m.hull_vertadr + g.hull); }
 }
 
-// support point (world) of a geom in world direction d
-MGS_DEV void geom_support(const DevModel &m, GeomRef &g, const real *d, real *out) {
-  real dl[3], p[3] = {0, 0, 0};
-  mulmatTvec3(dl, g.R, d);
-  if (g.type == GEOM_BOX) {
-    p[0] = dl[0] >= 0 ? g.size[0] : -g.size[0];
-    p[1] = dl[1] >= 0 ? g.size[1] : -g.size[1];
-    p[2] = dl[2] >= 0 ? g.size[2] : -g.size[2];
-  } else if (g.type == GEOM_MESH) {
+struct Sup { real x, y, z; int cur; };
+
+// support point (world) of collision geom `cg` in world direction d.  Arguments and result travel in
+// registers (the function is deliberately NOT inlined: one copy of the code serves every call site,
+// which keeps the kernel's instruction footprint small).
+MGS_DEVN Sup geom_support(const real *Rm, const real *gp, int cg, int type, int hull, int cur, real dx, real dy, real dz) {
+  real dl[3], p[3] = {0, 0, 0}, d[3] = {dx, dy, dz};
+  mulmatTvec3(dl, Rm, d);
+  real s0 = LDG(MD.cgeom_size + 3 * cg), s1 = LDG(MD.cgeom_size + 3 * cg + 1), s2 = LDG(MD.cgeom_size + 3 * cg + 2);
+  if (type == GEOM_BOX) {
+    p[0] = dl[0] >= 0 ? s0 : -s0;
+    p[1] = dl[1] >= 0 ? s1 : -s1;
+    p[2] = dl[2] >= 0 ? s2 : -s2;
+  } else if (type == GEOM_MESH) {
     // hill climbing on the hull's vertex graph from the previous answer
-    const real *V = m.hull_vert + 3 * g.vadr;
-    int cur = g.cur;
+    const int vadr = LDG(MD.hull_vertadr + hull), nvert = LDG(MD.hull_vertnum + hull);
+    const real *V = MD.hull_vert + 3 * vadr;
     real best = LDG(V + 3 * cur) * dl[0] + LDG(V + 3 * cur + 1) * dl[1] + LDG(V + 3 * cur + 2) * dl[2];
-    for (int guard = 0; guard < g.nvert; guard++) {
-      int na = LDG(m.hull_nbradr + g.vadr + cur), nn = LDG(m.hull_nbrnum + g.vadr + cur), nxt = cur;
+#pragma unroll 1
+    for (int guard = 0; guard < nvert; guard++) {
+      int na = LDG(MD.hull_nbradr + vadr + cur), nn = LDG(MD.hull_nbrnum + vadr + cur), nxt = cur;
+#pragma unroll 1
       for (int k = 0; k < nn; k++) {
-        int v = LDG(m.hull_nbr + na + k);
+        int v = LDG(MD.hull_nbr + na + k);
         real t = LDG(V + 3 * v) * dl[0] + LDG(V + 3 * v + 1) * dl[1] + LDG(V + 3 * v + 2) * dl[2];
         if (t > best) { best = t; nxt = v; }
       }
       if (nxt == cur) break;
       cur = nxt;
     }
-    g.cur = cur;
     ld3(p, V + 3 * cur);
-  } else if (g.type == GEOM_SPHERE) {
-    scl3(p, dl, g.size[0]);
-  } else if (g.type == GEOM_CAPSULE) {
-    scl3(p, dl, g.size[0]);
-    p[2] += dl[2] >= 0 ? g.size[1] : -g.size[1];
-  } else if (g.type == GEOM_CYLINDER) {
+  } else if (type == GEOM_SPHERE) {
+    scl3(p, dl, s0);
+  } else if (type == GEOM_CAPSULE) {
+    scl3(p, dl, s0);
+    p[2] += dl[2] >= 0 ? s1 : -s1;
+  } else if (type == GEOM_CYLINDER) {
     real n = sqrt(dl[0] * dl[0] + dl[1] * dl[1]);
-    if (n > MGS_MINVAL) { p[0] = dl[0] / n * g.size[0]; p[1] = dl[1] / n * g.size[0]; }
-    p[2] = dl[2] >= 0 ? g.size[1] : -g.size[1];
+    if (n > MGS_MINVAL) { p[0] = dl[0] / n * s0; p[1] = dl[1] / n * s0; }
+    p[2] = dl[2] >= 0 ? s1 : -s1;
   }
-  mulmatvec3(out, g.R, p);
-  add3(out, out, g.p);
+  real o[3];
+  mulmatvec3(o, Rm, p);
+  Sup r;
+  r.x = o[0] + gp[0]; r.y = o[1] + gp[1]; r.z = o[2] + gp[2]; r.cur = cur;
+  return r;
 }
 
-MGS_DEV void mink_support(const DevModel &m, GeomRef &g1, GeomRef &g2, const real *d, SupPt &o) {
-  real nd[3] = {-d[0], -d[1], -d[2]};
-  geom_support(m, g1, d, o.v1);
-  geom_support(m, g2, nd, o.v2);
+MGS_DEV void mink_support(GeomRef &g1, GeomRef &g2, const real *d, SupPt &o) {
+  Sup a = geom_support(g1.R, g1.p, g1.cg, g1.type, g1.hull, g1.cur, d[0], d[1], d[2]);
+  Sup b = geom_support(g2.R, g2.p, g2.cg, g2.type, g2.hull, g2.cur, -d[0], -d[1], -d[2]);
+  g1.cur = a.cur; g2.cur = b.cur;
+  o.v1[0] = a.x; o.v1[1] = a.y; o.v1[2] = a.z;
+  o.v2[0] = b.x; o.v2[1] = b.y; o.v2[2] = b.z;
   sub3(o.v, o.v1, o.v2);
 }
 
@@ -104,7 +112,7 @@ MGS_DEV int reach_tolerance(const SupPt &p1, const SupPt &p2, const SupPt &p3, c
   return mn <= tol;
 }
 
-MGS_DEV void closest_on_triangle(const real *a, const real *b, const real *c, real *out) {
+MGS_DEVN void closest_on_triangle(const real *a, const real *b, const real *c, real *out) {
   real ab[3], ac[3], ap[3] = {-a[0], -a[1], -a[2]};
   sub3(ab, b, a); sub3(ac, c, a);
   real d1 = dot3(ab, ap), d2 = dot3(ac, ap);
@@ -128,87 +136,123 @@ MGS_DEV void closest_on_triangle(const real *a, const real *b, const real *c, re
   copy3(out, a); addscl3(out, ab, v); addscl3(out, ac, w);
 }
 
-// returns 1 when penetrating: depth > 0, dir from g1 to g2 (unit), pos
-MGS_DEVN int mpr_penetration(const DevModel &m, GeomRef &g1, GeomRef &g2, real *depth, real *dir, real *pos) {
-  const real tol = m.mpr_tolerance;
-  SupPt p0, p1, p2, p3, v4;
-  real d[3], va[3], vb[3];
-  copy3(p0.v1, g1.p); copy3(p0.v2, g2.p);
-  sub3(p0.v, p0.v1, p0.v2);
-  if (dot3(p0.v, p0.v) < R_(1e-28)) p0.v[0] += R_(1e-10);
-  scl3(d, p0.v, -1); normalize3(d);
-  mink_support(m, g1, g2, d, p1);
-  if (dot3(p1.v, d) <= 0) return 0;
-  cross3(d, p0.v, p1.v);
-  if (dot3(d, d) < R_(1e-28) * fmax(R_(1e-30), dot3(p0.v, p0.v) * dot3(p1.v, p1.v))) {
-    *depth = sqrt(dot3(p1.v, p1.v));
-    copy3(dir, p1.v); normalize3(dir);
-    for (int k = 0; k < 3; k++) pos[k] = R_(0.5) * (p1.v1[k] + p1.v2[k]);
-    return *depth > 0;
+// Minkowski Portal Refinement as a LOCKSTEP STATE MACHINE: every lane owns one geom pair, and every
+// iteration of the loop makes exactly one support query at one call site.  Lanes therefore stay
+// converged through the expensive part (the hill-climbing hull support) no matter in which phase of
+// the algorithm their pair is (ncu r1_b: the straight-line version ran geom_support with 2 of 32 lanes
+// active and spent 24 % of all issued instructions there).
+// Phases: V1, V2 (first two portal vertices), V3 (third vertex / portal discovery), REFINE (portal must
+// pass the origin), PEN (push the portal to the surface).  `active` = this lane has a pair to test.
+// Returns 1 when penetrating: depth > 0, dir from g1 to g2 (unit), pos.
+enum { MPR_V1 = 0, MPR_V2, MPR_V3, MPR_REFINE, MPR_PEN, MPR_DONE };
+MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, real *depth, real *dir, real *pos) {
+  const real tol = MD.mpr_tolerance;
+  SupPt p0, p1, p2, p3, s;
+  real d[3] = {1, 0, 0}, va[3], vb[3];
+  int state = MPR_DONE, hit = 0, it = 0;
+  if (active) {
+    copy3(p0.v1, g1.p); copy3(p0.v2, g2.p);
+    sub3(p0.v, p0.v1, p0.v2);
+    if (dot3(p0.v, p0.v) < R_(1e-28)) p0.v[0] += R_(1e-10);
+    scl3(d, p0.v, -1); normalize3(d);
+    state = MPR_V1;
   }
-  normalize3(d);
-  mink_support(m, g1, g2, d, p2);
-  if (dot3(p2.v, d) <= 0) return 0;
-  sub3(va, p1.v, p0.v); sub3(vb, p2.v, p0.v);
-  cross3(d, va, vb); normalize3(d);
-  if (dot3(d, p0.v) > 0) { SupPt t = p1; p1 = p2; p2 = t; scl3(d, d, -1); }
-  for (int it = 0;; it++) {
-    if (it > 100) return 0;
-    mink_support(m, g1, g2, d, p3);
-    if (dot3(p3.v, d) <= 0) return 0;
-    int cont = 0;
-    cross3(va, p1.v, p3.v);
-    if (dot3(va, p0.v) < R_(-1e-30)) { p2 = p3; cont = 1; }
-    if (!cont) {
-      cross3(va, p3.v, p2.v);
-      if (dot3(va, p0.v) < R_(-1e-30)) { p1 = p3; cont = 1; }
-    }
-    if (!cont) break;
-    sub3(va, p1.v, p0.v); sub3(vb, p2.v, p0.v);
-    cross3(d, va, vb); normalize3(d);
-  }
-  for (int it = 0;; it++) {
-    portal_dir(p1, p2, p3, d);
-    if (dot3(d, p1.v) >= 0) break;
-    mink_support(m, g1, g2, d, v4);
-    if (dot3(v4.v, d) < 0 || reach_tolerance(p1, p2, p3, v4, d, tol) || it > m.mpr_iterations) return 0;
-    expand_portal(p0, p1, p2, p3, v4);
-  }
-  for (int it = 0;; it++) {
-    portal_dir(p1, p2, p3, d);
-    mink_support(m, g1, g2, d, v4);
-    if (reach_tolerance(p1, p2, p3, v4, d, tol) || it > m.mpr_iterations) {
-      real c[3];
-      closest_on_triangle(p1.v, p2.v, p3.v, c);
-      *depth = sqrt(dot3(c, c));
-      if (*depth < MGS_MINVAL) copy3(dir, d); else scl3(dir, c, R_(1.0) / *depth);
-      real b0, b1, b2, b3, t[3], sum;
-      cross3(t, p1.v, p2.v); b0 = dot3(t, p3.v);
-      cross3(t, p3.v, p2.v); b1 = dot3(t, p0.v);
-      cross3(t, p0.v, p1.v); b2 = dot3(t, p3.v);
-      cross3(t, p2.v, p1.v); b3 = dot3(t, p0.v);
-      sum = b0 + b1 + b2 + b3;
-      if (sum <= 0) {
-        b0 = 0;
-        cross3(t, p2.v, p3.v); b1 = dot3(t, d);
-        cross3(t, p3.v, p1.v); b2 = dot3(t, d);
-        cross3(t, p1.v, p2.v); b3 = dot3(t, d);
-        sum = b1 + b2 + b3;
+  #pragma unroll 1
+  for (;;) {
+    // single warp-collective test per iteration; no lane leaves the body early (no `continue`), so all
+    // lanes re-converge at the bottom of the loop
+    if (!wany(state != MPR_DONE)) break;
+    if (state != MPR_DONE) mink_support(g1, g2, d, s);  // the one (converged) support call site
+    if (state == MPR_V1) {
+      p1 = s;
+      if (dot3(p1.v, d) <= 0) state = MPR_DONE;
+      else {
+        cross3(d, p0.v, p1.v);
+        if (dot3(d, d) < R_(1e-28) * fmax(R_(1e-30), dot3(p0.v, p0.v) * dot3(p1.v, p1.v))) {
+          // origin on the segment v0-v1: penetration along v1
+          *depth = sqrt(dot3(p1.v, p1.v));
+          copy3(dir, p1.v); normalize3(dir);
+          for (int k = 0; k < 3; k++) pos[k] = R_(0.5) * (p1.v1[k] + p1.v2[k]);
+          hit = *depth > 0; state = MPR_DONE;
+        } else {
+          normalize3(d);
+          state = MPR_V2;
+        }
       }
-      real is = R_(0.5) / sum;
-      for (int k = 0; k < 3; k++)
-        pos[k] = (b0 * (p0.v1[k] + p0.v2[k]) + b1 * (p1.v1[k] + p1.v2[k]) + b2 * (p2.v1[k] + p2.v2[k]) + b3 * (p3.v1[k] + p3.v2[k])) * is;
-      return 1;
+    } else if (state == MPR_V2) {
+      p2 = s;
+      if (dot3(p2.v, d) <= 0) state = MPR_DONE;
+      else {
+        sub3(va, p1.v, p0.v); sub3(vb, p2.v, p0.v);
+        cross3(d, va, vb); normalize3(d);
+        if (dot3(d, p0.v) > 0) { SupPt t = p1; p1 = p2; p2 = t; scl3(d, d, -1); }
+        state = MPR_V3; it = 0;
+      }
+    } else if (state == MPR_V3) {
+      p3 = s;
+      if (dot3(p3.v, d) <= 0 || ++it > 100) state = MPR_DONE;
+      else {
+        int cont = 0;
+        cross3(va, p1.v, p3.v);
+        if (dot3(va, p0.v) < R_(-1e-30)) { p2 = p3; cont = 1; }
+        if (!cont) {
+          cross3(va, p3.v, p2.v);
+          if (dot3(va, p0.v) < R_(-1e-30)) { p1 = p3; cont = 1; }
+        }
+        if (cont) {
+          sub3(va, p1.v, p0.v); sub3(vb, p2.v, p0.v);
+          cross3(d, va, vb); normalize3(d);
+        } else {
+          portal_dir(p1, p2, p3, d);
+          state = (dot3(d, p1.v) >= 0) ? MPR_PEN : MPR_REFINE;  // origin already inside the portal?
+          it = 0;
+        }
+      }
+    } else if (state == MPR_REFINE) {
+      if (dot3(s.v, d) < 0 || reach_tolerance(p1, p2, p3, s, d, tol) || ++it > MD.mpr_iterations) state = MPR_DONE;
+      else {
+        expand_portal(p0, p1, p2, p3, s);
+        portal_dir(p1, p2, p3, d);
+        if (dot3(d, p1.v) >= 0) { state = MPR_PEN; it = 0; }
+      }
+    } else if (state == MPR_PEN) {
+      if (reach_tolerance(p1, p2, p3, s, d, tol) || ++it > MD.mpr_iterations) {
+        real c[3];
+        closest_on_triangle(p1.v, p2.v, p3.v, c);
+        *depth = sqrt(dot3(c, c));
+        if (*depth < MGS_MINVAL) copy3(dir, d); else scl3(dir, c, R_(1.0) / *depth);
+        real b0, b1, b2, b3, t[3], sum;
+        cross3(t, p1.v, p2.v); b0 = dot3(t, p3.v);
+        cross3(t, p3.v, p2.v); b1 = dot3(t, p0.v);
+        cross3(t, p0.v, p1.v); b2 = dot3(t, p3.v);
+        cross3(t, p2.v, p1.v); b3 = dot3(t, p0.v);
+        sum = b0 + b1 + b2 + b3;
+        if (sum <= 0) {
+          b0 = 0;
+          cross3(t, p2.v, p3.v); b1 = dot3(t, d);
+          cross3(t, p3.v, p1.v); b2 = dot3(t, d);
+          cross3(t, p1.v, p2.v); b3 = dot3(t, d);
+          sum = b1 + b2 + b3;
+        }
+        real is = R_(0.5) / sum;
+        for (int k = 0; k < 3; k++)
+          pos[k] = (b0 * (p0.v1[k] + p0.v2[k]) + b1 * (p1.v1[k] + p1.v2[k]) + b2 * (p2.v1[k] + p2.v2[k]) + b3 * (p3.v1[k] + p3.v2[k])) * is;
+        hit = 1; state = MPR_DONE;
+      } else {
+        expand_portal(p0, p1, p2, p3, s);
+        portal_dir(p1, p2, p3, d);
+      }
     }
-    expand_portal(p0, p1, p2, p3, v4);
   }
+  return hit;
 }
 
-MGS_DEV int best_face(const DevModel &m, const GeomRef &g, const real *n, real *align) {
+MGS_DEVN int best_face(const GeomRef &g, const real *n, real *align) {
   real nl[3], bd = R_(-1e30);
   mulmatTvec3(nl, g.R, n);
-  int fa = LDG(m.hull_faceadr + g.hull), fn = LDG(m.hull_facenum + g.hull), best = 0;
-  const real *FN = m.hull_facenormal + 3 * fa;
+  int fa = LDG(MD.hull_faceadr + g.hull), fn = LDG(MD.hull_facenum + g.hull), best = 0;
+  const real *FN = MD.hull_facenormal + 3 * fa;
+  #pragma unroll 1
   for (int f = 0; f < fn; f++) {
     real t = LDG(FN + 3 * f) * nl[0] + LDG(FN + 3 * f + 1) * nl[1] + LDG(FN + 3 * f + 2) * nl[2];
     if (t > bd) { bd = t; best = f; }
@@ -216,56 +260,63 @@ MGS_DEV int best_face(const DevModel &m, const GeomRef &g, const real *n, real *
   *align = bd;
   return best;
 }
-MGS_DEV int face_polygon(const DevModel &m, const GeomRef &g, int f, real (*poly)[3], real *nw) {
-  int gf = LDG(m.hull_faceadr + g.hull) + f;
-  int n = LDG(m.hull_facevertnum + gf), fva = LDG(m.hull_facevertadr + gf), va = LDG(m.hull_vertadr + g.hull);
+MGS_DEVN int face_polygon(const GeomRef &g, int f, real (*poly)[3], real *nw) {
+  int gf = LDG(MD.hull_faceadr + g.hull) + f;
+  int n = LDG(MD.hull_facevertnum + gf), fva = LDG(MD.hull_facevertadr + gf), va = LDG(MD.hull_vertadr + g.hull);
+  #pragma unroll 1
   for (int i = 0; i < n; i++) {
     real v[3];
-    ld3(v, m.hull_vert + 3 * (va + LDG(m.hull_facevert + fva + i)));
+    ld3(v, MD.hull_vert + 3 * (va + LDG(MD.hull_facevert + fva + i)));
     mulmatvec3(poly[i], g.R, v);
     add3(poly[i], poly[i], g.p);
   }
   real fnl[3];
-  ld3(fnl, m.hull_facenormal + 3 * gf);
+  ld3(fnl, MD.hull_facenormal + 3 * gf);
   mulmatvec3(nw, g.R, fnl);
   return n;
 }
 
 struct PairContacts { int n; real normal[3], pos[4][3], dist[4]; };
 
-// narrowphase for candidate pair `pair`; fills up to 4 contacts
-MGS_DEVN void collide_pair(const DevModel &m, const Env &e, int pair, PairContacts &out) {
+// narrowphase for candidate pair `pair` (this lane's pair; pair < 0: lane idle); fills up to 4 contacts.
+// Called by all lanes of the warp together: the MPR stage inside is warp-converged.
+MGS_DEVN void collide_pair(const Env &e, int pair, PairContacts &out) {
   out.n = 0;
-  int c1 = LDG(m.pair_geom1 + pair), c2 = LDG(m.pair_geom2 + pair);
-  real dc[3];
-  sub3(dc, e.gxpos + 3 * c1, e.gxpos + 3 * c2);
-  real rr = LDG(m.cgeom_rbound + c1) + LDG(m.cgeom_rbound + c2) + LDG(m.pair_margin + pair);
-  if (dot3(dc, dc) > rr * rr) return;
+  int active = 0, c1 = 0, c2 = 0;
+  if (pair >= 0) {
+    c1 = LDG(MD.pair_geom1 + pair); c2 = LDG(MD.pair_geom2 + pair);
+    real dc[3];
+    sub3(dc, EF(gxpos) + 3 * c1, EF(gxpos) + 3 * c2);
+    real rr = LDG(MD.cgeom_rbound + c1) + LDG(MD.cgeom_rbound + c2) + LDG(MD.pair_margin + pair);
+    active = dot3(dc, dc) <= rr * rr;
+  }
   GeomRef g1, g2;
-  geomref_init(g1, m, e, c1);
-  geomref_init(g2, m, e, c2);
-  real depth, n[3], pos[3];
-  if (!mpr_penetration(m, g1, g2, &depth, n, pos)) return;
-  if (!(depth > 0)) return;
+  geomref_init(g1, e, c1);
+  geomref_init(g2, e, c2);
+  real depth = 0, n[3], pos[3];
+  int hit = mpr_penetration(g1, g2, active, &depth, n, pos);
+  if (!hit || !(depth > 0)) return;
   int poly1 = (g1.type == GEOM_BOX || g1.type == GEOM_MESH), poly2 = (g2.type == GEOM_BOX || g2.type == GEOM_MESH);
   if (poly1 && poly2) {
     real a1, a2, nn[3] = {-n[0], -n[1], -n[2]};
-    int f1 = best_face(m, g1, n, &a1), f2 = best_face(m, g2, nn, &a2);
+    int f1 = best_face(g1, n, &a1), f2 = best_face(g2, nn, &a2);
     if (fmax(a1, a2) >= MGS_FACE_ALIGN_MIN) {
       const int ref_is_1 = a1 >= a2;
       const GeomRef &rg = ref_is_1 ? g1 : g2;
       const GeomRef &ig = ref_is_1 ? g2 : g1;
       real ref[MGS_MAXPOLY][3], nref[3], ninc[3], A[MGS_MAXCLIP][3], B[MGS_MAXCLIP][3], dist[MGS_MAXCLIP];
-      int nr = face_polygon(m, rg, ref_is_1 ? f1 : f2, ref, nref);
+      int nr = face_polygon(rg, ref_is_1 ? f1 : f2, ref, nref);
       real mn[3] = {-nref[0], -nref[1], -nref[2]}, al;
-      int incf = best_face(m, ig, mn, &al);
-      int na = face_polygon(m, ig, incf, A, ninc);
+      int incf = best_face(ig, mn, &al);
+      int na = face_polygon(ig, incf, A, ninc);
+      #pragma unroll 1
       for (int ed = 0; ed < nr && na > 0; ed++) {
         real edge[3], sn[3];
         int e2 = (ed + 1 == nr) ? 0 : ed + 1;
         sub3(edge, ref[e2], ref[ed]);
         cross3(sn, edge, nref);
         int nb2 = 0;
+        #pragma unroll 1
         for (int i = 0; i < na; i++) {
           const real *P = A[i], *Q = A[(i + 1 == na) ? 0 : i + 1];
           real t0[3], t1[3];
@@ -279,9 +330,11 @@ MGS_DEVN void collide_pair(const DevModel &m, const Env &e, int pair, PairContac
           }
         }
         na = nb2;
+        #pragma unroll 1
         for (int i = 0; i < na; i++) copy3(A[i], B[i]);
       }
       int np = 0;
+      #pragma unroll 1
       for (int i = 0; i < na; i++) {
         real t[3];
         sub3(t, A[i], ref[0]);
@@ -290,15 +343,18 @@ MGS_DEVN void collide_pair(const DevModel &m, const Env &e, int pair, PairContac
       }
       if (np > 0) {
         int sel[4], ns = 0, i0 = 0;
+        #pragma unroll 1
         for (int i = 1; i < np; i++) if (dist[i] < dist[i0]) i0 = i;
         sel[ns++] = i0;
         if (np > 1) {
           int i1 = -1; real bd = -1;
+          #pragma unroll 1
           for (int i = 0; i < np; i++) { real t[3]; sub3(t, A[i], A[i0]); real d2 = dot3(t, t); if (i != i0 && d2 > bd) { bd = d2; i1 = i; } }
           if (i1 >= 0 && bd > R_(1e-12)) {
             sel[ns++] = i1;
             real e01[3]; sub3(e01, A[i1], A[i0]);
             int i2 = -1, i3 = -1; real mx = R_(1e-12), mnv = R_(-1e-12);
+            #pragma unroll 1
             for (int i = 0; i < np; i++) {
               if (i == i0 || i == i1) continue;
               real t[3], c[3]; sub3(t, A[i], A[i0]); cross3(c, e01, t);
@@ -311,6 +367,7 @@ MGS_DEVN void collide_pair(const DevModel &m, const Env &e, int pair, PairContac
           }
         }
         if (ref_is_1) copy3(out.normal, nref); else scl3(out.normal, nref, -1);
+        #pragma unroll 1
         for (int k = 0; k < ns; k++) {
           copy3(out.pos[k], A[sel[k]]);
           addscl3(out.pos[k], nref, R_(-0.5) * dist[sel[k]]);
@@ -336,22 +393,22 @@ MGS_DEV void make_frame(real *frame) {
   cross3(z, x, y);
 }
 
-MGS_DEVN void collision_w(const DevModel &m, Env &e) {
+MGS_DEVN void collision_w(Env &e) {
   int base = 0;
-  for (int p0 = 0; p0 < m.npair; p0 += LANES) {
+  #pragma unroll 1
+  for (int p0 = 0; p0 < MD.npair; p0 += LANES) {
     int p = p0 + MGS_LANE;
     PairContacts pc;
-    pc.n = 0;
-    if (p < m.npair) collide_pair(m, e, p, pc);
+    collide_pair(e, p < MD.npair ? p : -1, pc);
     int total, off = wscan_excl(pc.n, &total);
+    #pragma unroll 1
     for (int k = 0; k < pc.n; k++) {
       int c = base + off + k;
       if (c >= e.ncon_max) break;
-      copy3(e.con_pos + 3 * c, pc.pos[k]);
-      copy3(e.con_frame + 9 * c, pc.normal);
-      make_frame(e.con_frame + 9 * c);
-      e.con_dist[c] = pc.dist[k];
-      IARR(e.con_pair)[c] = p;
+      copy3(EF(con_pos) + 3 * c, pc.pos[k]);
+      copy3(EF(con_normal) + 3 * c, pc.normal);
+      EF(con_dist)[c] = pc.dist[k];
+      IARR(EF(con_pair))[c] = p;
     }
     base += total;
   }
@@ -362,11 +419,12 @@ MGS_DEVN void collision_w(const DevModel &m, Env &e) {
 
 // gripper <-> object contact test (reference check_contact_with_object,
 // gravityless_object_grasping.py:309-321): a contact whose geom ids straddle the ground geom's id
-MGS_DEV int contact_with_object_w(const DevModel &m, const Env &e) {
-  int hit = 0, g = m.ground_geomid;
+MGS_DEVN int contact_with_object_w(const Env &e) {
+  int hit = 0, g = MD.ground_geomid;
+  #pragma unroll 1
   PFOR(c, e.ncon) {
-    int p = IARR(e.con_pair)[c];
-    int a = LDG(m.cgeom_geomid + LDG(m.pair_geom1 + p)), b = LDG(m.cgeom_geomid + LDG(m.pair_geom2 + p));
+    int p = IARR(EF(con_pair))[c];
+    int a = LDG(MD.cgeom_geomid + LDG(MD.pair_geom1 + p)), b = LDG(MD.cgeom_geomid + LDG(MD.pair_geom2 + p));
     if ((a < g && b > g) || (a > g && b < g)) hit = 1;
   }
   return wany(hit);

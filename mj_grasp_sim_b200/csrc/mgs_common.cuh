@@ -33,6 +33,7 @@ typedef float real;
 #define MGS_LANE 0
 #define WSYNC() ((void)0)
 #define LDG(p) (*(p))
+#define MGS_STAGE_BARRIER() ((void)0)
 #else
 #include <cuda_runtime.h>
 #define MGS_DEV __device__ __forceinline__
@@ -41,6 +42,18 @@ typedef float real;
 #define MGS_LANE ((int)(threadIdx.x & 31))
 #define WSYNC() __syncwarp()
 #define LDG(p) __ldg(p)
+// CTA-wide STAGE barrier.  The step is ~250 KB of SASS that every warp walks through once per step;
+// with independent warps on an SM each sits in a different part of it and the instruction caches thrash
+// (ncu r1_a / r1_c: "no instruction" = 12-17 of the 18-24 stall cycles per issue).  One CTA per SM whose
+// warps enter every stage together share the fetches.  The barriers carry no data dependency (warps
+// never touch each other's environment); they only align code position, and every warp executes the
+// same number of them per step, whatever its contact count or solver path.  -DMGS_NO_STAGE_BARRIER
+// turns them off for A/B measurements.
+#ifdef MGS_NO_STAGE_BARRIER
+#define MGS_STAGE_BARRIER() ((void)0)
+#else
+#define MGS_STAGE_BARRIER() __syncthreads()
+#endif
 #endif
 
 // lane-strided loop: on the GPU lane L handles i = L, L+32, ...; on the host build one lane does all
@@ -75,25 +88,31 @@ struct DevModel {
   const real *wrap_coef;
   const int *actuator_trntype, *actuator_trnid, *actuator_ctrllimited, *actuator_forcelimited;
   const real *actuator_gainprm, *actuator_biasprm, *actuator_ctrlrange, *actuator_forcerange, *actuator_gear;
-  const int *eq_type, *eq_obj1id, *eq_obj2id, *eq_active, *eq_rowadr;
+  const int *eq_type, *eq_obj1id, *eq_obj2id, *eq_active, *eq_rowadr, *tri_ab;
   const real *eq_data, *eq_solref, *eq_solimp;
   const real *mocap_pos0, *mocap_quat0;
 };
 
 // Per-environment scratch layout (offsets in `real` units into the warp's shared-memory slice).
-#define MGS_LAYOUT_FIELDS(X)                                                                                       \
+// Three groups: PERSIST lives for the whole rollout; TRANSIENT (kinematics/collision/inertia/RNE
+// temporaries) and SOLVER (constraint rows) are never live at the same time, so they OVERLAY each
+// other - shared memory per environment is what bounds the number of resident warps per SM.
+#define MGS_LAYOUT_PERSIST(X)                                                                                      \
   X(qpos, nq) X(qvel, nv) X(qacc_ws, nv) X(ctrl, nu) X(mocap, 7 * nmocap)                                          \
-  X(xpos, 3 * nbody) X(xquat, 4 * nbody) X(xmat, 9 * nbody) X(xipos, 3 * nbody) X(ximat, 9 * nbody)                \
-  X(xanchor, 3 * njnt) X(xaxis, 3 * njnt) X(gxpos, 3 * ncgeom) X(gxmat, 9 * ncgeom) X(rootcom, 3 * nbody)          \
-  X(cinert, 10 * nbody) X(crb, 10 * nbody) X(cdof, 6 * nv) X(cdof_dot, 6 * nv) X(cvel, 6 * nbody)                  \
-  X(cacc, 6 * nbody) X(cfrc, 6 * nbody) X(M, nv * nv) X(Minv, nv * nv) X(H, nv * nv)                               \
+  X(xpos, 3 * nbody) X(xquat, 4 * nbody) X(xmat, 9 * nbody) X(rootcom, 3 * nbody) X(cdof, 6 * nv)                  \
+  X(M, nv * nv) X(Minv, nv * nv) X(H, nv * nv)                                                                     \
   X(ten_length, ntendon) X(ten_J, ntendon * nv) X(act_moment, nu * nv) X(act_force, nu) X(act_length, nu)          \
   X(qfrc_smooth, nv) X(qacc_smooth, nv) X(qacc, nv) X(qfrc_constraint, nv) X(Ma, nv) X(grad, nv) X(search, nv)     \
-  X(Mv, nv) X(wvec, nv) X(con_pos, 3 * ncon_max) X(con_frame, 9 * ncon_max) X(con_dist, ncon_max)                  \
-  X(con_mu, ncon_max) X(con_pair, ncon_max) X(con_efc, ncon_max) X(hcone, 16 * ncon_max) X(J, nefc_max * nv)       \
-  X(efc_pos, nefc_max) X(efc_D, nefc_max) X(efc_R, nefc_max) X(efc_aref, nefc_max) X(efc_floss, nefc_max)          \
-  X(efc_force, nefc_max) X(efc_jar, nefc_max) X(efc_jv, nefc_max) X(efc_imp, nefc_max) X(efc_type, nefc_max)       \
-  X(efc_id, nefc_max) X(efc_state, nefc_max) X(nsB, 3 * nv) X(nsS, 32)
+  X(Mv, nv) X(wvec, nv) X(con_pos, 3 * ncon_max) X(con_normal, 3 * ncon_max) X(con_dist, ncon_max)                 \
+  X(con_mu, ncon_max) X(con_pair, ncon_max) X(con_efc, ncon_max) X(nsB, 3 * nv) X(nsS, 32)
+#define MGS_LAYOUT_TRANSIENT(X)                                                                                    \
+  X(xipos, 3 * nbody) X(ximat, 9 * nbody) X(xanchor, 3 * njnt) X(xaxis, 3 * njnt) X(gxpos, 3 * ncgeom)             \
+  X(gxmat, 9 * ncgeom) X(cinert, 10 * nbody) X(crb, 10 * nbody) X(cdof_dot, 6 * nv) X(cvel, 6 * nbody)             \
+  X(cacc, 6 * nbody) X(cfrc, 6 * nbody)
+#define MGS_LAYOUT_SOLVER(X)                                                                                       \
+  X(J, nefc_max * nv) X(efc_D, nefc_max) X(efc_R, nefc_max) X(efc_aref, nefc_max) X(efc_aux, nefc_max)             \
+  X(efc_force, nefc_max) X(efc_jar, nefc_max) X(efc_jv, nefc_max) X(efc_tsi, nefc_max)
+#define MGS_LAYOUT_FIELDS(X) MGS_LAYOUT_PERSIST(X) MGS_LAYOUT_TRANSIENT(X) MGS_LAYOUT_SOLVER(X)
 
 struct Layout {
 #define X(name, cnt) int name;
@@ -106,9 +125,14 @@ static inline void layout_compute(Layout *L, int nq, int nv, int nu, int nbody, 
                                   int ncon_max, int nefc_max) {
   int off = 0;
 #define X(name, cnt) L->name = off; off += ((cnt) + 3) & ~3;
-  MGS_LAYOUT_FIELDS(X)
+  MGS_LAYOUT_PERSIST(X)
+  const int overlay = off;
+  MGS_LAYOUT_TRANSIENT(X)
+  const int end_t = off;
+  off = overlay;
+  MGS_LAYOUT_SOLVER(X)
 #undef X
-  L->total = off;
+  L->total = off > end_t ? off : end_t;
   L->ncon_max = ncon_max;
   L->nefc_max = nefc_max;
 }

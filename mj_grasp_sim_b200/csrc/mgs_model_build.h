@@ -86,6 +86,10 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
   PR_(actuator_gainprm, 3 * nu); PR_(actuator_biasprm, 3 * nu); PR_(actuator_ctrlrange, 2 * nu); PR_(actuator_forcerange, 2 * nu); PR_(actuator_gear, nu);
   PI_(eq_type, d->neq); PI_(eq_obj1id, d->neq); PI_(eq_obj2id, d->neq); PI_(eq_active, d->neq);
   m.eq_rowadr = put<int>(b, rowadr.data(), d->neq);
+  std::vector<int> tri;
+  for (int a = 0; a < nv; a++)
+    for (int c = 0; c <= a; c++) tri.push_back((a << 8) | c);
+  m.tri_ab = put<int>(b, tri.data(), tri.size());
   PR_(eq_data, 11 * d->neq); PR_(eq_solref, 2 * d->neq); PR_(eq_solimp, 5 * d->neq);
   PR_(mocap_pos0, 3 * d->nmocap); PR_(mocap_quat0, 4 * d->nmocap);
 #undef PI_
@@ -96,8 +100,11 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
   for (int j = 0; j < nj; j++) nlim += d->jnt_limited[j] ? 1 : 0;
   int maxdim = 1;
   for (int p = 0; p < np; p++) if (d->pair_condim[p] > maxdim) maxdim = d->pair_condim[p];
-  out.ncon_max = 40;
-  out.nefc_max = ne + nfr + nlim + out.ncon_max * maxdim;
+  // capacities (contacts beyond them are dropped and flagged in the diagnostics): 32 contacts,
+  // of which at most 24 may have the largest cone dimension
+  out.ncon_max = 32;
+  out.nefc_max = ne + nfr + nlim + 24 * maxdim;
+  if (out.nefc_max < ne + nfr + nlim + 32 * 3) out.nefc_max = ne + nfr + nlim + 32 * 3;
   return true;
 }
 

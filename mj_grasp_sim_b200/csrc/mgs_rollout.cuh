@@ -14,25 +14,30 @@ static inline int mgs_diag_stride(int nv, int nbody, int ncon_max, int nefc_max)
   return MGS_DIAG_HEADER + 3 * nv + nv * nv + 7 * nbody + 5 * ncon_max + 4 * nefc_max;
 }
 
-MGS_DEV void reset_w(const DevModel &m, Env &e) {
-  PFOR(i, m.nq) e.qpos[i] = LDG(m.qpos0 + i);
-  PFOR(i, m.nv) { e.qvel[i] = 0; e.qacc_ws[i] = 0; }
-  PFOR(i, m.nu) e.ctrl[i] = 0;
-  PFOR(i, m.nmocap) {
-    for (int k = 0; k < 3; k++) e.mocap[7 * i + k] = LDG(m.mocap_pos0 + 3 * i + k);
-    for (int k = 0; k < 4; k++) e.mocap[7 * i + 3 + k] = LDG(m.mocap_quat0 + 4 * i + k);
+MGS_DEVN void reset_w(Env &e) {
+  #pragma unroll 1
+  PFOR(i, MD.nq) EF(qpos)[i] = LDG(MD.qpos0 + i);
+  #pragma unroll 1
+  PFOR(i, MD.nv) { EF(qvel)[i] = 0; EF(qacc_ws)[i] = 0; }
+  #pragma unroll 1
+  PFOR(i, MD.nu) EF(ctrl)[i] = 0;
+  #pragma unroll 1
+  PFOR(i, MD.nmocap) {
+    for (int k = 0; k < 3; k++) EF(mocap)[7 * i + k] = LDG(MD.mocap_pos0 + 3 * i + k);
+    for (int k = 0; k < 4; k++) EF(mocap)[7 * i + 3 + k] = LDG(MD.mocap_quat0 + 4 * i + k);
   }
   e.bad = 0; e.overflow = 0; e.ncon = 0; e.nefc = 0;
   WSYNC();
 }
 
 // set_qpos(joints) + set_pose(base): simualtion.py:45-49, gripper/base.py:48-59
-MGS_DEV void place_w(const RolloutParams &prm, Env &e, const float *pose7, const float *joints) {
-  if (joints) PFOR(k, prm.nj) e.qpos[prm.joint_qposadr[k]] = (real)LDG(joints + k);
+MGS_DEVN void place_w(Env &e, const float *pose7, const float *joints) {
+  if (joints) PFOR(k, PRM.nj) EF(qpos)[PRM.joint_qposadr[k]] = (real)LDG(joints + k);
+  #pragma unroll 1
   PFOR(k, 7) {
     real v = (real)LDG(pose7 + k);
-    e.qpos[prm.base_qposadr + k] = v;
-    e.mocap[k] = v;
+    EF(qpos)[PRM.base_qposadr + k] = v;
+    EF(mocap)[k] = v;
   }
   WSYNC();
 }
@@ -40,126 +45,153 @@ MGS_DEV void place_w(const RolloutParams &prm, Env &e, const float *pose7, const
 MGS_DEV real round32(real x) { return (real)(float)x; }
 
 // linear mocap ramp of n steps from start to target (targets are never quite reached: t/n, t<n)
-MGS_DEV int ramp_w(const DevModel &m, Env &e, const real *start, const real *target, int n, int check_every, int *steps) {
+MGS_DEVN int ramp_w(Env &e, const real *start, const real *target, int n, int check_every, int *steps) {
+  #pragma unroll 1
   for (int t = 0; t < n; t++) {
     real f = (real)t / (real)n;
-    PFOR(k, 3) e.mocap[k] = start[k] + (target[k] - start[k]) * f;
+    #pragma unroll 1
+    PFOR(k, 3) EF(mocap)[k] = start[k] + (target[k] - start[k]) * f;
     WSYNC();
-    if (step_w(m, e, 1, steps)) return 1;
-    if (check_every > 0 && t > 0 && t % check_every == 0 && !contact_with_object_w(m, e)) return 1;
+    if (step_w(e, 1, steps)) return 1;
+    if (check_every > 0 && t > 0 && t % check_every == 0 && !contact_with_object_w(e)) return 1;
   }
   return 0;
 }
 
-MGS_DEVN int stability_program_w(const DevModel &m, Env &e, const RolloutParams &prm, const float *pose7, const float *joints, int *steps) {
-  reset_w(m, e);
-  place_w(prm, e, pose7, joints);
-  forward_w(m, e);
+MGS_DEVN int stability_program_w(Env &e, const float *pose7, const float *joints, int *steps) {
+  reset_w(e);
+  place_w(e, pose7, joints);
+  forward_w(e);
+  MGS_STAGE_BARRIER();  // the integrate slot of a step (keeps the CTA stage-aligned)
   // close_gripper_at (panda.py:225-241 and the five siblings): mocap <- pose, ctrl <- close signal
-  if (prm.repose_on_close) place_w(prm, e, pose7, (const float *)0);
-  PFOR(k, 7) e.mocap[k] = (real)LDG(pose7 + k);
-  PFOR(u, m.nu) e.ctrl[u] = prm.close_ctrl[u];
+  if (PRM.repose_on_close) place_w(e, pose7, (const float *)0);
+  #pragma unroll 1
+  PFOR(k, 7) EF(mocap)[k] = (real)LDG(pose7 + k);
+  #pragma unroll 1
+  PFOR(u, MD.nu) EF(ctrl)[u] = PRM.close_ctrl[u];
   WSYNC();
-  if (step_w(m, e, prm.nstep_close, steps)) return 0;
-  if (!contact_with_object_w(m, e)) return 0;
+  if (step_w(e, PRM.nstep_close, steps)) return 0;
+  if (!contact_with_object_w(e)) return 0;
   // lift (:205-226)
   real start[3], target[3];
-  copy3(start, e.mocap);
+  copy3(start, EF(mocap));
   copy3(target, start);
-  target[2] = start[2] + prm.lift_dist;
+  target[2] = start[2] + PRM.lift_dist;
   WSYNC();
-  if (ramp_w(m, e, start, target, prm.nstep_lift, 100, steps)) return 0;
-  if (!contact_with_object_w(m, e)) return 0;
+  if (ramp_w(e, start, target, PRM.nstep_lift, 100, steps)) return 0;
+  if (!contact_with_object_w(e)) return 0;
   // shake (:229-276); current_mocap_pose passes through SE3Pose => float32 pos/quat/rotation
   real p32[3], q32[4], Rm[9], tb[3], tr[3], tl[3];
-  for (int k = 0; k < 3; k++) p32[k] = round32(e.mocap[k]);
-  for (int k = 0; k < 4; k++) q32[k] = round32(e.mocap[3 + k]);
+  for (int k = 0; k < 3; k++) p32[k] = round32(EF(mocap)[k]);
+  for (int k = 0; k < 4; k++) q32[k] = round32(EF(mocap)[3 + k]);
   normquat(q32);
   quat2mat(Rm, q32);
   for (int k = 0; k < 9; k++) Rm[k] = round32(Rm[k]);
-  for (int k = 0; k < 3; k++) tb[k] = p32[k] - Rm[3 * k + 2] * prm.shake_dist;  // back = R (0,0,-1)
-  copy3(start, e.mocap);
+  for (int k = 0; k < 3; k++) tb[k] = p32[k] - Rm[3 * k + 2] * PRM.shake_dist;  // back = R (0,0,-1)
+  copy3(start, EF(mocap));
   WSYNC();
-  if (ramp_w(m, e, start, tb, prm.shake_steps, 0, steps)) return 0;
-  if (!contact_with_object_w(m, e)) return 0;
-  for (int k = 0; k < 3; k++) tr[k] = tb[k] + Rm[3 * k + 1] * prm.shake_dist;  // right = R (0,1,0)
-  copy3(start, e.mocap);
+  if (ramp_w(e, start, tb, PRM.shake_steps, 0, steps)) return 0;
+  if (!contact_with_object_w(e)) return 0;
+  for (int k = 0; k < 3; k++) tr[k] = tb[k] + Rm[3 * k + 1] * PRM.shake_dist;  // right = R (0,1,0)
+  copy3(start, EF(mocap));
   WSYNC();
-  if (ramp_w(m, e, start, tr, prm.shake_steps, 0, steps)) return 0;
-  if (!contact_with_object_w(m, e)) return 0;
+  if (ramp_w(e, start, tr, PRM.shake_steps, 0, steps)) return 0;
+  if (!contact_with_object_w(e)) return 0;
   // left: restarts from the START of the right move (reference quirk: ~2 cm mocap jump at t=0)
-  for (int k = 0; k < 3; k++) tl[k] = start[k] - Rm[3 * k + 1] * (2 * prm.shake_dist);
-  if (ramp_w(m, e, start, tl, 2 * prm.shake_steps, 0, steps)) return 0;
-  if (!contact_with_object_w(m, e)) return 0;
+  for (int k = 0; k < 3; k++) tl[k] = start[k] - Rm[3 * k + 1] * (2 * PRM.shake_dist);
+  if (ramp_w(e, start, tl, 2 * PRM.shake_steps, 0, steps)) return 0;
+  if (!contact_with_object_w(e)) return 0;
   return 1;
 }
 
-MGS_DEV void write_diag_w(const DevModel &m, const Env &e, real *o) {
-  const int nv = m.nv;
+MGS_DEVN void write_diag_w(const Env &e, real *o) {
+  const int nv = MD.nv;
+  #pragma unroll 1
   PFOR(k, 1) { o[0] = (real)e.ncon; o[1] = (real)e.nefc; o[2] = (real)e.niter; o[3] = (real)e.bad; o[4] = (real)e.overflow; o[5] = (real)e.ne; o[6] = (real)e.nf; o[7] = (real)e.nl; }
   real *p = o + MGS_DIAG_HEADER;
-  PFOR(d, nv) { p[d] = e.qacc[d]; p[nv + d] = e.qacc_smooth[d]; p[2 * nv + d] = e.qfrc_smooth[d]; }
+  #pragma unroll 1
+  PFOR(d, nv) { p[d] = EF(qacc)[d]; p[nv + d] = EF(qacc_smooth)[d]; p[2 * nv + d] = EF(qfrc_smooth)[d]; }
   p += 3 * nv;
-  PFOR(i, nv * nv) p[i] = e.M[i];
+  #pragma unroll 1
+  PFOR(i, nv * nv) p[i] = EF(M)[i];
   p += nv * nv;
-  PFOR(i, 3 * m.nbody) p[i] = e.xpos[i];
-  p += 3 * m.nbody;
-  PFOR(i, 4 * m.nbody) p[i] = e.xquat[i];
-  p += 4 * m.nbody;
+  #pragma unroll 1
+  PFOR(i, 3 * MD.nbody) p[i] = EF(xpos)[i];
+  p += 3 * MD.nbody;
+  #pragma unroll 1
+  PFOR(i, 4 * MD.nbody) p[i] = EF(xquat)[i];
+  p += 4 * MD.nbody;
+  #pragma unroll 1
   PFOR(c, e.ncon_max) {
     int ok = c < e.ncon;
-    p[5 * c] = ok ? e.con_dist[c] : 0;
-    for (int k = 0; k < 3; k++) p[5 * c + 1 + k] = ok ? e.con_pos[3 * c + k] : 0;
-    p[5 * c + 4] = ok ? (real)IARR(e.con_pair)[c] : -1;
+    p[5 * c] = ok ? EF(con_dist)[c] : 0;
+    for (int k = 0; k < 3; k++) p[5 * c + 1 + k] = ok ? EF(con_pos)[3 * c + k] : 0;
+    p[5 * c + 4] = ok ? (real)IARR(EF(con_pair))[c] : -1;
   }
   p += 5 * e.ncon_max;
+  #pragma unroll 1
   PFOR(i, e.nefc_max) {
     int ok = i < e.nefc;
-    p[4 * i] = ok ? e.efc_aref[i] : 0; p[4 * i + 1] = ok ? e.efc_D[i] : 0;
-    p[4 * i + 2] = ok ? e.efc_force[i] : 0; p[4 * i + 3] = ok ? e.efc_jar[i] : 0;
+    p[4 * i] = ok ? EF(efc_aref)[i] : 0; p[4 * i + 1] = ok ? EF(efc_D)[i] : 0;
+    p[4 * i + 2] = ok ? EF(efc_force)[i] : 0; p[4 * i + 3] = ok ? EF(efc_jar)[i] : 0;
   }
 }
 
 // run one candidate / environment on this warp
-MGS_DEVN void run_env_w(const DevModel &m, Env &e, const RolloutParams &prm, const BatchIO &io, int env) {
+MGS_DEVN void run_env_w(Env &e, int env) {
   int steps = 0;
-  if (prm.mode == MGS_MODE_STEP) {
-    const real *in = io.state_in + (size_t)env * io.state_stride;
+  if (PRM.mode == MGS_MODE_STEP) {
+    const real *in = IO.state_in + (size_t)env * IO.state_stride;
     e.bad = 0; e.overflow = 0;
-    PFOR(i, m.nq) e.qpos[i] = in[i];
-    PFOR(i, m.nv) { e.qvel[i] = in[m.nq + i]; e.qacc_ws[i] = in[m.nq + m.nv + i]; }
-    PFOR(i, m.nu) e.ctrl[i] = in[m.nq + 2 * m.nv + i];
-    PFOR(i, 7 * m.nmocap) e.mocap[i] = in[m.nq + 2 * m.nv + m.nu + i];
+    #pragma unroll 1
+    PFOR(i, MD.nq) EF(qpos)[i] = in[i];
+    #pragma unroll 1
+    PFOR(i, MD.nv) { EF(qvel)[i] = in[MD.nq + i]; EF(qacc_ws)[i] = in[MD.nq + MD.nv + i]; }
+    #pragma unroll 1
+    PFOR(i, MD.nu) EF(ctrl)[i] = in[MD.nq + 2 * MD.nv + i];
+    #pragma unroll 1
+    PFOR(i, 7 * MD.nmocap) EF(mocap)[i] = in[MD.nq + 2 * MD.nv + MD.nu + i];
     WSYNC();
-    if (prm.nstep > 0) step_w(m, e, prm.nstep, &steps);
-    else forward_w(m, e);
-    real *out = io.state_out + (size_t)env * io.state_stride;
-    PFOR(i, m.nq) out[i] = e.qpos[i];
-    PFOR(i, m.nv) { out[m.nq + i] = e.qvel[i]; out[m.nq + m.nv + i] = e.qacc_ws[i]; }
-    PFOR(i, m.nu) out[m.nq + 2 * m.nv + i] = e.ctrl[i];
-    PFOR(i, 7 * m.nmocap) out[m.nq + 2 * m.nv + m.nu + i] = e.mocap[i];
-    if (io.diag_out) write_diag_w(m, e, io.diag_out + (size_t)env * io.diag_stride);
-    PFOR(k, 1) { if (io.labels) io.labels[env] = (uint8_t)(e.bad ? 0 : 1); if (io.steps) io.steps[env] = steps; }
+    if (PRM.nstep > 0) step_w(e, PRM.nstep, &steps);
+    else { forward_w(e); MGS_STAGE_BARRIER(); }
+    real *out = IO.state_out + (size_t)env * IO.state_stride;
+    #pragma unroll 1
+    PFOR(i, MD.nq) out[i] = EF(qpos)[i];
+    #pragma unroll 1
+    PFOR(i, MD.nv) { out[MD.nq + i] = EF(qvel)[i]; out[MD.nq + MD.nv + i] = EF(qacc_ws)[i]; }
+    #pragma unroll 1
+    PFOR(i, MD.nu) out[MD.nq + 2 * MD.nv + i] = EF(ctrl)[i];
+    #pragma unroll 1
+    PFOR(i, 7 * MD.nmocap) out[MD.nq + 2 * MD.nv + MD.nu + i] = EF(mocap)[i];
+    if (IO.diag_out) write_diag_w(e, IO.diag_out + (size_t)env * IO.diag_stride);
+    #pragma unroll 1
+    PFOR(k, 1) { if (IO.labels) IO.labels[env] = (uint8_t)(e.bad ? 0 : 1); if (IO.steps) IO.steps[env] = steps; }
     WSYNC();
     return;
   }
-  const float *pose7 = io.pose7 + (size_t)env * 7, *joints = io.joints + (size_t)env * prm.nj;
+  const float *pose7 = IO.pose7 + (size_t)env * 7, *joints = IO.joints + (size_t)env * PRM.nj;
   int label;
-  if (prm.mode == MGS_MODE_COLLISION) {
-    reset_w(m, e);
-    place_w(prm, e, pose7, joints);
-    forward_w(m, e);
+  if (PRM.mode == MGS_MODE_COLLISION) {
+    reset_w(e);
+    place_w(e, pose7, joints);
+    forward_w(e);
+    MGS_STAGE_BARRIER();
     label = (e.ncon == 0);  // collision-free mask: no contact of any kind (check_contact, :306-307)
   } else {
-    label = stability_program_w(m, e, prm, pose7, joints, &steps);
+    label = stability_program_w(e, pose7, joints, &steps);
   }
-  PFOR(k, 1) { io.labels[env] = (uint8_t)label; if (io.steps) io.steps[env] = steps; }
-  if (io.state_out) {
-    real *out = io.state_out + (size_t)env * io.state_stride;
-    PFOR(i, m.nq) out[i] = e.qpos[i];
-    PFOR(i, m.nv) { out[m.nq + i] = e.qvel[i]; out[m.nq + m.nv + i] = e.qacc_ws[i]; }
-    PFOR(i, m.nu) out[m.nq + 2 * m.nv + i] = e.ctrl[i];
-    PFOR(i, 7 * m.nmocap) out[m.nq + 2 * m.nv + m.nu + i] = e.mocap[i];
+  #pragma unroll 1
+  PFOR(k, 1) { IO.labels[env] = (uint8_t)label; if (IO.steps) IO.steps[env] = steps; }
+  if (IO.state_out) {
+    real *out = IO.state_out + (size_t)env * IO.state_stride;
+    #pragma unroll 1
+    PFOR(i, MD.nq) out[i] = EF(qpos)[i];
+    #pragma unroll 1
+    PFOR(i, MD.nv) { out[MD.nq + i] = EF(qvel)[i]; out[MD.nq + MD.nv + i] = EF(qacc_ws)[i]; }
+    #pragma unroll 1
+    PFOR(i, MD.nu) out[MD.nq + 2 * MD.nv + i] = EF(ctrl)[i];
+    #pragma unroll 1
+    PFOR(i, 7 * MD.nmocap) out[MD.nq + 2 * MD.nv + MD.nu + i] = EF(mocap)[i];
   }
   WSYNC();
 }

@@ -94,39 +94,56 @@ MGS_DEV void ld3(real *r, const real *g) { r[0] = LDG(g); r[1] = LDG(g + 1); r[2
 MGS_DEV void ld4(real *r, const real *g) { r[0] = LDG(g); r[1] = LDG(g + 1); r[2] = LDG(g + 2); r[3] = LDG(g + 3); }
 
 // ---------------------------------------------------------------------------------- environment
+// Model constants, the scratch layout, the rollout parameters and the I/O pointers live in
+// __constant__ memory (uniform loads through the constant cache; nothing is copied to the stack when
+// the non-inlined stage functions are called).
+struct KernelConsts { DevModel m; Layout L; RolloutParams prm; BatchIO io; };
+#ifdef MGS_HOST
+static KernelConsts g_k;
+#define MGS_K g_k
+#else
+__constant__ KernelConsts c_k;
+#define MGS_K c_k
+#endif
+#define MD (MGS_K.m)
+#define LY (MGS_K.L)
+#define PRM (MGS_K.prm)
+#define IO (MGS_K.io)
+// per-environment scratch arrays: slice base + constant offset
+#define EF(name) (e.base + LY.name)
 struct Env {
-#define X(name, cnt) real *name;
-  MGS_LAYOUT_FIELDS(X)
-#undef X
+  real *base;
   int ncon, nefc, ne, nf, nl, niter, bad, ncon_max, nefc_max, overflow;
 };
-MGS_DEV void env_bind(Env &e, real *base, const Layout &L) {
-#define X(name, cnt) e.name = base + L.name;
-  MGS_LAYOUT_FIELDS(X)
-#undef X
+MGS_DEV void env_bind(Env &e, real *base) {
+  e.base = base;
   e.ncon = e.nefc = e.ne = e.nf = e.nl = e.niter = e.bad = e.overflow = 0;
-  e.ncon_max = L.ncon_max;
-  e.nefc_max = L.nefc_max;
+  e.ncon_max = LY.ncon_max;
+  e.nefc_max = LY.nefc_max;
 }
 #define IARR(p) ((int *)(p))
 
 // ---------------------------------------------------------------------------------- dense linear algebra (warp)
 // In-place lower Cholesky of the n x n matrix A (row-major, only the lower triangle is read).
 MGS_DEVN void chol_factor_w(real *A, int n) {
+  #pragma unroll 1
   for (int j = 0; j < n; j++) {
     WSYNC();
     real d = A[j * n + j];
     d = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL);
     real inv = R_(1.0) / d;
     WSYNC();
+    #pragma unroll 1
     PFOR(i, n) {
       if (i == j) A[j * n + j] = d;
       else if (i > j) A[i * n + j] *= inv;
     }
     WSYNC();
+    #pragma unroll 1
     PFOR(i, n) {
       if (i > j) {
         real lij = A[i * n + j];
+        #pragma unroll 1
         for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
       }
     }
@@ -135,19 +152,23 @@ MGS_DEVN void chol_factor_w(real *A, int n) {
 }
 // x <- (L L')^-1 x, warp-cooperative (column oriented substitution)
 MGS_DEVN void chol_solve_w(const real *L, real *x, int n) {
+  #pragma unroll 1
   for (int k = 0; k < n; k++) {
     WSYNC();
     real xk = x[k] / L[k * n + k];
     WSYNC();
+    #pragma unroll 1
     PFOR(i, n) {
       if (i == k) x[k] = xk;
       else if (i > k) x[i] -= L[i * n + k] * xk;
     }
   }
+  #pragma unroll 1
   for (int k = n - 1; k >= 0; k--) {
     WSYNC();
     real xk = x[k] / L[k * n + k];
     WSYNC();
+    #pragma unroll 1
     PFOR(i, n) {
       if (i == k) x[k] = xk;
       else if (i < k) x[i] -= L[k * n + i] * xk;
@@ -157,14 +178,19 @@ MGS_DEVN void chol_solve_w(const real *L, real *x, int n) {
 }
 // Ainv <- (L L')^-1, one column per lane (serial substitution inside the lane)
 MGS_DEVN void chol_inverse_w(const real *L, real *Ainv, int n) {
+  #pragma unroll 1
   PFOR(c, n) {
+    #pragma unroll 1
     for (int i = 0; i < n; i++) {
       real s = (i == c) ? R_(1.0) : R_(0.0);
+      #pragma unroll 1
       for (int k = 0; k < i; k++) s -= L[i * n + k] * Ainv[k * n + c];
       Ainv[i * n + c] = s / L[i * n + i];
     }
+    #pragma unroll 1
     for (int i = n - 1; i >= 0; i--) {
       real s = Ainv[i * n + c];
+      #pragma unroll 1
       for (int k = i + 1; k < n; k++) s -= L[k * n + i] * Ainv[k * n + c];
       Ainv[i * n + c] = s / L[i * n + i];
     }
@@ -172,9 +198,11 @@ MGS_DEVN void chol_inverse_w(const real *L, real *Ainv, int n) {
   WSYNC();
 }
 // y <- A x for a dense n x n A (lane per row)
-MGS_DEV void matvec_w(real *y, const real *A, const real *x, int n) {
+MGS_DEVN void matvec_w(real *y, const real *A, const real *x, int n) {
+  #pragma unroll 1
   PFOR(i, n) {
     real t = 0;
+    #pragma unroll 1
     for (int j = 0; j < n; j++) t += A[i * n + j] * x[j];
     y[i] = t;
   }
@@ -182,50 +210,54 @@ MGS_DEV void matvec_w(real *y, const real *A, const real *x, int n) {
 }
 
 // ---------------------------------------------------------------------------------- kinematics
-MGS_DEVN void kinematics_w(const DevModel &m, Env &e) {
+MGS_DEVN void kinematics_w(Env &e) {
+  #pragma unroll 1
   PFOR(i, 1) {
-    e.xpos[0] = e.xpos[1] = e.xpos[2] = 0;
-    e.xquat[0] = 1; e.xquat[1] = e.xquat[2] = e.xquat[3] = 0;
-    for (int k = 0; k < 9; k++) e.xmat[k] = e.ximat[k] = (k % 4 == 0) ? R_(1.0) : R_(0.0);
-    e.xipos[0] = e.xipos[1] = e.xipos[2] = 0;
+    EF(xpos)[0] = EF(xpos)[1] = EF(xpos)[2] = 0;
+    EF(xquat)[0] = 1; EF(xquat)[1] = EF(xquat)[2] = EF(xquat)[3] = 0;
+    for (int k = 0; k < 9; k++) EF(xmat)[k] = EF(ximat)[k] = (k % 4 == 0) ? R_(1.0) : R_(0.0);
+    EF(xipos)[0] = EF(xipos)[1] = EF(xipos)[2] = 0;
   }
   WSYNC();
-  for (int lvl = 1; lvl <= m.maxdepth; lvl++) {
-    PFOR(b, m.nbody) {
-      if (LDG(m.body_depth + b) != lvl) continue;
-      int p = LDG(m.body_parentid + b);
+  #pragma unroll 1
+  for (int lvl = 1; lvl <= MD.maxdepth; lvl++) {
+    #pragma unroll 1
+    PFOR(b, MD.nbody) {
+      if (LDG(MD.body_depth + b) != lvl) continue;
+      int p = LDG(MD.body_parentid + b);
       real xp[3], xq[4], t[3], bq[4];
-      int mid = LDG(m.body_mocapid + b);
+      int mid = LDG(MD.body_mocapid + b);
       if (mid >= 0) {
-        copy3(xp, e.mocap + 7 * mid);
-        xq[0] = e.mocap[7 * mid + 3]; xq[1] = e.mocap[7 * mid + 4]; xq[2] = e.mocap[7 * mid + 5]; xq[3] = e.mocap[7 * mid + 6];
+        copy3(xp, EF(mocap) + 7 * mid);
+        xq[0] = EF(mocap)[7 * mid + 3]; xq[1] = EF(mocap)[7 * mid + 4]; xq[2] = EF(mocap)[7 * mid + 5]; xq[3] = EF(mocap)[7 * mid + 6];
         normquat(xq);
       } else {
-        ld3(t, m.body_pos + 3 * b);
-        mulmatvec3(xp, e.xmat + 9 * p, t);
-        add3(xp, xp, e.xpos + 3 * p);
-        ld4(bq, m.body_quat + 4 * b);
-        mulquat(xq, e.xquat + 4 * p, bq);
+        ld3(t, MD.body_pos + 3 * b);
+        mulmatvec3(xp, EF(xmat) + 9 * p, t);
+        add3(xp, xp, EF(xpos) + 3 * p);
+        ld4(bq, MD.body_quat + 4 * b);
+        mulquat(xq, EF(xquat) + 4 * p, bq);
       }
-      int ja = LDG(m.body_jntadr + b), jn = LDG(m.body_jntnum + b);
+      int ja = LDG(MD.body_jntadr + b), jn = LDG(MD.body_jntnum + b);
+      #pragma unroll 1
       for (int j = ja; j < ja + jn; j++) {
-        int qa = LDG(m.jnt_qposadr + j), jt = LDG(m.jnt_type + j);
-        real *anchor = e.xanchor + 3 * j, *axis = e.xaxis + 3 * j;
+        int qa = LDG(MD.jnt_qposadr + j), jt = LDG(MD.jnt_type + j);
+        real *anchor = EF(xanchor) + 3 * j, *axis = EF(xaxis) + 3 * j;
         if (jt == JNT_FREE) {
-          copy3(xp, e.qpos + qa);
-          normquat(e.qpos + qa + 3);
-          xq[0] = e.qpos[qa + 3]; xq[1] = e.qpos[qa + 4]; xq[2] = e.qpos[qa + 5]; xq[3] = e.qpos[qa + 6];
+          copy3(xp, EF(qpos) + qa);
+          normquat(EF(qpos) + qa + 3);
+          xq[0] = EF(qpos)[qa + 3]; xq[1] = EF(qpos)[qa + 4]; xq[2] = EF(qpos)[qa + 5]; xq[3] = EF(qpos)[qa + 6];
           copy3(anchor, xp);
           axis[0] = 0; axis[1] = 0; axis[2] = 1;
           continue;
         }
         real Rm[9], ja3[3], jp3[3];
         quat2mat(Rm, xq);
-        ld3(ja3, m.jnt_axis + 3 * j); ld3(jp3, m.jnt_pos + 3 * j);
+        ld3(ja3, MD.jnt_axis + 3 * j); ld3(jp3, MD.jnt_pos + 3 * j);
         mulmatvec3(axis, Rm, ja3);
         mulmatvec3(anchor, Rm, jp3);
         add3(anchor, anchor, xp);
-        real dq = e.qpos[qa] - LDG(m.qpos0 + qa);
+        real dq = EF(qpos)[qa] - LDG(MD.qpos0 + qa);
         if (jt == JNT_SLIDE) {
           addscl3(xp, axis, dq);
         } else {
@@ -238,28 +270,29 @@ MGS_DEVN void kinematics_w(const DevModel &m, Env &e) {
         }
       }
       normquat(xq);
-      copy3(e.xpos + 3 * b, xp);
-      e.xquat[4 * b] = xq[0]; e.xquat[4 * b + 1] = xq[1]; e.xquat[4 * b + 2] = xq[2]; e.xquat[4 * b + 3] = xq[3];
-      quat2mat(e.xmat + 9 * b, xq);
-      ld3(t, m.body_ipos + 3 * b);
-      mulmatvec3(t, e.xmat + 9 * b, t);
-      add3(e.xipos + 3 * b, xp, t);
-      ld4(bq, m.body_iquat + 4 * b);
+      copy3(EF(xpos) + 3 * b, xp);
+      EF(xquat)[4 * b] = xq[0]; EF(xquat)[4 * b + 1] = xq[1]; EF(xquat)[4 * b + 2] = xq[2]; EF(xquat)[4 * b + 3] = xq[3];
+      quat2mat(EF(xmat) + 9 * b, xq);
+      ld3(t, MD.body_ipos + 3 * b);
+      mulmatvec3(t, EF(xmat) + 9 * b, t);
+      add3(EF(xipos) + 3 * b, xp, t);
+      ld4(bq, MD.body_iquat + 4 * b);
       real qi[4];
       mulquat(qi, xq, bq);
-      quat2mat(e.ximat + 9 * b, qi);
+      quat2mat(EF(ximat) + 9 * b, qi);
     }
     WSYNC();
   }
-  PFOR(g, m.ncgeom) {
-    int b = LDG(m.cgeom_bodyid + g);
+  #pragma unroll 1
+  PFOR(g, MD.ncgeom) {
+    int b = LDG(MD.cgeom_bodyid + g);
     real t[3], q[4], gq[4];
-    ld3(t, m.cgeom_pos + 3 * g);
-    mulmatvec3(t, e.xmat + 9 * b, t);
-    add3(e.gxpos + 3 * g, e.xpos + 3 * b, t);
-    ld4(gq, m.cgeom_quat + 4 * g);
-    mulquat(q, e.xquat + 4 * b, gq);
-    quat2mat(e.gxmat + 9 * g, q);
+    ld3(t, MD.cgeom_pos + 3 * g);
+    mulmatvec3(t, EF(xmat) + 9 * b, t);
+    add3(EF(gxpos) + 3 * g, EF(xpos) + 3 * b, t);
+    ld4(gq, MD.cgeom_quat + 4 * g);
+    mulquat(q, EF(xquat) + 4 * b, gq);
+    quat2mat(EF(gxmat) + 9 * g, q);
   }
   WSYNC();
 }
@@ -291,28 +324,31 @@ MGS_DEV void cross_force(real *res, const real *vel, const real *f) {
 }
 
 // CoM frames, composite inertias, motion axes, mass matrix, M^-1
-MGS_DEVN void inertia_w(const DevModel &m, Env &e) {
-  const int nb = m.nbody, nv = m.nv;
+MGS_DEVN void inertia_w(Env &e) {
+  const int nb = MD.nbody, nv = MD.nv;
   // centre of mass of every kinematic tree (origin of its spatial quantities)
+  #pragma unroll 1
   PFOR(b, nb) {
-    if (b == 0 || LDG(m.body_parentid + b) != 0) continue;
-    real c[3] = {0, 0, 0}, mt = LDG(m.body_subtreemass + b);
-    if (mt < MGS_MINVAL) copy3(c, e.xipos + 3 * b);
+    if (b == 0 || LDG(MD.body_parentid + b) != 0) continue;
+    real c[3] = {0, 0, 0}, mt = LDG(MD.body_subtreemass + b);
+    if (mt < MGS_MINVAL) copy3(c, EF(xipos) + 3 * b);
     else {
+      #pragma unroll 1
       for (int k = b; k < nb; k++)
-        if (LDG(m.body_rootid + k) == b) addscl3(c, e.xipos + 3 * k, LDG(m.body_mass + k));
+        if (LDG(MD.body_rootid + k) == b) addscl3(c, EF(xipos) + 3 * k, LDG(MD.body_mass + k));
       scl3(c, c, R_(1.0) / mt);
     }
-    copy3(e.rootcom + 3 * b, c);
+    copy3(EF(rootcom) + 3 * b, c);
   }
   WSYNC();
+  #pragma unroll 1
   PFOR(b, nb) {
-    real *ci = e.cinert + 10 * b;
+    real *ci = EF(cinert) + 10 * b;
     if (b == 0) { for (int k = 0; k < 10; k++) ci[k] = 0; continue; }
-    real dif[3], diag[3], mass = LDG(m.body_mass + b);
-    const real *Rm = e.ximat + 9 * b;
-    sub3(dif, e.xipos + 3 * b, e.rootcom + 3 * LDG(m.body_rootid + b));
-    ld3(diag, m.body_inertia + 3 * b);
+    real dif[3], diag[3], mass = LDG(MD.body_mass + b);
+    const real *Rm = EF(ximat) + 9 * b;
+    sub3(dif, EF(xipos) + 3 * b, EF(rootcom) + 3 * LDG(MD.body_rootid + b));
+    ld3(diag, MD.body_inertia + 3 * b);
     real I[6];  // xx yy zz xy xz yz
     I[0] = Rm[0] * diag[0] * Rm[0] + Rm[1] * diag[1] * Rm[1] + Rm[2] * diag[2] * Rm[2];
     I[1] = Rm[3] * diag[0] * Rm[3] + Rm[4] * diag[1] * Rm[4] + Rm[5] * diag[2] * Rm[5];
@@ -328,161 +364,186 @@ MGS_DEVN void inertia_w(const DevModel &m, Env &e) {
     ci[4] = I[4] - mass * dif[0] * dif[2];
     ci[5] = I[5] - mass * dif[1] * dif[2];
     ci[6] = mass * dif[0]; ci[7] = mass * dif[1]; ci[8] = mass * dif[2]; ci[9] = mass;
-    for (int k = 0; k < 10; k++) e.crb[10 * b + k] = ci[k];
+    for (int k = 0; k < 10; k++) EF(crb)[10 * b + k] = ci[k];
   }
-  PFOR(j, m.njnt) {
-    int b = LDG(m.jnt_bodyid + j), da = LDG(m.jnt_dofadr + j), jt = LDG(m.jnt_type + j);
+  #pragma unroll 1
+  PFOR(j, MD.njnt) {
+    int b = LDG(MD.jnt_bodyid + j), da = LDG(MD.jnt_dofadr + j), jt = LDG(MD.jnt_type + j);
     real off[3];
-    sub3(off, e.rootcom + 3 * LDG(m.body_rootid + b), e.xanchor + 3 * j);
+    sub3(off, EF(rootcom) + 3 * LDG(MD.body_rootid + b), EF(xanchor) + 3 * j);
     if (jt == JNT_FREE) {
-      for (int k = 0; k < 36; k++) e.cdof[6 * da + k] = 0;
-      for (int k = 0; k < 3; k++) e.cdof[6 * (da + k) + 3 + k] = 1;
+      for (int k = 0; k < 36; k++) EF(cdof)[6 * da + k] = 0;
+      for (int k = 0; k < 3; k++) EF(cdof)[6 * (da + k) + 3 + k] = 1;
       for (int k = 0; k < 3; k++) {
-        real ax[3] = {e.xmat[9 * b + k], e.xmat[9 * b + 3 + k], e.xmat[9 * b + 6 + k]};
-        real *c = e.cdof + 6 * (da + 3 + k);
+        real ax[3] = {EF(xmat)[9 * b + k], EF(xmat)[9 * b + 3 + k], EF(xmat)[9 * b + 6 + k]};
+        real *c = EF(cdof) + 6 * (da + 3 + k);
         copy3(c, ax);
         cross3(c + 3, ax, off);
       }
     } else if (jt == JNT_SLIDE) {
-      real *c = e.cdof + 6 * da;
+      real *c = EF(cdof) + 6 * da;
       c[0] = c[1] = c[2] = 0;
-      copy3(c + 3, e.xaxis + 3 * j);
+      copy3(c + 3, EF(xaxis) + 3 * j);
     } else {
-      real *c = e.cdof + 6 * da;
-      copy3(c, e.xaxis + 3 * j);
-      cross3(c + 3, e.xaxis + 3 * j, off);
+      real *c = EF(cdof) + 6 * da;
+      copy3(c, EF(xaxis) + 3 * j);
+      cross3(c + 3, EF(xaxis) + 3 * j, off);
     }
   }
-  PFOR(i, nv * nv) e.M[i] = 0;
+  #pragma unroll 1
+  PFOR(i, nv * nv) EF(M)[i] = 0;
   WSYNC();
   // composite inertias: parents absorb their children, deepest level first
-  for (int lvl = m.maxdepth - 1; lvl >= 1; lvl--) {
+  #pragma unroll 1
+  for (int lvl = MD.maxdepth - 1; lvl >= 1; lvl--) {
+    #pragma unroll 1
     PFOR(b, nb) {
-      if (LDG(m.body_depth + b) != lvl) continue;
+      if (LDG(MD.body_depth + b) != lvl) continue;
+      #pragma unroll 1
       for (int c = b + 1; c < nb; c++)
-        if (LDG(m.body_parentid + c) == b)
-          for (int k = 0; k < 10; k++) e.crb[10 * b + k] += e.crb[10 * c + k];
+        if (LDG(MD.body_parentid + c) == b)
+          for (int k = 0; k < 10; k++) EF(crb)[10 * b + k] += EF(crb)[10 * c + k];
     }
     WSYNC();
   }
+  #pragma unroll 1
   PFOR(i, nv) {
     real buf[6];
-    mul_inert_vec(buf, e.crb + 10 * LDG(m.dof_bodyid + i), e.cdof + 6 * i);
-    for (int j = i; j >= 0; j = LDG(m.dof_parentid + j)) {
+    mul_inert_vec(buf, EF(crb) + 10 * LDG(MD.dof_bodyid + i), EF(cdof) + 6 * i);
+    #pragma unroll 1
+    for (int j = i; j >= 0; j = LDG(MD.dof_parentid + j)) {
       real v = 0;
-      for (int k = 0; k < 6; k++) v += e.cdof[6 * j + k] * buf[k];
-      if (j == i) v += LDG(m.dof_armature + i);
-      e.M[i * nv + j] = v;
-      e.M[j * nv + i] = v;
+      for (int k = 0; k < 6; k++) v += EF(cdof)[6 * j + k] * buf[k];
+      if (j == i) v += LDG(MD.dof_armature + i);
+      EF(M)[i * nv + j] = v;
+      EF(M)[j * nv + i] = v;
     }
   }
   WSYNC();
-  PFOR(i, nv * nv) e.H[i] = e.M[i];
-  chol_factor_w(e.H, nv);
-  chol_inverse_w(e.H, e.Minv, nv);
+  #pragma unroll 1
+  PFOR(i, nv * nv) EF(H)[i] = EF(M)[i];
+  chol_factor_w(EF(H), nv);
+  chol_inverse_w(EF(H), EF(Minv), nv);
 }
 
 // fixed tendons + actuator transmission
-MGS_DEVN void transmission_w(const DevModel &m, Env &e) {
-  const int nv = m.nv;
-  PFOR(i, m.ntendon * nv) e.ten_J[i] = 0;
-  PFOR(i, m.nu * nv) e.act_moment[i] = 0;
+MGS_DEVN void transmission_w(Env &e) {
+  const int nv = MD.nv;
+  #pragma unroll 1
+  PFOR(i, MD.ntendon * nv) EF(ten_J)[i] = 0;
+  #pragma unroll 1
+  PFOR(i, MD.nu * nv) EF(act_moment)[i] = 0;
   WSYNC();
-  PFOR(t, m.ntendon) {
+  #pragma unroll 1
+  PFOR(t, MD.ntendon) {
     real L = 0;
-    int a = LDG(m.tendon_adr + t), n = LDG(m.tendon_num + t);
+    int a = LDG(MD.tendon_adr + t), n = LDG(MD.tendon_num + t);
+    #pragma unroll 1
     for (int w = a; w < a + n; w++) {
-      real c = LDG(m.wrap_coef + w);
-      L += c * e.qpos[LDG(m.wrap_qposadr + w)];
-      e.ten_J[t * nv + LDG(m.wrap_dofadr + w)] += c;
+      real c = LDG(MD.wrap_coef + w);
+      L += c * EF(qpos)[LDG(MD.wrap_qposadr + w)];
+      EF(ten_J)[t * nv + LDG(MD.wrap_dofadr + w)] += c;
     }
-    e.ten_length[t] = L;
+    EF(ten_length)[t] = L;
   }
   WSYNC();
-  PFOR(a, m.nu) {
-    real gear = LDG(m.actuator_gear + a);
-    int id = LDG(m.actuator_trnid + a);
-    if (LDG(m.actuator_trntype + a) == 0) {
-      e.act_length[a] = gear * e.qpos[LDG(m.jnt_qposadr + id)];
-      e.act_moment[a * nv + LDG(m.jnt_dofadr + id)] = gear;
+  #pragma unroll 1
+  PFOR(a, MD.nu) {
+    real gear = LDG(MD.actuator_gear + a);
+    int id = LDG(MD.actuator_trnid + a);
+    if (LDG(MD.actuator_trntype + a) == 0) {
+      EF(act_length)[a] = gear * EF(qpos)[LDG(MD.jnt_qposadr + id)];
+      EF(act_moment)[a * nv + LDG(MD.jnt_dofadr + id)] = gear;
     } else {
-      e.act_length[a] = gear * e.ten_length[id];
-      for (int d = 0; d < nv; d++) e.act_moment[a * nv + d] = gear * e.ten_J[id * nv + d];
+      EF(act_length)[a] = gear * EF(ten_length)[id];
+      #pragma unroll 1
+      for (int d = 0; d < nv; d++) EF(act_moment)[a * nv + d] = gear * EF(ten_J)[id * nv + d];
     }
   }
   WSYNC();
 }
 
 // velocities, bias (RNE without acceleration), passive and actuator forces -> qfrc_smooth, qacc_smooth
-MGS_DEVN void smooth_forces_w(const DevModel &m, Env &e) {
-  const int nb = m.nbody, nv = m.nv;
-  PFOR(k, 6) { e.cvel[k] = 0; e.cfrc[k] = 0; e.cacc[k] = (k < 3) ? R_(0.0) : -m.gravity[k - 3]; }
+MGS_DEVN void smooth_forces_w(Env &e) {
+  const int nb = MD.nbody, nv = MD.nv;
+  #pragma unroll 1
+  PFOR(k, 6) { EF(cvel)[k] = 0; EF(cfrc)[k] = 0; EF(cacc)[k] = (k < 3) ? R_(0.0) : -MD.gravity[k - 3]; }
   WSYNC();
-  for (int lvl = 1; lvl <= m.maxdepth; lvl++) {
+  #pragma unroll 1
+  for (int lvl = 1; lvl <= MD.maxdepth; lvl++) {
+    #pragma unroll 1
     PFOR(b, nb) {
-      if (LDG(m.body_depth + b) != lvl) continue;
-      int p = LDG(m.body_parentid + b);
+      if (LDG(MD.body_depth + b) != lvl) continue;
+      int p = LDG(MD.body_parentid + b);
       real cv[6], ca[6];
-      for (int k = 0; k < 6; k++) { cv[k] = e.cvel[6 * p + k]; ca[k] = e.cacc[6 * p + k]; }
-      int ja = LDG(m.body_jntadr + b), jn = LDG(m.body_jntnum + b);
+      for (int k = 0; k < 6; k++) { cv[k] = EF(cvel)[6 * p + k]; ca[k] = EF(cacc)[6 * p + k]; }
+      int ja = LDG(MD.body_jntadr + b), jn = LDG(MD.body_jntnum + b);
+      #pragma unroll 1
       for (int j = ja; j < ja + jn; j++) {
-        int da = LDG(m.jnt_dofadr + j);
-        if (LDG(m.jnt_type + j) == JNT_FREE) {
-          for (int k = 0; k < 18; k++) e.cdof_dot[6 * da + k] = 0;
+        int da = LDG(MD.jnt_dofadr + j);
+        if (LDG(MD.jnt_type + j) == JNT_FREE) {
+          for (int k = 0; k < 18; k++) EF(cdof_dot)[6 * da + k] = 0;
           for (int k = 0; k < 3; k++)
-            for (int c = 0; c < 6; c++) cv[c] += e.cdof[6 * (da + k) + c] * e.qvel[da + k];
-          for (int k = 3; k < 6; k++) cross_motion(e.cdof_dot + 6 * (da + k), cv, e.cdof + 6 * (da + k));
+            for (int c = 0; c < 6; c++) cv[c] += EF(cdof)[6 * (da + k) + c] * EF(qvel)[da + k];
+          for (int k = 3; k < 6; k++) cross_motion(EF(cdof_dot) + 6 * (da + k), cv, EF(cdof) + 6 * (da + k));
           for (int k = 3; k < 6; k++)
-            for (int c = 0; c < 6; c++) cv[c] += e.cdof[6 * (da + k) + c] * e.qvel[da + k];
+            for (int c = 0; c < 6; c++) cv[c] += EF(cdof)[6 * (da + k) + c] * EF(qvel)[da + k];
           for (int k = 3; k < 6; k++)
-            for (int c = 0; c < 6; c++) ca[c] += e.cdof_dot[6 * (da + k) + c] * e.qvel[da + k];
+            for (int c = 0; c < 6; c++) ca[c] += EF(cdof_dot)[6 * (da + k) + c] * EF(qvel)[da + k];
         } else {
-          cross_motion(e.cdof_dot + 6 * da, cv, e.cdof + 6 * da);
-          for (int c = 0; c < 6; c++) { cv[c] += e.cdof[6 * da + c] * e.qvel[da]; ca[c] += e.cdof_dot[6 * da + c] * e.qvel[da]; }
+          cross_motion(EF(cdof_dot) + 6 * da, cv, EF(cdof) + 6 * da);
+          for (int c = 0; c < 6; c++) { cv[c] += EF(cdof)[6 * da + c] * EF(qvel)[da]; ca[c] += EF(cdof_dot)[6 * da + c] * EF(qvel)[da]; }
         }
       }
       real t1[6], t2[6];
-      mul_inert_vec(t1, e.cinert + 10 * b, cv);
+      mul_inert_vec(t1, EF(cinert) + 10 * b, cv);
       cross_force(t2, cv, t1);
-      mul_inert_vec(t1, e.cinert + 10 * b, ca);
-      for (int k = 0; k < 6; k++) { e.cvel[6 * b + k] = cv[k]; e.cacc[6 * b + k] = ca[k]; e.cfrc[6 * b + k] = t1[k] + t2[k]; }
+      mul_inert_vec(t1, EF(cinert) + 10 * b, ca);
+      for (int k = 0; k < 6; k++) { EF(cvel)[6 * b + k] = cv[k]; EF(cacc)[6 * b + k] = ca[k]; EF(cfrc)[6 * b + k] = t1[k] + t2[k]; }
     }
     WSYNC();
   }
-  for (int lvl = m.maxdepth - 1; lvl >= 1; lvl--) {
+  #pragma unroll 1
+  for (int lvl = MD.maxdepth - 1; lvl >= 1; lvl--) {
+    #pragma unroll 1
     PFOR(b, nb) {
-      if (LDG(m.body_depth + b) != lvl) continue;
+      if (LDG(MD.body_depth + b) != lvl) continue;
+      #pragma unroll 1
       for (int c = b + 1; c < nb; c++)
-        if (LDG(m.body_parentid + c) == b)
-          for (int k = 0; k < 6; k++) e.cfrc[6 * b + k] += e.cfrc[6 * c + k];
+        if (LDG(MD.body_parentid + c) == b)
+          for (int k = 0; k < 6; k++) EF(cfrc)[6 * b + k] += EF(cfrc)[6 * c + k];
     }
     WSYNC();
   }
   // actuator forces (lane per actuator), then per-dof totals
-  PFOR(a, m.nu) {
-    real c = e.ctrl[a], vel = 0;
-    if (LDG(m.actuator_ctrllimited + a)) c = fmax(LDG(m.actuator_ctrlrange + 2 * a), fmin(LDG(m.actuator_ctrlrange + 2 * a + 1), c));
-    for (int d = 0; d < nv; d++) vel += e.act_moment[a * nv + d] * e.qvel[d];
-    real f = LDG(m.actuator_gainprm + 3 * a) * c + LDG(m.actuator_biasprm + 3 * a) + LDG(m.actuator_biasprm + 3 * a + 1) * e.act_length[a] +
-             LDG(m.actuator_biasprm + 3 * a + 2) * vel;
-    if (LDG(m.actuator_forcelimited + a)) f = fmax(LDG(m.actuator_forcerange + 2 * a), fmin(LDG(m.actuator_forcerange + 2 * a + 1), f));
-    e.act_force[a] = f;
+  #pragma unroll 1
+  PFOR(a, MD.nu) {
+    real c = EF(ctrl)[a], vel = 0;
+    if (LDG(MD.actuator_ctrllimited + a)) c = fmax(LDG(MD.actuator_ctrlrange + 2 * a), fmin(LDG(MD.actuator_ctrlrange + 2 * a + 1), c));
+    #pragma unroll 1
+    for (int d = 0; d < nv; d++) vel += EF(act_moment)[a * nv + d] * EF(qvel)[d];
+    real f = LDG(MD.actuator_gainprm + 3 * a) * c + LDG(MD.actuator_biasprm + 3 * a) + LDG(MD.actuator_biasprm + 3 * a + 1) * EF(act_length)[a] +
+             LDG(MD.actuator_biasprm + 3 * a + 2) * vel;
+    if (LDG(MD.actuator_forcelimited + a)) f = fmax(LDG(MD.actuator_forcerange + 2 * a), fmin(LDG(MD.actuator_forcerange + 2 * a + 1), f));
+    EF(act_force)[a] = f;
   }
   WSYNC();
+  #pragma unroll 1
   PFOR(d, nv) {
     real bias = 0;
-    int b = LDG(m.dof_bodyid + d);
-    for (int c = 0; c < 6; c++) bias += e.cdof[6 * d + c] * e.cfrc[6 * b + c];
-    real f = -LDG(m.dof_damping + d) * e.qvel[d] - bias;
-    int j = LDG(m.dof_jntid + d);
-    if (LDG(m.jnt_type + j) != JNT_FREE) {
-      real k = LDG(m.jnt_stiffness + j);
-      int qa = LDG(m.jnt_qposadr + j);
-      if (k != 0) f -= k * (e.qpos[qa] - LDG(m.qpos_spring + qa));
+    int b = LDG(MD.dof_bodyid + d);
+    for (int c = 0; c < 6; c++) bias += EF(cdof)[6 * d + c] * EF(cfrc)[6 * b + c];
+    real f = -LDG(MD.dof_damping + d) * EF(qvel)[d] - bias;
+    int j = LDG(MD.dof_jntid + d);
+    if (LDG(MD.jnt_type + j) != JNT_FREE) {
+      real k = LDG(MD.jnt_stiffness + j);
+      int qa = LDG(MD.jnt_qposadr + j);
+      if (k != 0) f -= k * (EF(qpos)[qa] - LDG(MD.qpos_spring + qa));
     }
-    for (int a = 0; a < m.nu; a++) f += e.act_moment[a * nv + d] * e.act_force[a];
-    e.qfrc_smooth[d] = f;
+    #pragma unroll 1
+    for (int a = 0; a < MD.nu; a++) f += EF(act_moment)[a * nv + d] * EF(act_force)[a];
+    EF(qfrc_smooth)[d] = f;
   }
   WSYNC();
-  matvec_w(e.qacc_smooth, e.Minv, e.qfrc_smooth, nv);
+  matvec_w(EF(qacc_smooth), EF(Minv), EF(qfrc_smooth), nv);
 }

@@ -76,7 +76,7 @@ _LIBS = {}
 
 
 def load(f64: bool = False):
-    so = SO_PATH_F64 if f64 else SO_PATH
+    so = SO_PATH_F64 if f64 else os.environ.get("MGS_B200_SO", SO_PATH)  # env override: A/B builds while profiling
     if so not in _LIBS:
         if not os.path.exists(so):
             raise MgsError(f"{so} is missing: build it with mj_grasp_sim_b200.lib.build() (nvcc, sm_100a). "
@@ -186,7 +186,8 @@ class BatchSim:
     # ---- the two reference loops ---------------------------------------------------------
     def _prep(self, pose7, joints, joint_qposadr):
         pose7 = np.ascontiguousarray(pose7, dtype=np.float32).reshape(-1, 7)
-        joints = np.ascontiguousarray(joints, dtype=np.float32).reshape(len(pose7), -1)
+        joints = np.ascontiguousarray(joints, dtype=np.float32)
+        joints = joints.reshape(len(pose7), joints.shape[-1] if joints.ndim > 1 else len(np.atleast_1d(joint_qposadr)))
         jadr = np.ascontiguousarray(joint_qposadr, dtype=np.int32)
         return pose7, joints, jadr
 

@@ -49,9 +49,10 @@ extern "C" int l1_model_info(const L1Model *M, MgsModelInfo *info) {
 
 static void run_all(L1Model *M, const RolloutParams &prm, const BatchIO &io) {
   Env e;
+  g_k.m = M->dm; g_k.L = M->L; g_k.prm = prm; g_k.io = io;
   for (int env = 0; env < prm.n; env++) {
-    env_bind(e, M->scratch.data(), M->L);
-    run_env_w(M->dm, e, prm, io, env);
+    env_bind(e, M->scratch.data());
+    run_env_w(e, env);
   }
 }
 

@@ -1,0 +1,57 @@
+"""Summarise an .ncu-rep of mgs_rollout_kernel: headline metrics + per-function instruction/stall shares.
+
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [libmgs_b200.so]  (needs ncu, cuobjdump, nvdisasm; no GPU)
+"""
+import collections, csv, io, os, re, subprocess, sys, tempfile
+
+rep = sys.argv[1]
+so = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mj_grasp_sim_b200", "libmgs_b200.so")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, vals = rows[0], rows[1], rows[2]
+want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__average_warp_latency_per_inst_issued.ratio",
+        "sass__inst_executed_local_loads", "sass__inst_executed_local_stores", "l1tex__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__stack_size"]
+print("== headline")
+for h, u, v in zip(hdr, units, vals):
+    if h in want or (h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio") and float(v or 0) > 0.05):
+        print(f"{h} [{u}] {v}")
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+srows = list(csv.reader(io.StringIO(src)))
+shdr = srows[1]
+ci, si, ti = shdr.index("Instructions Executed"), shdr.index("# Samples"), shdr.index("Thread Instructions Executed")
+data = srows[2:]
+with tempfile.TemporaryDirectory() as td:
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=td, capture_output=True)
+    cub = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
+    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout
+func, line, seq = None, None, []
+for l in dis.split("\n"):
+    m = re.match(r'\s*//## File "(.*?)", line (\d+)', l)
+    if m:
+        line = (m.group(1).split("/")[-1], int(m.group(2)))
+        continue
+    m = re.match(r"^(\$?[_A-Za-z][\w$]*):\s*$", l)
+    if m and not m.group(1).startswith(".L"):
+        func = m.group(1)
+    if re.match(r"^\s+/\*[0-9a-f]{4,5}\*/", l):
+        seq.append((func, line))
+if len(seq) != len(data):
+    print(f"WARNING: SASS length mismatch ({len(seq)} vs {len(data)}): the .so does not match the profiled build")
+byf = collections.defaultdict(lambda: [0, 0, 0])
+byl = collections.defaultdict(lambda: [0, 0, 0])
+for (f, ln), r in zip(seq, data):
+    n, s, t = int(r[ci]), int(r[si]), int(r[ti])
+    for d, k in ((byf, f), (byl, ln)):
+        d[k][0] += n; d[k][1] += s; d[k][2] += t
+tot, tots = sum(v[0] for v in byf.values()), sum(v[1] for v in byf.values())
+print(f"== by function (total warp-instructions {tot}, samples {tots}): %inst %samples lane-efficiency")
+for k, v in sorted(byf.items(), key=lambda kv: -kv[1][1])[:28]:
+    name = re.sub(r"^\$?_Z\d+mgs_rollout_kernelv\$", "", str(k))
+    print(f"{100*v[0]/tot:6.2f} {100*v[1]/tots:6.2f} {v[2]/max(1,v[0])/32:5.2f}  {name}")
+print("== top source lines: %inst %samples lane-efficiency")
+for k, v in sorted(byl.items(), key=lambda kv: -kv[1][1])[:25]:
+    print(f"{100*v[0]/tot:6.2f} {100*v[1]/tots:6.2f} {v[2]/max(1,v[0])/32:5.2f}  {k}")
