@@ -133,7 +133,9 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = load()
     model, info, pose7, joints = scenes.workload("panda", "hull", rank, N_CAND)  # one object per rank (weak scaling)
-    sim = BatchSim(model, device=local_rank)
+    # per-environment capacities for this workload: 20 contacts / 90 constraint rows (the oracle sees at
+    # most 16 / 72 on these hull objects; the library counts any environment that would need more)
+    sim = BatchSim(model, device=local_rank, ncon_max=20, nefc_max=90)
     cfg = MgsRolloutCfg(**ROLLOUT)
     dev = torch.device("cuda", local_rank)
     d_pose = torch.from_numpy(pose7).to(dev)
@@ -173,6 +175,7 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         t_wall = time.perf_counter() - t_begin
     launches = lib.mgs_launch_count() - launches0
+    overflowed = sim.overflow_count()
     dev_s = sum(kern_ms) / 1e3
     labels_dev = d_lab.clone()
     # end-to-end through the host-pointer C ABI (pinned staging, H2D + kernel + D2H inside the call)
@@ -210,7 +213,8 @@ def run_ours(args, rank, world, local_rank):
                 "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "candidates_per_gpu": N_CAND, "l2": "flushed between timed iterations (256 MiB fill)",
-                           "stable_fraction": stable_frac},
+                           "stable_fraction": stable_frac, "capacity": {"ncon_max": 20, "nefc_max": 90, "envs_overflowed": overflowed},
+                           "envs_per_sm": sim.info.warps_per_block * sim.info.blocks_per_sm, "smem_bytes_per_env": sim.info.smem_bytes_per_env},
                 "grasps_per_s": world * N_CAND * args.steps / dev_s,
                 "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(pose7.nbytes + joints.nbytes),
                         "d2h_bytes_per_step": int(N_CAND * 5), "grasps_per_s": world * N_CAND * args.steps / e2e_s},

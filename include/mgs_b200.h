@@ -48,6 +48,10 @@ typedef struct MgsModelInfo {
 } MgsModelInfo;
 
 int mgs_model_create(const MgsModelDesc *desc, int device, MgsModel **out);
+/* Same, with explicit per-environment capacities (0 = default: 32 contacts, static rows + 96 contact
+ * rows).  Shared memory per environment - and so the number of environments resident per SM - follows
+ * from them.  Contacts beyond capacity are dropped and counted in the diagnostics' overflow field. */
+int mgs_model_create_ex(const MgsModelDesc *desc, int device, int ncon_max, int nefc_max, MgsModel **out);
 void mgs_model_destroy(MgsModel *model);
 int mgs_model_info(const MgsModel *model, MgsModelInfo *info);
 
@@ -73,6 +77,10 @@ int mgs_rollout_device(MgsModel *model, int mode, int n, const float *d_pose7, c
 int mgs_step_host(MgsModel *model, int n, int nstep, const void *state_in, void *state_out, void *diag_out);
 int mgs_step_device(MgsModel *model, int n, int nstep, const void *d_state_in, void *d_state_out, void *d_diag_out,
                     void *stream);
+
+/* environments of the most recent launch on this model that dropped contacts for lack of capacity
+ * (synchronises the device); re-run with larger capacities if non-zero and exactness matters */
+int mgs_overflow_count(MgsModel *model);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 long long mgs_launch_count(void);

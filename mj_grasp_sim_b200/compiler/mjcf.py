@@ -642,6 +642,13 @@ def compile_mjcf(xml: str, assets: dict | None = None, massprops: dict | None = 
             if w1 != 0 and w2 != 0 and (w1 == pw2 or w2 == pw1):
                 continue
             pairs.append((ia, ib) + mix(g1, g2))
+    # Order of the candidate list = order of narrowphase lanes = order of contacts.  Pairs that involve a
+    # free-floating single-body tree (the grasped objects) go first: they are the pairs that actually
+    # collide during a grasp, and packing them into the same batch of 32 lanes lets the other batches
+    # (gripper self-pairs, ground) finish after one or two support queries.
+    def _is_object(b):
+        return body_parent[b] == 0 and body_dofnum[b] == 6 and not any(body_parent[c] == b for c in range(nbody))
+    pairs.sort(key=lambda p: 0 if (_is_object(G["body"][cg[p[0]]]) or _is_object(G["body"][cg[p[1]]])) else 1)
     npair = len(pairs)
 
     m = Model()

@@ -65,6 +65,10 @@ extern "C" const char *mgs_last_error(void) { return g_err.c_str(); }
 extern "C" long long mgs_launch_count(void) { return g_launches; }
 
 extern "C" int mgs_model_create(const MgsModelDesc *desc, int device, MgsModel **out) {
+  return mgs_model_create_ex(desc, device, 0, 0, out);
+}
+
+extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int ncon_max, int nefc_max, MgsModel **out) {
   if (!desc || !out) return fail("null argument");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device: libmgs_b200 has no CPU path");
@@ -73,6 +77,10 @@ extern "C" int mgs_model_create(const MgsModelDesc *desc, int device, MgsModel *
   ModelBlob blob;
   std::string err;
   if (!build_model_blob(desc, blob, err)) return fail("model: " + err);
+  if (ncon_max > 0) blob.ncon_max = ncon_max;
+  if (nefc_max > 0) blob.nefc_max = nefc_max;
+  if (blob.ncon_max > 64 || blob.nefc_max < desc->nv || 6 * blob.ncon_max > 2 * blob.nefc_max)
+    return fail("bad contact capacities (need ncon_max <= 64 and nefc_max >= 3 * ncon_max)");
   MgsModel *M = new MgsModel();
   memset(M, 0, sizeof(*M));
   M->device = device;
@@ -80,7 +88,7 @@ extern "C" int mgs_model_create(const MgsModelDesc *desc, int device, MgsModel *
   CU(cudaMemcpy(M->d_blob, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice));
   M->dm = blob.dm;
   rebase_model(M->dm, M->d_blob);
-  CU(cudaMalloc(&M->d_counter, sizeof(unsigned int)));
+  CU(cudaMalloc(&M->d_counter, 2 * sizeof(unsigned int)));  // [0] work queue head, [1] environments that overflowed a capacity
   layout_compute(&M->L, desc->nq, desc->nv, desc->nu, desc->nbody, desc->njnt, desc->nmocap, desc->ntendon, desc->ncgeom, blob.ncon_max,
                  blob.nefc_max);
   cudaDeviceProp prop;
@@ -125,6 +133,15 @@ extern "C" void mgs_model_destroy(MgsModel *M) {
   delete M;
 }
 
+extern "C" int mgs_overflow_count(MgsModel *M) {
+  if (!M) return fail("null model");
+  unsigned int v[2] = {0, 0};
+  if (cudaSetDevice(M->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpy(v, M->d_counter, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail("mgs_overflow_count: CUDA error");
+  return (int)v[1];
+}
+
 extern "C" int mgs_model_info(const MgsModel *M, MgsModelInfo *info) {
   if (!M || !info) return fail("null argument");
   info->nq = M->dm.nq; info->nv = M->dm.nv; info->nu = M->dm.nu; info->nmocap = M->dm.nmocap;
@@ -140,7 +157,7 @@ static int launch(MgsModel *M, const RolloutParams &prm, const BatchIO &io_in, c
   if (prm.n <= 0) return 0;
   BatchIO io = io_in;
   io.work_counter = M->d_counter;
-  CU(cudaMemsetAsync(M->d_counter, 0, sizeof(unsigned int), st));
+  CU(cudaMemsetAsync(M->d_counter, 0, 2 * sizeof(unsigned int), st));
   int blocks_needed = (prm.n + M->warps_per_block - 1) / M->warps_per_block;
   int grid = M->num_sms * M->blocks_per_sm;
   if (grid > blocks_needed) grid = blocks_needed;

@@ -33,7 +33,7 @@ typedef float real;
 #define MGS_LANE 0
 #define WSYNC() ((void)0)
 #define LDG(p) (*(p))
-#define MGS_STAGE_BARRIER() ((void)0)
+#define MGS_STAGE_BARRIER(k) ((void)0)
 #else
 #include <cuda_runtime.h>
 #define MGS_DEV __device__ __forceinline__
@@ -49,11 +49,13 @@ typedef float real;
 // never touch each other's environment); they only align code position, and every warp executes the
 // same number of them per step, whatever its contact count or solver path.  -DMGS_NO_STAGE_BARRIER
 // turns them off for A/B measurements.
-#ifdef MGS_NO_STAGE_BARRIER
-#define MGS_STAGE_BARRIER() ((void)0)
-#else
-#define MGS_STAGE_BARRIER() __syncthreads()
+// MGS_BAR_MASK selects which of the six per-step barriers are compiled in (bit k = barrier k):
+// 0 step start, 1 before collision, 2 after collision, 3 after constraint assembly, 4 after Newton,
+// 5 before integration.
+#ifndef MGS_BAR_MASK
+#define MGS_BAR_MASK 63
 #endif
+#define MGS_STAGE_BARRIER(k) do { if ((MGS_BAR_MASK >> (k)) & 1) __syncthreads(); } while (0)
 #endif
 
 // lane-strided loop: on the GPU lane L handles i = L, L+32, ...; on the host build one lane does all
@@ -69,13 +71,13 @@ enum { MGS_MODE_STEP = 0, MGS_MODE_COLLISION = 1, MGS_MODE_STABILITY = 2 };
 // Model constants on the device (all pointers into one read-only blob).
 struct DevModel {
   int nq, nv, nu, nbody, njnt, neq, nmocap, ntendon, nwrap, ncgeom, npair, nhull;
-  int maxdepth, ne_rows, cone_elliptic, iterations, ls_iterations, noslip_iterations, mpr_iterations, ground_geomid;
+  int maxdepth, max_tree_dofs, ne_rows, cone_elliptic, iterations, ls_iterations, noslip_iterations, mpr_iterations, ground_geomid;
   real timestep, impratio, tolerance, ls_tolerance, noslip_tolerance, mpr_tolerance, meaninertia, gravity[3];
   const int *body_parentid, *body_rootid, *body_mocapid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_depth;
   const real *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0, *body_subtreemass;
   const int *jnt_type, *jnt_bodyid, *jnt_qposadr, *jnt_dofadr, *jnt_limited;
   const real *jnt_pos, *jnt_axis, *jnt_range, *jnt_stiffness, *jnt_solref, *jnt_solimp, *jnt_margin, *qpos0, *qpos_spring;
-  const int *dof_bodyid, *dof_jntid, *dof_parentid;
+  const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_treeadr, *dof_treenum;
   const real *dof_armature, *dof_damping, *dof_frictionloss, *dof_solref, *dof_solimp, *dof_invweight0;
   const int *cgeom_geomid, *cgeom_type, *cgeom_bodyid, *cgeom_hullid;
   const real *cgeom_pos, *cgeom_quat, *cgeom_size, *cgeom_rbound;

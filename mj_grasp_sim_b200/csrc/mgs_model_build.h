@@ -33,6 +33,7 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
   b.resize(16);
   memset(&m, 0, sizeof(m));
   if (d->nu > MGS_MAX_NU) { err = "too many actuators"; return false; }
+  if (d->nv > 32) { err = "nv > 32: the warp-per-environment kernel holds one dof per lane (env-per-block variant not built yet)"; return false; }
   if (d->nmocap > 1) { err = "at most one mocap body is supported"; return false; }
   for (int p = 0; p < d->npair; p++)
     if (d->pair_condim[p] != 1 && d->pair_condim[p] != 3 && d->pair_condim[p] != 4) { err = "condim must be 1, 3 or 4"; return false; }
@@ -73,6 +74,21 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
   PR_(jnt_pos, 3 * nj); PR_(jnt_axis, 3 * nj); PR_(jnt_range, 2 * nj); PR_(jnt_stiffness, nj); PR_(jnt_solref, 2 * nj); PR_(jnt_solimp, 5 * nj);
   PR_(jnt_margin, nj); PR_(qpos0, nq); PR_(qpos_spring, nq);
   PI_(dof_bodyid, nv); PI_(dof_jntid, nv); PI_(dof_parentid, nv);
+  {
+    // kinematic trees = diagonal blocks of the mass matrix (dofs of one tree are contiguous)
+    std::vector<int> tadr(nv, 0), tnum(nv, 0);
+    int maxt = 0;
+    for (int i = 0; i < nv;) {
+      int root = d->body_rootid[d->dof_bodyid[i]], j = i;
+      while (j < nv && d->body_rootid[d->dof_bodyid[j]] == root) j++;
+      for (int k = i; k < j; k++) { tadr[k] = i; tnum[k] = j - i; }
+      if (j - i > maxt) maxt = j - i;
+      i = j;
+    }
+    m.dof_treeadr = put<int>(b, tadr.data(), nv);
+    m.dof_treenum = put<int>(b, tnum.data(), nv);
+    m.max_tree_dofs = maxt;
+  }
   PR_(dof_armature, nv); PR_(dof_damping, nv); PR_(dof_frictionloss, nv); PR_(dof_solref, 2 * nv); PR_(dof_solimp, 5 * nv); PR_(dof_invweight0, nv);
   PI_(cgeom_geomid, ng); PI_(cgeom_type, ng); PI_(cgeom_bodyid, ng); PI_(cgeom_hullid, ng);
   PR_(cgeom_pos, 3 * ng); PR_(cgeom_quat, 4 * ng); PR_(cgeom_size, 3 * ng); PR_(cgeom_rbound, ng);

@@ -62,7 +62,7 @@ MGS_DEVN int stability_program_w(Env &e, const float *pose7, const float *joints
   reset_w(e);
   place_w(e, pose7, joints);
   forward_w(e);
-  MGS_STAGE_BARRIER();  // the integrate slot of a step (keeps the CTA stage-aligned)
+  MGS_STAGE_BARRIER(5);  // the integrate slot of a step (keeps the CTA stage-aligned)
   // close_gripper_at (panda.py:225-241 and the five siblings): mocap <- pose, ctrl <- close signal
   if (PRM.repose_on_close) place_w(e, pose7, (const float *)0);
   #pragma unroll 1
@@ -153,7 +153,7 @@ MGS_DEVN void run_env_w(Env &e, int env) {
     PFOR(i, 7 * MD.nmocap) EF(mocap)[i] = in[MD.nq + 2 * MD.nv + MD.nu + i];
     WSYNC();
     if (PRM.nstep > 0) step_w(e, PRM.nstep, &steps);
-    else { forward_w(e); MGS_STAGE_BARRIER(); }
+    else { forward_w(e); MGS_STAGE_BARRIER(5); }
     real *out = IO.state_out + (size_t)env * IO.state_stride;
     #pragma unroll 1
     PFOR(i, MD.nq) out[i] = EF(qpos)[i];
@@ -175,13 +175,19 @@ MGS_DEVN void run_env_w(Env &e, int env) {
     reset_w(e);
     place_w(e, pose7, joints);
     forward_w(e);
-    MGS_STAGE_BARRIER();
+    MGS_STAGE_BARRIER(5);
     label = (e.ncon == 0);  // collision-free mask: no contact of any kind (check_contact, :306-307)
   } else {
     label = stability_program_w(e, pose7, joints, &steps);
   }
   #pragma unroll 1
-  PFOR(k, 1) { IO.labels[env] = (uint8_t)label; if (IO.steps) IO.steps[env] = steps; }
+  PFOR(k, 1) {
+    IO.labels[env] = (uint8_t)label;
+    if (IO.steps) IO.steps[env] = steps;
+#ifndef MGS_HOST
+    if (e.overflow) atomicAdd(IO.work_counter + 1, 1u);
+#endif
+  }
   if (IO.state_out) {
     real *out = IO.state_out + (size_t)env * IO.state_stride;
     #pragma unroll 1

@@ -124,74 +124,120 @@ MGS_DEV void env_bind(Env &e, real *base) {
 #define IARR(p) ((int *)(p))
 
 // ---------------------------------------------------------------------------------- dense linear algebra (warp)
+// `blocked` != 0: the matrix is block diagonal with one block per kinematic tree (the mass matrix M and
+// the implicit-integration matrix M - h dF/dv).  Lane i works on row i of ITS tree's block, all blocks
+// advance one column per step together, so the number of column steps is the largest tree, not nv.
 // In-place lower Cholesky of the n x n matrix A (row-major, only the lower triangle is read).
-MGS_DEVN void chol_factor_w(real *A, int n) {
-  #pragma unroll 1
+#ifdef MGS_HOST
+// 1-lane host build: the same factorisation written serially (per block)
+MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
   for (int j = 0; j < n; j++) {
-    WSYNC();
+    const int hi = blocked ? MD.dof_treeadr[j] + MD.dof_treenum[j] : n;
     real d = A[j * n + j];
     d = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL);
-    real inv = R_(1.0) / d;
+    const real inv = R_(1.0) / d;
+    A[j * n + j] = d;
+    for (int i = j + 1; i < hi; i++) A[i * n + j] *= inv;
+    for (int i = j + 1; i < hi; i++) {
+      const real lij = A[i * n + j];
+      for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+    }
+  }
+}
+MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
+  for (int k = 0; k < n; k++) {
+    const int hi = blocked ? MD.dof_treeadr[k] + MD.dof_treenum[k] : n;
+    const real xk = x[k] / L[k * n + k];
+    x[k] = xk;
+    for (int i = k + 1; i < hi; i++) x[i] -= L[i * n + k] * xk;
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    const int lo = blocked ? MD.dof_treeadr[k] : 0;
+    const real xk = x[k] / L[k * n + k];
+    x[k] = xk;
+    for (int i = lo; i < k; i++) x[i] -= L[k * n + i] * xk;
+  }
+}
+#else
+// GPU: lane i owns row i (n <= 32); every block advances one pivot column per step
+MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
+  const int nsteps = blocked ? MD.max_tree_dofs : n;
+  const int i = MGS_LANE;
+  int tadr = 0, tnum = n;
+  if (blocked && i < n) { tadr = LDG(MD.dof_treeadr + i); tnum = LDG(MD.dof_treenum + i); }
+  #pragma unroll 1
+  for (int t = 0; t < nsteps; t++) {
+    const int j = tadr + t;
+    const int live = (i < n) && (t < tnum);
     WSYNC();
-    #pragma unroll 1
-    PFOR(i, n) {
+    real d = 1;
+    if (live) { d = A[j * n + j]; d = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL); }
+    WSYNC();
+    if (live) {
       if (i == j) A[j * n + j] = d;
-      else if (i > j) A[i * n + j] *= inv;
+      else if (i > j) A[i * n + j] *= R_(1.0) / d;
     }
     WSYNC();
-    #pragma unroll 1
-    PFOR(i, n) {
-      if (i > j) {
-        real lij = A[i * n + j];
-        #pragma unroll 1
-        for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
-      }
+    if (live && i > j) {
+      const real lij = A[i * n + j];
+      #pragma unroll 1
+      for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
     }
   }
   WSYNC();
 }
-// x <- (L L')^-1 x, warp-cooperative (column oriented substitution)
-MGS_DEVN void chol_solve_w(const real *L, real *x, int n) {
+// x <- (L L')^-1 x (column-oriented substitution)
+MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
+  const int nsteps = blocked ? MD.max_tree_dofs : n;
+  const int i = MGS_LANE;
+  int tadr = 0, tnum = n;
+  if (blocked && i < n) { tadr = LDG(MD.dof_treeadr + i); tnum = LDG(MD.dof_treenum + i); }
   #pragma unroll 1
-  for (int k = 0; k < n; k++) {
+  for (int t = 0; t < nsteps; t++) {
+    const int k = tadr + t, live = (i < n) && (t < tnum);
     WSYNC();
-    real xk = x[k] / L[k * n + k];
+    real xk = 0;
+    if (live) xk = x[k] / L[k * n + k];
     WSYNC();
-    #pragma unroll 1
-    PFOR(i, n) {
+    if (live) {
       if (i == k) x[k] = xk;
       else if (i > k) x[i] -= L[i * n + k] * xk;
     }
   }
   #pragma unroll 1
-  for (int k = n - 1; k >= 0; k--) {
+  for (int t = nsteps - 1; t >= 0; t--) {
+    const int k = tadr + t, live = (i < n) && (t < tnum);
     WSYNC();
-    real xk = x[k] / L[k * n + k];
+    real xk = 0;
+    if (live) xk = x[k] / L[k * n + k];
     WSYNC();
-    #pragma unroll 1
-    PFOR(i, n) {
+    if (live) {
       if (i == k) x[k] = xk;
       else if (i < k) x[i] -= L[k * n + i] * xk;
     }
   }
   WSYNC();
 }
+#endif
 // Ainv <- (L L')^-1, one column per lane (serial substitution inside the lane)
-MGS_DEVN void chol_inverse_w(const real *L, real *Ainv, int n) {
+MGS_DEVN void chol_inverse_w(const real *L, real *Ainv, int n, int blocked) {
   #pragma unroll 1
   PFOR(c, n) {
+    const int lo = blocked ? LDG(MD.dof_treeadr + c) : 0, hi = blocked ? lo + LDG(MD.dof_treenum + c) : n;
     #pragma unroll 1
-    for (int i = 0; i < n; i++) {
+    for (int i = 0; i < n; i++) if (i < lo || i >= hi) Ainv[i * n + c] = 0;
+    #pragma unroll 1
+    for (int i = lo; i < hi; i++) {
       real s = (i == c) ? R_(1.0) : R_(0.0);
       #pragma unroll 1
-      for (int k = 0; k < i; k++) s -= L[i * n + k] * Ainv[k * n + c];
+      for (int k = lo; k < i; k++) s -= L[i * n + k] * Ainv[k * n + c];
       Ainv[i * n + c] = s / L[i * n + i];
     }
     #pragma unroll 1
-    for (int i = n - 1; i >= 0; i--) {
+    for (int i = hi - 1; i >= lo; i--) {
       real s = Ainv[i * n + c];
       #pragma unroll 1
-      for (int k = i + 1; k < n; k++) s -= L[k * n + i] * Ainv[k * n + c];
+      for (int k = i + 1; k < hi; k++) s -= L[k * n + i] * Ainv[k * n + c];
       Ainv[i * n + c] = s / L[i * n + i];
     }
   }
@@ -422,8 +468,8 @@ MGS_DEVN void inertia_w(Env &e) {
   WSYNC();
   #pragma unroll 1
   PFOR(i, nv * nv) EF(H)[i] = EF(M)[i];
-  chol_factor_w(EF(H), nv);
-  chol_inverse_w(EF(H), EF(Minv), nv);
+  chol_factor_w(EF(H), nv, 1);
+  chol_inverse_w(EF(H), EF(Minv), nv, 1);
 }
 
 // fixed tendons + actuator transmission

@@ -501,7 +501,7 @@ MGS_DEVN void newton_hessian_w(Env &e) {
     }
   }
   WSYNC();
-  chol_factor_w(EF(H), nv);
+  chol_factor_w(EF(H), nv, 0);
 }
 
 MGS_DEVN void solve_newton_w(Env &e) {
@@ -539,7 +539,7 @@ MGS_DEVN void solve_newton_w(Env &e) {
     real tol_eff = fmax(MD.tolerance, R_(20.0) * (real)REAL_EPS * scale * fabs(cost));
     if (iter > 0 && scale * sqrt(gn) < tol_eff) break;
     newton_hessian_w(e);
-    chol_solve_w(EF(H), EF(search), nv);
+    chol_solve_w(EF(H), EF(search), nv, 0);
     #pragma unroll 1
     PFOR(d, nv) EF(search)[d] = -EF(search)[d];
     WSYNC();
@@ -632,14 +632,45 @@ MGS_DEVN void qcqp_small(real *res, const real *A, const real *b, const real *d,
   for (int i = 0; i < n; i++) res[i] = v[i] * d[i];
 }
 
-// mj_solNoSlip.  wvec tracks qacc - qacc_smooth = M^-1 J' f so that no nefc x nefc matrix is formed.
+// mj_solNoSlip: Gauss-Seidel on the friction rows with the UNREGULARISED A = J M^-1 J'.
+// wvec tracks qacc - qacc_smooth = M^-1 J' f, so no nefc x nefc matrix is formed: a row's residual is
+// J_i (qacc_smooth + w) - aref_i and a force change dF moves w by M^-1 J' dF.  The small diagonal blocks
+// A_c = J_c M^-1 J_c' (one per contact, <= 3x3) do not change between sweeps: they are computed once, one
+// contact per lane, into the (now free) jar/jv scratch.
 MGS_DEVN void solve_noslip_w(Env &e) {
   const int nv = MD.nv;
   const real scale = R_(1.0) / (MD.meaninertia * (nv > 1 ? nv : 1));
+  real *AC = EF(efc_jar);  // 6 reals per contact: upper triangle of A_c (jar and jv are dead after Newton)
+  real *T = EF(nsB);       // nv-vector scratch
   #pragma unroll 1
   PFOR(d, nv) EF(wvec)[d] = EF(qacc)[d] - EF(qacc_smooth)[d];
+  #pragma unroll 1
+  PFOR(c, e.ncon) {
+    const int i = IARR(EF(con_efc))[c];
+    if (i < 0) continue;
+    const int dim = LDG(MD.pair_condim + IARR(EF(con_pair))[c]);
+    int n = dim - 1;
+    if (n > 3) n = 3;
+    int q = 0;
+    #pragma unroll 1
+    for (int j = 0; j < n; j++)
+      #pragma unroll 1
+      for (int k = j; k < n; k++) {
+        const real *Jj = EF(J) + (i + 1 + j) * nv, *Jk = EF(J) + (i + 1 + k) * nv;
+        real acc = 0;
+        #pragma unroll 1
+        for (int a = 0; a < nv; a++) {
+          const real ja = Jj[a];
+          if (ja == 0) continue;
+          real t = 0;
+          #pragma unroll 1
+          for (int b2 = 0; b2 < nv; b2++) t += EF(Minv)[a * nv + b2] * Jk[b2];
+          acc += ja * t;
+        }
+        AC[6 * c + q++] = acc;
+      }
+  }
   WSYNC();
-  real *B = EF(nsB), *S = EF(nsS);
   #pragma unroll 1
   for (int iter = 0; iter < MD.noslip_iterations; iter++) {
     real improvement = 0;
@@ -653,31 +684,19 @@ MGS_DEVN void solve_noslip_w(Env &e) {
       }
       improvement += wsum(t);
     }
-    // dry friction rows
+    // dry-friction rows: J_i is the unit vector of dof d, so everything is a table lookup
     #pragma unroll 1
     for (int i = e.ne; i < e.ne + e.nf; i++) {
-      const real *Ji = EF(J) + i * nv;
-      #pragma unroll 1
-      PFOR(d, nv) {
-        real t = 0;
-        #pragma unroll 1
-        for (int k = 0; k < nv; k++) t += EF(Minv)[d * nv + k] * Ji[k];
-        B[d] = t;
-      }
-      WSYNC();
-      real res = 0, Aii = 0;
-      #pragma unroll 1
-      PFOR(d, nv) { res += Ji[d] * (EF(qacc_smooth)[d] + EF(wvec)[d]); Aii += Ji[d] * B[d]; }
-      res = wsum(res) - EF(efc_aref)[i]; Aii = wsum(Aii);
-      real old = EF(efc_force)[i], fl = EF(efc_aux)[i];
+      const int d = EFC_ID(i);
+      const real res = EF(qacc_smooth)[d] + EF(wvec)[d] - EF(efc_aref)[i], Aii = EF(Minv)[d * nv + d];
+      const real old = EF(efc_force)[i], fl = EF(efc_aux)[i];
       real fn = old - res / fmax(MGS_MINVAL, Aii);
       fn = fmax(-fl, fmin(fl, fn));
       real delta = fn - old, change = R_(0.5) * delta * delta * Aii + delta * res;
       if (change > R_(1e-10)) { fn = old; delta = 0; change = 0; }
       WSYNC();
       #pragma unroll 1
-      PFOR(d, nv) EF(wvec)[d] += B[d] * delta;
-      #pragma unroll 1
+      PFOR(k, nv) EF(wvec)[k] += EF(Minv)[k * nv + d] * delta;
       PFOR(k, 1) EF(efc_force)[i] = fn;
       improvement -= change;
       WSYNC();
@@ -685,64 +704,62 @@ MGS_DEVN void solve_noslip_w(Env &e) {
     // contact friction dims
     #pragma unroll 1
     for (int c = 0; c < e.ncon; c++) {
-      int i = IARR(EF(con_efc))[c];
+      const int i = IARR(EF(con_efc))[c];
       if (i < 0) continue;
-      int p = IARR(EF(con_pair))[c], dim = LDG(MD.pair_condim + p), n = dim - 1;
+      const int p = IARR(EF(con_pair))[c], dim = LDG(MD.pair_condim + p);
       if (dim < 3) continue;
+      int n = dim - 1;
       if (n > 3) n = 3;
-      // B_j = M^-1 J_j'
-      #pragma unroll 1
-      PFOR(idx, n * nv) {
-        int j = idx / nv, d = idx - j * nv;
-        const real *Jj = EF(J) + (i + 1 + j) * nv;
-        real t = 0;
+      // residuals of the n friction rows: lane j does row j, then the values are shared
+      real myres = 0;
+      if (MGS_LANE < n || LANES == 1) {
         #pragma unroll 1
-        for (int k = 0; k < nv; k++) t += EF(Minv)[d * nv + k] * Jj[k];
-        B[j * nv + d] = t;
-      }
-      WSYNC();
-      // Ac (n x n) and res (n): one small dot product per lane
-      #pragma unroll 1
-      PFOR(idx, n * n + n) {
-        if (idx < n * n) {
-          int j = idx / n, k = idx - j * n;
-          const real *Jj = EF(J) + (i + 1 + j) * nv;
-          real t = 0;
-          #pragma unroll 1
-          for (int d = 0; d < nv; d++) t += Jj[d] * B[k * nv + d];
-          S[idx] = t;
-        } else {
-          int j = idx - n * n;
+        for (int j = (LANES == 1 ? 0 : MGS_LANE); j < (LANES == 1 ? n : MGS_LANE + 1); j++) {
           const real *Jj = EF(J) + (i + 1 + j) * nv;
           real t = -EF(efc_aref)[i + 1 + j];
           #pragma unroll 1
           for (int d = 0; d < nv; d++) t += Jj[d] * (EF(qacc_smooth)[d] + EF(wvec)[d]);
-          S[idx] = t;
+          if (LANES == 1) EF(nsS)[j] = t; else myres = t;
         }
       }
-      WSYNC();
-      // tiny QCQP, computed redundantly by every lane (no divergence, no extra sync)
-      real Ac[9], res[3], old[3], bc[3], v[3], delta[3], fr[3];
-      #pragma unroll 1
-      for (int k = 0; k < n * n; k++) Ac[k] = S[k];
-      #pragma unroll 1
-      for (int j = 0; j < n; j++) { res[j] = S[n * n + j]; old[j] = EF(efc_force)[i + 1 + j]; fr[j] = LDG(MD.pair_friction + 5 * p + j); }
-      #pragma unroll 1
-      for (int j = 0; j < n; j++) { bc[j] = res[j]; for (int k = 0; k < n; k++) bc[j] -= Ac[j * n + k] * old[k]; }
-      real fnorm = EF(efc_force)[i];
-      if (fnorm < MGS_MINVAL) { for (int j = 0; j < n; j++) v[j] = 0; }
+      real res[3], Ac[9], old[3], bc[3], v[3], delta[3], fr[3];
+#ifdef MGS_HOST
+      for (int j = 0; j < n; j++) res[j] = EF(nsS)[j];
+      (void)myres;
+#else
+      res[0] = __shfl_sync(0xffffffffu, myres, 0); res[1] = __shfl_sync(0xffffffffu, myres, 1); res[2] = __shfl_sync(0xffffffffu, myres, 2);
+#endif
+      {
+        int q = 0;
+        for (int j = 0; j < 3; j++)
+          for (int k = j; k < 3; k++)
+            if (j < n && k < n) { Ac[j * n + k] = Ac[k * n + j] = AC[6 * c + q]; q++; }
+      }
+      for (int j = 0; j < 3; j++) if (j < n) { old[j] = EF(efc_force)[i + 1 + j]; fr[j] = LDG(MD.pair_friction + 5 * p + j); }
+      for (int j = 0; j < 3; j++) if (j < n) { bc[j] = res[j]; for (int k = 0; k < 3; k++) if (k < n) bc[j] -= Ac[j * n + k] * old[k]; }
+      const real fnorm = EF(efc_force)[i];
+      if (fnorm < MGS_MINVAL) { for (int j = 0; j < 3; j++) v[j] = 0; }
       else qcqp_small(v, Ac, bc, fr, fnorm, n);
       real change = 0;
+      for (int j = 0; j < 3; j++) delta[j] = (j < n) ? v[j] - old[j] : R_(0.0);
+      for (int j = 0; j < 3; j++) if (j < n) { change += delta[j] * res[j]; for (int k = 0; k < 3; k++) if (k < n) change += R_(0.5) * delta[j] * Ac[j * n + k] * delta[k]; }
+      if (change > R_(1e-10)) { for (int j = 0; j < 3; j++) { v[j] = (j < n) ? old[j] : R_(0.0); delta[j] = 0; } change = 0; }
+      // w += M^-1 (J_c' delta)
       #pragma unroll 1
-      for (int j = 0; j < n; j++) delta[j] = v[j] - old[j];
-      #pragma unroll 1
-      for (int j = 0; j < n; j++) { change += delta[j] * res[j]; for (int k = 0; k < n; k++) change += R_(0.5) * delta[j] * Ac[j * n + k] * delta[k]; }
-      if (change > R_(1e-10)) { for (int j = 0; j < n; j++) { v[j] = old[j]; delta[j] = 0; } change = 0; }
+      PFOR(d, nv) {
+        real t = 0;
+        for (int j = 0; j < 3; j++) if (j < n) t += EF(J)[(i + 1 + j) * nv + d] * delta[j];
+        T[d] = t;
+      }
+      PFOR(j, n) EF(efc_force)[i + 1 + j] = v[j];
       WSYNC();
       #pragma unroll 1
-      PFOR(d, nv) { real t = 0; for (int j = 0; j < n; j++) t += B[j * nv + d] * delta[j]; EF(wvec)[d] += t; }
-      #pragma unroll 1
-      PFOR(j, n) EF(efc_force)[i + 1 + j] = v[j];
+      PFOR(d, nv) {
+        real t = 0;
+        #pragma unroll 1
+        for (int k = 0; k < nv; k++) t += EF(Minv)[d * nv + k] * T[k];
+        EF(wvec)[d] += t;
+      }
       improvement -= change;
       WSYNC();
     }
@@ -760,16 +777,16 @@ MGS_DEVN void solve_noslip_w(Env &e) {
 // candidate) still take the integrate stage's barrier so that all warps of the CTA stay stage-aligned.
 MGS_DEVN void forward_w(Env &e) {
   const int nv = MD.nv;
-  MGS_STAGE_BARRIER();
+  MGS_STAGE_BARRIER(0);
   kinematics_w(e);
   inertia_w(e);
   transmission_w(e);
-  MGS_STAGE_BARRIER();
+  MGS_STAGE_BARRIER(1);
   collision_w(e);
-  MGS_STAGE_BARRIER();
+  MGS_STAGE_BARRIER(2);
   smooth_forces_w(e);
   make_constraint_w(e);
-  MGS_STAGE_BARRIER();
+  MGS_STAGE_BARRIER(3);
   if (e.nefc == 0) {
     #pragma unroll 1
     PFOR(d, nv) { EF(qacc)[d] = EF(qacc_smooth)[d]; EF(qacc_ws)[d] = EF(qacc_smooth)[d]; EF(qfrc_constraint)[d] = 0; }
@@ -780,7 +797,7 @@ MGS_DEVN void forward_w(Env &e) {
     PFOR(d, nv) EF(qacc_ws)[d] = EF(qacc)[d];
     WSYNC();
   }
-  MGS_STAGE_BARRIER();
+  MGS_STAGE_BARRIER(4);
   if (e.nefc != 0) {
     if (MD.noslip_iterations > 0) solve_noslip_w(e);
     else {
@@ -830,8 +847,8 @@ MGS_DEVN void integrate_w(Env &e) {
   #pragma unroll 1
   PFOR(d, nv) EF(search)[d] = EF(qfrc_smooth)[d] + EF(qfrc_constraint)[d];
   WSYNC();
-  chol_factor_w(EF(H), nv);
-  chol_solve_w(EF(H), EF(search), nv);
+  chol_factor_w(EF(H), nv, 1);
+  chol_solve_w(EF(H), EF(search), nv, 1);
   #pragma unroll 1
   PFOR(d, nv) EF(qvel)[d] += h * EF(search)[d];
   WSYNC();
@@ -860,7 +877,7 @@ MGS_DEVN int step_w(Env &e, int nstep, int *steps_done) {
   for (int k = 0; k < nstep; k++) {
     if (e.bad || bad_state_w(e, 0)) { e.bad = 1; return 1; }
     forward_w(e);
-    MGS_STAGE_BARRIER();
+    MGS_STAGE_BARRIER(5);
     if (bad_state_w(e, 1)) { e.bad = 1; return 1; }
     integrate_w(e);
     (*steps_done)++;

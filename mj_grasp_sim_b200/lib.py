@@ -61,11 +61,13 @@ def bind(L, prefix="mgs_"):
     g("step_host").argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     if prefix == "mgs_":
         L.mgs_model_create.argtypes = [C.POINTER(MgsModelDesc), C.c_int, C.POINTER(vp)]
+        L.mgs_model_create_ex.argtypes = [C.POINTER(MgsModelDesc), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
         L.mgs_grasp_collision_mask.argtypes = [vp, C.c_int, fp, fp, C.c_int, ip, C.c_int, u8p]
         L.mgs_grasp_stability.argtypes = [vp, C.c_int, fp, fp, C.c_int, ip, C.c_int, dp, C.POINTER(MgsRolloutCfg), u8p, ip]
         L.mgs_rollout_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, ip, C.c_int, dp, C.POINTER(MgsRolloutCfg), vp, vp, vp]
         L.mgs_step_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
         L.mgs_launch_count.restype = C.c_longlong
+        L.mgs_overflow_count.argtypes = [vp]
     else:
         L.l1_model_create.argtypes = [C.POINTER(MgsModelDesc), C.POINTER(vp)]
         L.l1_rollout_host.argtypes = [vp, C.c_int, C.c_int, fp, fp, C.c_int, ip, C.c_int, dp, C.POINTER(MgsRolloutCfg), u8p, ip]
@@ -98,14 +100,16 @@ class BatchSim:
     through the same wrapper; product code always uses the defaults (the CUDA library).
     """
 
-    def __init__(self, model, device: int = 0, f64: bool = False, lib=None, prefix: str = "mgs_"):
+    def __init__(self, model, device: int = 0, f64: bool = False, lib=None, prefix: str = "mgs_", ncon_max: int = 0, nefc_max: int = 0):
         self.model = model
         self.L = lib if lib is not None else load(f64)
         self.p = prefix
         self.desc, self._keep = make_desc(model)
         h = C.c_void_p()
         if prefix == "mgs_":
-            rc = self.L.mgs_model_create(C.byref(self.desc), device, C.byref(h))
+            ncon_max = ncon_max or int(os.environ.get("MGS_NCON_MAX", "0"))
+            nefc_max = nefc_max or int(os.environ.get("MGS_NEFC_MAX", "0"))
+            rc = self.L.mgs_model_create_ex(C.byref(self.desc), device, ncon_max, nefc_max, C.byref(h))
         else:
             rc = self.L.l1_model_create(C.byref(self.desc), C.byref(h))
         self._check(rc)
@@ -216,6 +220,13 @@ class BatchSim:
                                         C.byref(cfg), _u8(out), _ip(steps))
         self._check(rc)
         return out.astype(bool), steps
+
+    def overflow_count(self) -> int:
+        """Environments of the last launch that dropped contacts (capacity too small)."""
+        rc = self.L.mgs_overflow_count(self.h)
+        if rc < 0:
+            self._check(rc)
+        return rc
 
     def rollout_device(self, mode, n, d_pose7_ptr, d_joints_ptr, nj, joint_qposadr, base_qposadr, close_ctrl, cfg, d_labels_ptr,
                        d_steps_ptr, stream_ptr=0):
