@@ -6,6 +6,7 @@
 // instead of idling until the slowest lane of a fixed assignment finishes.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <string>
@@ -103,7 +104,9 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
   // CTA size = the warps-per-block that gives the most resident warps per SM (shared memory per
   // environment and the per-CTA reservation decide)
   int best_warps = 0;
+  const char *force_wpb = getenv("MGS_WARPS_PER_BLOCK");  // tuning knob: force the CTA size
   for (int w = 1; w <= MGS_MAX_WARPS_PER_BLOCK; w++) {
+    if (force_wpb && atoi(force_wpb) != w) continue;
     if ((size_t)env_bytes * w > prop.sharedMemPerBlockOptin) break;
     CU(cudaFuncSetAttribute(mgs_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, env_bytes * w));
     int occ = 0;

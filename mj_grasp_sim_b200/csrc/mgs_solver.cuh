@@ -644,31 +644,32 @@ MGS_DEVN void solve_noslip_w(Env &e) {
   real *T = EF(nsB);       // nv-vector scratch
   #pragma unroll 1
   PFOR(d, nv) EF(wvec)[d] = EF(qacc)[d] - EF(qacc_smooth)[d];
+  // one (contact, upper-triangle entry) per lane; M^-1 is block diagonal per kinematic tree
   #pragma unroll 1
-  PFOR(c, e.ncon) {
+  PFOR(idx, 6 * e.ncon) {
+    const int c = idx / 6, q = idx - 6 * c;
     const int i = IARR(EF(con_efc))[c];
     if (i < 0) continue;
     const int dim = LDG(MD.pair_condim + IARR(EF(con_pair))[c]);
     int n = dim - 1;
     if (n > 3) n = 3;
-    int q = 0;
+    // q -> (j,k), j <= k, packed row-major over the n x n upper triangle
+    int j = 0, k = q;
+    if (k >= n) { k -= n; j = 1; k += 1; if (k >= n) { k -= n; j = 2; k += 2; } }
+    if (j >= n || k >= n || q >= n * (n + 1) / 2) continue;
+    const real *Jj = EF(J) + (i + 1 + j) * nv, *Jk = EF(J) + (i + 1 + k) * nv;
+    real acc = 0;
     #pragma unroll 1
-    for (int j = 0; j < n; j++)
+    for (int a = 0; a < nv; a++) {
+      const real ja = Jj[a];
+      if (ja == 0) continue;
+      const int lo = LDG(MD.dof_treeadr + a), hi = lo + LDG(MD.dof_treenum + a);
+      real t = 0;
       #pragma unroll 1
-      for (int k = j; k < n; k++) {
-        const real *Jj = EF(J) + (i + 1 + j) * nv, *Jk = EF(J) + (i + 1 + k) * nv;
-        real acc = 0;
-        #pragma unroll 1
-        for (int a = 0; a < nv; a++) {
-          const real ja = Jj[a];
-          if (ja == 0) continue;
-          real t = 0;
-          #pragma unroll 1
-          for (int b2 = 0; b2 < nv; b2++) t += EF(Minv)[a * nv + b2] * Jk[b2];
-          acc += ja * t;
-        }
-        AC[6 * c + q++] = acc;
-      }
+      for (int b2 = lo; b2 < hi; b2++) t += EF(Minv)[a * nv + b2] * Jk[b2];
+      acc += ja * t;
+    }
+    AC[6 * c + q] = acc;
   }
   WSYNC();
   #pragma unroll 1
