@@ -1,0 +1,16 @@
+"""get_gripper(cfg): name -> gripper instance (/root/reference/mgs/gripper/selector.py:33-66).
+`cfg` is anything with a `.name` (the reference passes a Hydra node; Hydra is not required here)."""
+import numpy as np
+
+from ..util.geo.transforms import SE3Pose
+from .panda import GripperPanda
+
+_REGISTRY = {"PandaGripper": GripperPanda}
+
+
+def get_gripper(cfg, default_pose=None):
+    pose = SE3Pose(np.array([0, 0, 0]), np.array([1, 0, 0, 0]), type="wxyz") if default_pose is None else default_pose
+    name = cfg if isinstance(cfg, str) else cfg.name
+    if name not in _REGISTRY:
+        raise ValueError(f"Unknown gripper: {name}")
+    return _REGISTRY[name](pose)

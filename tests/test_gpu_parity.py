@@ -141,3 +141,28 @@ def test_device_pointer_entry_with_torch(libs, panda_cube):
                      info["close_ctrl"], sched, dl.data_ptr(), ds.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(dl.cpu().numpy().astype(bool), ref) and np.array_equal(ds.cpu().numpy(), rs)
+
+
+def test_mgs_env_api_and_cli_files(libs, tmp_path):
+    """The reference-facing Python surface end to end: candidates.npz -> filter_to_stable -> the two output files."""
+    from mj_grasp_sim_b200 import scenes
+    from mj_grasp_sim_b200.mgs.cli import filter_to_stable
+    from mj_grasp_sim_b200.mgs.obj.selector import get_object
+    mlib, orc = libs
+    obj = get_object("hull:1")
+    v, t = obj.mesh()
+    H, w = scenes.antipodal_candidates(v, t, 48, 1)
+    d = tmp_path / "PandaGripper" / "hull:1"
+    d.mkdir(parents=True)
+    np.savez(d / "candidates.npz", pose=H, joints=scenes.panda_width_to_joints(w))
+    free, stable = filter_to_stable.run("PandaGripper", "hull:1", str(tmp_path))
+    cf = np.load(d / "candidates_collision_free.npz")
+    st = np.load(d / "stable_grasps.npz")
+    assert cf["pose"].shape == (int(free.sum()), 4, 4) and cf["joints"].shape == (int(free.sum()), 2)
+    assert st["pose"].shape == (int(stable.sum()), 4, 4)
+    # same labels as the oracle on the same inputs
+    m, info, pose7, joints = scenes.workload("panda", "hull", 1, 48)
+    ofree, _ = _oracle_batch(orc, m, info, 0, pose7, joints, FULL)
+    assert (free == ofree).mean() >= 0.97
+    olab, _ = _oracle_batch(orc, m, info, 1, pose7[free], joints[free], FULL)
+    assert (stable == olab).mean() >= 0.97

@@ -1,0 +1,57 @@
+"""The `mgs` drop-in mirror: SE3Pose semantics, selectors, model equivalence, argument checks (CPU)."""
+import numpy as np
+import pytest
+
+from mj_grasp_sim_b200 import scenes
+from mj_grasp_sim_b200.mgs.env.gravityless_object_grasping import GravitylessObjectGrasping
+from mj_grasp_sim_b200.mgs.gripper.selector import get_gripper
+from mj_grasp_sim_b200.mgs.obj.selector import get_object
+from mj_grasp_sim_b200.mgs.util.geo.transforms import SE3Pose
+
+
+def test_se3pose_semantics():
+    p = SE3Pose(np.array([0.1, 0.2, 0.3]), np.array([1.0, 0, 0, 0]), "wxyz")
+    assert p.pos.dtype == np.float32 and p.quat.dtype == np.float32
+    assert p.to_mat().dtype == np.float32
+    with pytest.raises(AssertionError):
+        SE3Pose(np.zeros(3), np.array([2.0, 0, 0, 0]), "wxyz")  # not unit norm
+    H = np.eye(4)[None].repeat(3, 0)
+    H[:, :3, 3] = np.arange(9).reshape(3, 3) * 0.01
+    q = SE3Pose.from_mat(H)
+    assert len(q) == 3 and np.allclose(q[1].pos, H[1, :3, 3])
+    b2c = get_gripper("PandaGripper").base_to_contact_transform()
+    r = q @ b2c
+    assert np.allclose(r.pos, H[:, :3, 3] + [0, 0, -0.102], atol=1e-7)
+    assert np.allclose(np.abs(r.quat), [[0.70710677, 0, 0, 0.70710677]] * 3, atol=1e-6)
+    a = SE3Pose(np.array([0.1, 0.0, 0.0]), np.array([0.70710678, 0, 0, 0.70710678]), "wxyz")
+    inv = a.inverse()
+    assert np.allclose(a.pos, inv.pos) and np.allclose(a.quat, inv.quat)  # reference quirk: inverse() mutates self
+    assert np.allclose(inv.pos, [0, 0.1, 0], atol=1e-6)
+
+
+def test_env_matches_scene_builder_and_checks_arguments():
+    env = GravitylessObjectGrasping(get_gripper("PandaGripper"), get_object("hull:0"))
+    m2, info, pose7, joints = scenes.workload("panda", "hull", 0, 8)
+    for k in ("body_mass", "body_inertia", "hull_vert", "pair_friction", "qpos0", "eq_data"):
+        assert np.allclose(env.model.arr[k], m2.arr[k]), k
+    assert env.get_joint_idxs(env.gripper.get_actuator_joint_names()) == list(info["joint_qposadr"])
+    assert env.gripper.get_freejoint_idxs(env) == list(range(7))
+    assert env.get_joint_idxs(["no_such_joint"]) == [int(env.model.jnt_qposadr[-1])]  # reference quirk (simualtion.py:37-43)
+    v, t = env.obj.mesh()
+    H, w = scenes.antipodal_candidates(v, t, 8, 0)
+    p7, j32, jadr = env._process(SE3Pose.from_mat(H), scenes.panda_width_to_joints(w))
+    assert np.array_equal(p7, pose7) and np.allclose(j32, joints)
+    with pytest.raises(ValueError):
+        env._process(SE3Pose.from_mat(H), joints[:3])
+    with pytest.raises(ValueError):
+        env._process(SE3Pose.from_mat(H), np.zeros((8, 5)))
+
+
+def test_selectors_reject_unknown():
+    with pytest.raises(ValueError):
+        get_gripper("NoSuchGripper")
+    with pytest.raises(ValueError):
+        get_object("003_cracker_box")  # YCB assets are not shipped offline
+    cube = get_object("cube")
+    xml, assets = cube.to_xml()
+    assert 'name="geom:cube"' in xml and assets == {}
