@@ -55,6 +55,7 @@ typedef float real;
 #ifndef MGS_BAR_MASK
 #define MGS_BAR_MASK 63
 #endif
+// (Taking the barriers only every K-th step was measured too: K=2 -3 %, K=4 -34 %, K=8 -47 %.)
 #define MGS_STAGE_BARRIER(k) do { if ((MGS_BAR_MASK >> (k)) & 1) __syncthreads(); } while (0)
 #endif
 

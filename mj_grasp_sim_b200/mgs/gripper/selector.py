@@ -4,8 +4,10 @@ import numpy as np
 
 from ..util.geo.transforms import SE3Pose
 from .panda import GripperPanda
+from .robotiq2f85 import GripperRobotiq2f85
+from .vx300 import GripperVX300
 
-_REGISTRY = {"PandaGripper": GripperPanda}
+_REGISTRY = {"PandaGripper": GripperPanda, "Robotiq2f85Gripper": GripperRobotiq2f85, "VXGripper": GripperVX300}
 
 
 def get_gripper(cfg, default_pose=None):

@@ -40,6 +40,15 @@ CUBE_XML = """<worldbody><body name="{name}" pos="0 0 0" quat="1 0 0 0"><freejoi
 GRIPPERS = {
     "panda": dict(dir="panda", freejoint="freejoint", joints=["finger_joint1", "finger_joint2"], close_ctrl=[0.0, -0.04],
                   b2c_pos=[0, 0, -0.102], b2c_quat=[0.707106781, 0.0, 0.0, 0.707106781], repose=0),
+    # the reference lists two misnamed joints ("right_spring_link", "left_spring_link": robotiq2f85.py:275,279);
+    # mj_name2id -> -1 -> jnt_qposadr[-1] = the LAST joint (the object's free joint): reproduced via None
+    "robotiq2f85": dict(dir="robotiq2f85", freejoint="freejoint",
+                        joints=["right_driver_joint", "right_coupler_joint", None, "right_follower_joint",
+                                "left_driver_joint", "left_coupler_joint", None, "left_follower_joint"],
+                        close_ctrl=[255.0], b2c_pos=[0, 0, -0.15], b2c_quat=[1.0, 0.0, 0.0, 0.0], repose=0),
+    # b2c = Rz(90 deg) * Ry(-90 deg), offset (0,0,-0.12)  (vx300.py:242-257)
+    "vx300": dict(dir="vx300", freejoint="freejoint", joints=["left_finger", "right_finger"], close_ctrl=[0.021, -0.021],
+                  b2c_pos=[0, 0, -0.12], b2c_quat=[0.5, 0.5, -0.5, 0.5], repose=0),
 }
 
 
@@ -84,7 +93,7 @@ def build_scene(gripper: str, obj_xml: str, obj_assets: dict):
     model = compile_mjcf(GRAVITYLESS_XML.format(gripper=gx, object=obj_xml), {**ga, **obj_assets})
     g = GRIPPERS[gripper]
     info = dict(base_qposadr=int(model.jnt_qposadr[model.names["joint"][g["freejoint"]]]),
-                joint_qposadr=np.array([model.jnt_qposadr[model.names["joint"][j]] for j in g["joints"]], dtype=np.int32),
+                joint_qposadr=np.array([model.jnt_qposadr[model.names["joint"][j] if j is not None else -1] for j in g["joints"]], dtype=np.int32),
                 close_ctrl=np.array(g["close_ctrl"], dtype=np.float64), repose=g["repose"], gripper=gripper)
     return model, info
 
@@ -183,6 +192,11 @@ def workload(gripper: str, kind: str, seed: int, n: int, n_v: int = 32):
     pose7 = process_poses(H, gripper)
     if gripper == "panda":
         joints = panda_width_to_joints(width)
+    elif gripper == "vx300":
+        w = np.clip(np.clip(width + 0.045, 0.003, 0.114), 0.042, 0.114)  # _clamp_width then width_to_joints (vx300.py:284-294,337-339)
+        joints = np.stack([np.clip(0.5 * w, 0.021, 0.057), np.clip(-0.5 * w, -0.057, -0.021)], axis=-1)
+    elif gripper == "robotiq2f85":
+        joints = np.zeros((n, 8))  # open; the two misnamed columns then write 0 to the object's x - a no-op
     else:
         raise NotImplementedError(gripper)
     return model, info, pose7, joints.astype(np.float32)

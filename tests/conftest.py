@@ -23,3 +23,15 @@ def panda_cube():
 def panda_hull():
     from mj_grasp_sim_b200 import scenes
     return scenes.workload("panda", "hull", 0, 64)
+
+
+@pytest.fixture(scope="session")
+def robotiq_hull():
+    from mj_grasp_sim_b200 import scenes
+    return scenes.workload("robotiq2f85", "hull", 0, 48)
+
+
+@pytest.fixture(scope="session")
+def vx300_hull():
+    from mj_grasp_sim_b200 import scenes
+    return scenes.workload("vx300", "hull", 0, 48)

@@ -68,3 +68,29 @@ def test_rollout_labels_short_schedule(panda_hull):
     assert (free == ofree).all()
     assert (lab == olab).mean() >= 11 / 12
     assert np.array_equal(steps[lab == olab], osteps[lab == olab])
+
+
+@pytest.mark.parametrize("fixture,qtol", [("robotiq_hull", 2e-4), ("vx300_hull", 1e-4)])
+def test_other_grippers_first_steps_and_labels(request, fixture, qtol):
+    """Robotiq 2F-85 (4-bar linkage: connect + joint equalities, tendon actuator, 800-vertex hulls) and
+    ViperX 300 (condim-4 pads, impratio 10) through the same kernel source."""
+    m, info, pose7, joints = request.getfixturevalue(fixture)
+    s = OracleSim(m)
+    L = lane1.sim(m)
+    i = 0
+    s.reset()
+    s.place(pose7[i].astype(np.float64), info["base_qposadr"], joints[i].astype(np.float64), info["joint_qposadr"])
+    s.ctrl[:] = info["close_ctrl"]
+    st = L.pack_state(s.qpos.copy(), s.qvel.copy(), ctrl=s.ctrl.copy(), mocap_pos=s.mocap_pos[0].copy(), mocap_quat=s.mocap_quat[0].copy())
+    for k in range(5):
+        s.step(10)
+        st, d = L.step(st, 10, want_diag=True)
+        u = L.unpack_state(st)
+        assert d["overflow"][0] == 0 and d["bad"][0] == 0
+        assert np.abs(u["qpos"][0] - s.qpos).max() <= qtol * max(1.0, np.abs(s.qpos).max())
+    n = 6
+    sched = (500, 150, 30, 0, 0.02, 0.02)
+    lab, steps = L.stability(pose7[:n], joints[:n], info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], MgsRolloutCfg(*sched))
+    olab, osteps = batch(m, 1, pose7[:n].astype(np.float64), info["base_qposadr"], joints[:n].astype(np.float64), info["joint_qposadr"],
+                         info["close_ctrl"], RolloutCfg(*sched), 4)
+    assert (lab == olab).mean() >= 5 / 6

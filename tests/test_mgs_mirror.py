@@ -55,3 +55,16 @@ def test_selectors_reject_unknown():
     cube = get_object("cube")
     xml, assets = cube.to_xml()
     assert 'name="geom:cube"' in xml and assets == {}
+
+
+def test_robotiq_and_vx300_mirror_classes():
+    from mj_grasp_sim_b200 import scenes
+    for name, key in (("Robotiq2f85Gripper", "robotiq2f85"), ("VXGripper", "vx300")):
+        g = get_gripper(name)
+        env = GravitylessObjectGrasping(g, get_object("hull:0"))
+        m2, info, _, _ = scenes.workload(key, "hull", 0, 2)
+        assert np.allclose(env.model.body_mass, m2.body_mass)
+        assert env.get_joint_idxs(g.get_actuator_joint_names()) == list(info["joint_qposadr"])  # incl. the misnamed Robotiq joints
+        b2c = g.base_to_contact_transform()
+        assert np.allclose(b2c.pos, scenes.GRIPPERS[key]["b2c_pos"]) and np.allclose(b2c.quat, scenes.GRIPPERS[key]["b2c_quat"], atol=1e-6)
+        assert np.allclose(g.close_ctrl(), scenes.GRIPPERS[key]["close_ctrl"])
