@@ -116,11 +116,22 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
   for (int j = 0; j < nj; j++) nlim += d->jnt_limited[j] ? 1 : 0;
   int maxdim = 1;
   for (int p = 0; p < np; p++) if (d->pair_condim[p] > maxdim) maxdim = d->pair_condim[p];
-  // capacities (contacts beyond them are dropped and flagged in the diagnostics): 32 contacts,
-  // of which at most 24 may have the largest cone dimension
-  out.ncon_max = 32;
-  out.nefc_max = ne + nfr + nlim + 24 * maxdim;
-  if (out.nefc_max < ne + nfr + nlim + 32 * 3) out.nefc_max = ne + nfr + nlim + 32 * 3;
+  // Default capacities (contacts beyond them are dropped and flagged): twice the number of candidate
+  // pairs that involve a free single-body tree (a grasped object), clamped to [32, 64] contacts.
+  int nobjpair = 0;
+  for (int p = 0; p < np; p++) {
+    for (int side = 0; side < 2; side++) {
+      const int bd = d->cgeom_bodyid[side ? d->pair_geom2[p] : d->pair_geom1[p]];
+      bool leaf = true;
+      for (int c = 0; c < nb; c++) if (d->body_parentid[c] == bd && c != bd) leaf = false;
+      if (d->body_parentid[bd] == 0 && d->body_dofnum[bd] == 6 && leaf) { nobjpair++; break; }
+    }
+  }
+  int nc = 2 * nobjpair;
+  nc = nc < 32 ? 32 : (nc > 64 ? 64 : nc);
+  nc = (nc + 3) & ~3;
+  out.ncon_max = nc;
+  out.nefc_max = ne + nfr + nlim + nc * (maxdim < 3 ? 3 : maxdim);  // every contact slot can hold the largest cone
   return true;
 }
 

@@ -566,18 +566,34 @@ MGS_DEVN void solve_newton_w(Env &e) {
     if (!(d1 < 0) || sn < R_(1e-30)) break;
     const real d1_0 = d1;
     real gtol = fmax(MD.tolerance * MD.ls_tolerance * sqrt(sn) / scale, R_(50.0) * (real)REAL_EPS * fabs(d1_0));
-    real alpha = -d1 / d2, lo = 0, hi = -1;
+    // Exact line search on the convex, piecewise-smooth 1-D cost: zero of its monotone derivative.
+    // Newton steps while they stay inside the bracket [lo, hi]; otherwise the secant of the end
+    // derivatives; bisection when the same end moved twice in a row or two iterations did not halve the
+    // bracket (kinks where the second derivative jumps - cone zone changes - make plain Newton bounce).
+    // Without convergence the answer is `lo` (negative derivative: by convexity the cost went down).
+    real alpha = -d1 / d2, lo = 0, hi = -1, dlo = d1, dhi = 0, w1 = -1, w2 = -1;
+    int last_side = 0, same_side = 0, converged = 0;
     #pragma unroll 1
     for (int it = 0; it < MD.ls_iterations; it++) {
       ls_eval_w(e, alpha, &d1, &d2);
       d1 = wsum(d1) + g1 + alpha * g2; d2 = wsum(d2) + g2;
-      if (fabs(d1) < gtol) break;
-      if (d1 < 0) lo = alpha; else hi = alpha;
+      if (fabs(d1) < gtol) { converged = 1; break; }
+      const int side = d1 < 0 ? -1 : 1;
+      same_side = (side == last_side) ? same_side + 1 : 0;
+      last_side = side;
+      if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
       real an = alpha - d1 / d2;
-      if (hi > 0 && (an <= lo || an >= hi)) an = R_(0.5) * (lo + hi);
-      if (fabs(an - alpha) <= R_(4.0) * (real)REAL_EPS * fabs(alpha)) { alpha = an; break; }
+      if (hi < 0) { if (!(an > alpha)) an = 2 * alpha; }
+      else {
+        const real w = hi - lo;
+        if (!(an > lo && an < hi)) an = (same_side >= 1) ? R_(0.5) * (lo + hi) : lo - dlo * (hi - lo) / (dhi - dlo);
+        if (!(an > lo && an < hi) || (w2 > 0 && w > R_(0.5) * w2)) an = R_(0.5) * (lo + hi);
+        w2 = w1; w1 = w;
+        if (w <= R_(8.0) * (real)REAL_EPS * hi) break;
+      }
       alpha = an;
     }
+    if (!converged) alpha = lo > 0 ? lo : alpha;
     if (!(alpha > 0)) break;
     #pragma unroll 1
     PFOR(d, nv) { EF(qacc)[d] += alpha * EF(search)[d]; EF(Ma)[d] += alpha * EF(Mv)[d]; }
@@ -587,6 +603,17 @@ MGS_DEVN void solve_newton_w(Env &e) {
     real oldcost = cost;
     cost = wsum(constraint_update_w(e) + gauss_cost_w(e, EF(qacc)));
     WSYNC();
+    if (cost > oldcost) {
+      // never accept an uphill step: back to the previous iterate (forces consistent with it) and stop
+      #pragma unroll 1
+      PFOR(d, nv) { EF(qacc)[d] -= alpha * EF(search)[d]; EF(Ma)[d] -= alpha * EF(Mv)[d]; }
+      #pragma unroll 1
+      PFOR(i, e.nefc) EF(efc_jar)[i] -= alpha * EF(efc_jv)[i];
+      WSYNC();
+      cost = wsum(constraint_update_w(e) + gauss_cost_w(e, EF(qacc)));
+      WSYNC();
+      break;
+    }
     e.niter = iter + 1;
     tol_eff = fmax(MD.tolerance, R_(20.0) * (real)REAL_EPS * scale * fabs(cost));
     if (scale * (oldcost - cost) < tol_eff) break;

@@ -64,7 +64,7 @@ typedef struct OrcSim {
   double efc_diagApprox[NEFC_MAX], efc_KBIP[NEFC_MAX][4];
   int efc_type[NEFC_MAX], efc_id[NEFC_MAX], efc_state[NEFC_MAX];
   /* diagnostics */
-  int solver_niter, bad, nstep_done, ncon_overflow;
+  int solver_niter, bad, nstep_done, ncon_overflow, ncon_peak, nefc_peak;
   /* scratch */
   double *w1, *w2, *w3, *w4, *w5, *w6, *jtmp;
 } OrcSim;
@@ -1256,19 +1256,42 @@ static void solve_newton(OrcSim *s) {
       jv[i] = t;
     }
     double gtol = m->tolerance * m->ls_tolerance * sqrt(sn) / scale;
-    double d1, d2, alpha = 0, lo = 0, hi = -1;
+    /* exact line search on the convex, piecewise-smooth 1-D cost: find the zero of its (monotone)
+     * derivative.  Newton steps while they stay inside the bracket [lo, hi]; otherwise the secant of the
+     * bracket's end derivatives, or bisection when the same end moved twice in a row (kinks where the
+     * second derivative jumps - cone zone changes - defeat plain Newton).  If the tolerance is not met
+     * the answer is `lo`, a point with negative derivative: by convexity its cost is below the start's. */
+    double d1, d2, alpha = 0, lo = 0, hi = -1, dlo, dhi = 0;
+    int last_side = 0, same_side = 0, converged = 0;
+    double w1 = -1, w2 = -1; /* bracket widths one and two iterations ago */
     ls_eval(s, jar, jv, 0, g1, g2, &d1, &d2);
     if (d1 >= 0 || sn < 1e-300) break;
+    dlo = d1;
     alpha = -d1 / d2;
     for (int it = 0; it < m->ls_iterations; it++) {
       ls_eval(s, jar, jv, alpha, g1, g2, &d1, &d2);
-      if (fabs(d1) < gtol) break;
-      if (d1 < 0) lo = alpha; else hi = alpha;
+      if (fabs(d1) < gtol) { converged = 1; break; }
+      int side = d1 < 0 ? -1 : 1;
+      same_side = (side == last_side) ? same_side + 1 : 0;
+      last_side = side;
+      if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
       double an = alpha - d1 / d2;
-      if (hi > 0 && (an <= lo || an >= hi)) an = 0.5 * (lo + hi);
-      if (fabs(an - alpha) <= 1e-15 * fabs(alpha)) { alpha = an; break; }
+      if (hi < 0) { if (!(an > alpha)) an = 2 * alpha; }
+      else {
+        const double w = hi - lo;
+        if (!(an > lo && an < hi)) an = (same_side >= 1) ? 0.5 * (lo + hi) : lo - dlo * (hi - lo) / (dhi - dlo);
+        /* Newton/secant steps that bounce across a kink shrink the bracket too slowly: bisect whenever
+         * two iterations did not halve it */
+        if (!(an > lo && an < hi) || (w2 > 0 && w > 0.5 * w2)) an = 0.5 * (lo + hi);
+        w2 = w1; w1 = w;
+        if (w <= 1e-14 * hi) break;
+      }
       alpha = an;
     }
+    if (!converged) alpha = lo > 0 ? lo : alpha;
+#ifdef ORC_DEBUG
+    fprintf(stderr, "newton iter %d cost %.10g gradnorm %.4g alpha %.6g d1 %.4g lo %.4g hi %.4g conv %d\n", iter, cost, sqrt(gn), alpha, d1, lo, hi, converged);
+#endif
     if (alpha <= 0) break;
     for (int d = 0; d < nv; d++) { qacc[d] += alpha * search[d]; Ma[d] += alpha * Mv[d]; }
     for (int i = 0; i < nefc; i++) jar[i] += alpha * jv[i];
@@ -1277,7 +1300,18 @@ static void solve_newton(OrcSim *s) {
     double g = 0;
     for (int d = 0; d < nv; d++) g += (Ma[d] - s->qfrc_smooth[d]) * (qacc[d] - s->qacc_smooth[d]);
     cost += 0.5 * g;
+    if (cost > oldcost) {
+      /* never accept an uphill step (an unconverged line search that only had the first, overshooting
+       * point): go back to the previous iterate, whose forces are consistent with it, and stop */
+      for (int d = 0; d < nv; d++) { qacc[d] -= alpha * search[d]; Ma[d] -= alpha * Mv[d]; }
+      for (int i = 0; i < nefc; i++) jar[i] -= alpha * jv[i];
+      cost = constraint_update(s, jar, s->efc_force, hcone);
+      break;
+    }
     s->solver_niter = iter + 1;
+#ifdef ORC_DEBUG
+    fprintf(stderr, "   -> new cost %.10g (improvement %.4g)\n", cost, oldcost - cost);
+#endif
     if (scale * (oldcost - cost) < m->tolerance) break;
   }
   memcpy(s->efc_jar, jar, sizeof(double) * nefc);
@@ -1394,6 +1428,8 @@ void orc_forward(OrcSim *s) {
   int nv = m->nv;
   kinematics(s); com_pos(s); tendon(s); transmission(s); crb_factor(s);
   collision(s); make_constraint(s);
+  if (s->ncon > s->ncon_peak) s->ncon_peak = s->ncon;
+  if (s->nefc > s->nefc_peak) s->nefc_peak = s->nefc;
   com_vel(s); passive(s); rne(s); actuation(s);
   for (int d = 0; d < nv; d++) s->qfrc_smooth[d] = s->qfrc_passive[d] - s->qfrc_bias[d] + s->qfrc_actuator[d];
   memcpy(s->qacc_smooth, s->qfrc_smooth, sizeof(double) * nv);
@@ -1612,6 +1648,8 @@ ACC(qpos) ACC(qvel) ACC(ctrl) ACC(mocap_pos) ACC(mocap_quat) ACC(qacc_warmstart)
 ACC(gxpos) ACC(gxmat) ACC(M) ACC(qfrc_bias) ACC(qfrc_passive) ACC(qfrc_actuator) ACC(qfrc_smooth) ACC(qacc_smooth) ACC(qacc)
 ACC(qfrc_constraint) ACC(J) ACC(efc_pos) ACC(efc_D) ACC(efc_R) ACC(efc_aref) ACC(efc_force) ACC(efc_jar) ACC(subtree_com) ACC(cdof)
 int orc_ncon(OrcSim *s) { return s->ncon; }
+int orc_ncon_peak(OrcSim *s) { return s->ncon_peak; }
+int orc_nefc_peak(OrcSim *s) { return s->nefc_peak; }
 int orc_nefc(OrcSim *s) { return s->nefc; }
 int orc_niter(OrcSim *s) { return s->solver_niter; }
 int orc_bad(OrcSim *s) { return s->bad; }

@@ -47,7 +47,7 @@ def lib():
         for name in ("destroy", "reset", "forward", "kinematics_only", "collision_only"):
             getattr(L, "orc_" + name).argtypes = [C.c_void_p]
             getattr(L, "orc_" + name).restype = None
-        for name in ("ncon", "nefc", "niter", "bad", "contact_with_object"):
+        for name in ("ncon", "nefc", "niter", "bad", "contact_with_object", "ncon_peak", "nefc_peak"):
             getattr(L, "orc_" + name).argtypes = [C.c_void_p]
             getattr(L, "orc_" + name).restype = C.c_int
         L.orc_step.argtypes = [C.c_void_p, C.c_int]
