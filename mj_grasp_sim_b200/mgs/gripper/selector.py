@@ -6,8 +6,10 @@ from ..util.geo.transforms import SE3Pose
 from .panda import GripperPanda
 from .robotiq2f85 import GripperRobotiq2f85
 from .vx300 import GripperVX300
+from .allegro import GripperAllegro
+from .leap import GripperLeap
 
-_REGISTRY = {"PandaGripper": GripperPanda, "Robotiq2f85Gripper": GripperRobotiq2f85, "VXGripper": GripperVX300}
+_REGISTRY = {"PandaGripper": GripperPanda, "Robotiq2f85Gripper": GripperRobotiq2f85, "VXGripper": GripperVX300, "AllegroGripper": GripperAllegro, "LeapGripper": GripperLeap}
 
 
 def get_gripper(cfg, default_pose=None):

@@ -49,6 +49,17 @@ GRIPPERS = {
     # b2c = Rz(90 deg) * Ry(-90 deg), offset (0,0,-0.12)  (vx300.py:242-257)
     "vx300": dict(dir="vx300", freejoint="freejoint", joints=["left_finger", "right_finger"], close_ctrl=[0.021, -0.021],
                   b2c_pos=[0, 0, -0.12], b2c_quat=[0.5, 0.5, -0.5, 0.5], repose=0),
+    # allegro.py:300-347 (open/close poses, b2c = Ry(-90 deg) with offset Ry(-90 deg) * (-0.08, 0, 0.01))
+    "allegro": dict(dir="allegro", freejoint="freejoint", joints=[f"{f}j{k}" for f in ("ff", "mf", "rf", "th") for k in range(4)],
+                    close_ctrl=[-0.08, 0.95, 1, 0.95, 0, 0.95, 1.2, 0.85, 0.08, 0.95, 1.2, 0.9, 1.4, 0.55, 0.29, 1.45],
+                    open_pose=[-0.08, 0.715, 0.710, 0.95, 0, 0.8, 0.71, 0.67, 0.08, 0.715, 0.710, 0.95, 1.4, 0.55, -0.19, 1.45],
+                    b2c_pos=[-0.01, 0.0, -0.08], b2c_quat=[0.70710678, 0.0, -0.70710678, 0.0], repose=1),
+    # leap.py:373-398; pre-grasp joints of the reference's contact sampler (mgs/sampler/kin/leap.py:462-484)
+    "leap": dict(dir="leap", freejoint="freejoint",
+                 joints=[f"{f}_{j}" for f, js in (("if", ("mcp", "rot", "pip", "dip")), ("mf", ("mcp", "rot", "pip", "dip")),
+                                                  ("rf", ("mcp", "rot", "pip", "dip")), ("th", ("cmc", "axl", "mcp", "ipl"))) for j in js],
+                 close_ctrl=[0.576, 0.0, 1.43, 0.453, 0.856, 0.0, 0.68, 0.826, 0.945, 0.0, 1.3, 0.2, 1.81, 0.258, 0.505, 0.351],
+                 open_pose=[0.785, 0, 0, 0] * 4, b2c_pos=[0, 0, 0], b2c_quat=[1.0, 0.0, 0.0, 0.0], repose=1),
 }
 
 
@@ -189,12 +200,28 @@ def workload(gripper: str, kind: str, seed: int, n: int, n_v: int = 32):
         ox, oa, (verts, tri) = hull_object_fragment(seed, n_v)
     model, info = build_scene(gripper, ox, oa)
     H, width = antipodal_candidates(verts, tri, n, seed)
+    if gripper == "leap":
+        # The reference's LEAP candidates come from its contact sampler (palm poses, identity b2c); that
+        # sampler is out of scope, so the harness turns the antipodal frame into a palm pose: fingers point
+        # along -z of the palm and close along its x axis around the point c (palm frame), hence
+        # palm = frame * [Rx(180 deg), -Rx(180 deg) c].
+        Rx = np.diag([1.0, -1.0, -1.0])
+        T = np.eye(4)
+        T[:3, :3] = Rx
+        T[:3, 3] = -Rx @ np.array([0.0, -0.035, -0.09])
+        H = H @ T
     pose7 = process_poses(H, gripper)
     if gripper == "panda":
         joints = panda_width_to_joints(width)
     elif gripper == "vx300":
         w = np.clip(np.clip(width + 0.045, 0.003, 0.114), 0.042, 0.114)  # _clamp_width then width_to_joints (vx300.py:284-294,337-339)
         joints = np.stack([np.clip(0.5 * w, 0.021, 0.057), np.clip(-0.5 * w, -0.057, -0.021)], axis=-1)
+    elif gripper in ("allegro", "leap"):
+        # pre-grasp posture + N(0, 0.05), clipped to the joint ranges
+        rng = np.random.default_rng(3000 + seed)
+        joints = np.asarray(GRIPPERS[gripper]["open_pose"])[None] + rng.normal(scale=0.05, size=(n, 16))
+        jid = [model.names["joint"][j] for j in GRIPPERS[gripper]["joints"]]
+        joints = np.clip(joints, model.jnt_range[jid, 0], model.jnt_range[jid, 1])
     elif gripper == "robotiq2f85":
         joints = np.zeros((n, 8))  # open; the two misnamed columns then write 0 to the object's x - a no-op
     else:

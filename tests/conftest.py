@@ -35,3 +35,15 @@ def robotiq_hull():
 def vx300_hull():
     from mj_grasp_sim_b200 import scenes
     return scenes.workload("vx300", "hull", 0, 48)
+
+
+@pytest.fixture(scope="session")
+def allegro_hull():
+    from mj_grasp_sim_b200 import scenes
+    return scenes.workload("allegro", "hull", 0, 48)
+
+
+@pytest.fixture(scope="session")
+def leap_hull():
+    from mj_grasp_sim_b200 import scenes
+    return scenes.workload("leap", "hull", 0, 32)

@@ -94,3 +94,18 @@ def test_other_grippers_first_steps_and_labels(request, fixture, qtol):
     olab, osteps = batch(m, 1, pose7[:n].astype(np.float64), info["base_qposadr"], joints[:n].astype(np.float64), info["joint_qposadr"],
                          info["close_ctrl"], RolloutCfg(*sched), 4)
     assert (lab == olab).mean() >= 5 / 6
+
+
+@pytest.mark.parametrize("fixture", ["allegro_hull", "leap_hull"])
+def test_dexterous_hands_short_rollouts(request, fixture):
+    """Allegro (capsules + boxes, 16 hinge actuators, geom-derived inertias) and LEAP (67 boxes + 4 tip
+    meshes, 22 dry-friction dofs, top-level defaults leaking into the scene): nv = 28, tree depth 5."""
+    m, info, pose7, joints = request.getfixturevalue(fixture)
+    assert (m.nq, m.nv, m.nu) == (30, 28, 16)
+    n = 8
+    sched = (400, 150, 30, 1, 0.02, 0.02)
+    L = lane1.sim(m, f64=True)
+    lab, steps = L.stability(pose7[:n], joints[:n], info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], MgsRolloutCfg(*sched))
+    olab, osteps = batch(m, 1, pose7[:n].astype(np.float64), info["base_qposadr"], joints[:n].astype(np.float64), info["joint_qposadr"],
+                         info["close_ctrl"], RolloutCfg(*sched), 4)
+    assert (lab == olab).mean() >= 7 / 8
