@@ -33,7 +33,7 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
   b.resize(16);
   memset(&m, 0, sizeof(m));
   if (d->nu > MGS_MAX_NU) { err = "too many actuators"; return false; }
-  if (d->nv > 32) { err = "nv > 32: the warp-per-environment kernel holds one dof per lane (env-per-block variant not built yet)"; return false; }
+  if (d->nv > 255) { err = "nv > 255 (the lower-triangle index table packs a dof index in 8 bits)"; return false; }
   if (d->nmocap > 1) { err = "at most one mocap body is supported"; return false; }
   for (int p = 0; p < d->npair; p++)
     if (d->pair_condim[p] != 1 && d->pair_condim[p] != 3 && d->pair_condim[p] != 4) { err = "condim must be 1, 3 or 4"; return false; }

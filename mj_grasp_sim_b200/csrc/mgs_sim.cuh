@@ -159,29 +159,34 @@ MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
   }
 }
 #else
-// GPU: lane i owns row i (n <= 32); every block advances one pivot column per step
+// GPU: lanes own rows (row i on lane i % 32); every diagonal block advances one pivot column per step
 MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
   const int nsteps = blocked ? MD.max_tree_dofs : n;
-  const int i = MGS_LANE;
-  int tadr = 0, tnum = n;
-  if (blocked && i < n) { tadr = LDG(MD.dof_treeadr + i); tnum = LDG(MD.dof_treenum + i); }
   #pragma unroll 1
   for (int t = 0; t < nsteps; t++) {
-    const int j = tadr + t;
-    const int live = (i < n) && (t < tnum);
     WSYNC();
-    real d = 1;
-    if (live) { d = A[j * n + j]; d = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL); }
-    WSYNC();
-    if (live) {
-      if (i == j) A[j * n + j] = d;
-      else if (i > j) A[i * n + j] *= R_(1.0) / d;
+    #pragma unroll 1
+    PFOR(i, n) {  // pivot rows: sqrt of the diagonal
+      const int j = blocked ? LDG(MD.dof_treeadr + i) + t : t;
+      if (i == j) { const real d = A[j * n + j]; A[j * n + j] = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL); }
     }
     WSYNC();
-    if (live && i > j) {
-      const real lij = A[i * n + j];
-      #pragma unroll 1
-      for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+    #pragma unroll 1
+    PFOR(i, n) {  // scale the pivot column
+      const int j = blocked ? LDG(MD.dof_treeadr + i) + t : t;
+      const int live = blocked ? (t < LDG(MD.dof_treenum + i)) : 1;
+      if (live && i > j) A[i * n + j] /= A[j * n + j];
+    }
+    WSYNC();
+    #pragma unroll 1
+    PFOR(i, n) {  // trailing update of this lane's rows
+      const int j = blocked ? LDG(MD.dof_treeadr + i) + t : t;
+      const int live = blocked ? (t < LDG(MD.dof_treenum + i)) : 1;
+      if (live && i > j) {
+        const real lij = A[i * n + j];
+        #pragma unroll 1
+        for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+      }
     }
   }
   WSYNC();
@@ -189,31 +194,26 @@ MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
 // x <- (L L')^-1 x (column-oriented substitution)
 MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
   const int nsteps = blocked ? MD.max_tree_dofs : n;
-  const int i = MGS_LANE;
-  int tadr = 0, tnum = n;
-  if (blocked && i < n) { tadr = LDG(MD.dof_treeadr + i); tnum = LDG(MD.dof_treenum + i); }
   #pragma unroll 1
-  for (int t = 0; t < nsteps; t++) {
-    const int k = tadr + t, live = (i < n) && (t < tnum);
-    WSYNC();
-    real xk = 0;
-    if (live) xk = x[k] / L[k * n + k];
-    WSYNC();
-    if (live) {
-      if (i == k) x[k] = xk;
-      else if (i > k) x[i] -= L[i * n + k] * xk;
-    }
-  }
-  #pragma unroll 1
-  for (int t = nsteps - 1; t >= 0; t--) {
-    const int k = tadr + t, live = (i < n) && (t < tnum);
-    WSYNC();
-    real xk = 0;
-    if (live) xk = x[k] / L[k * n + k];
-    WSYNC();
-    if (live) {
-      if (i == k) x[k] = xk;
-      else if (i < k) x[i] -= L[k * n + i] * xk;
+  for (int pass = 0; pass < 2; pass++) {
+    #pragma unroll 1
+    for (int tt = 0; tt < nsteps; tt++) {
+      const int t = pass == 0 ? tt : nsteps - 1 - tt;
+      WSYNC();
+      #pragma unroll 1
+      PFOR(i, n) {
+        const int k = blocked ? LDG(MD.dof_treeadr + i) + t : t;
+        if (i == k) x[k] /= L[k * n + k];
+      }
+      WSYNC();
+      #pragma unroll 1
+      PFOR(i, n) {
+        const int k = blocked ? LDG(MD.dof_treeadr + i) + t : t;
+        const int live = blocked ? (t < LDG(MD.dof_treenum + i)) : 1;
+        if (!live) continue;
+        if (pass == 0 && i > k) x[i] -= L[i * n + k] * x[k];
+        else if (pass == 1 && i < k) x[i] -= L[k * n + i] * x[k];
+      }
     }
   }
   WSYNC();

@@ -8,8 +8,9 @@ from .robotiq2f85 import GripperRobotiq2f85
 from .vx300 import GripperVX300
 from .allegro import GripperAllegro
 from .leap import GripperLeap
+from .shadow import GripperShadowRight
 
-_REGISTRY = {"PandaGripper": GripperPanda, "Robotiq2f85Gripper": GripperRobotiq2f85, "VXGripper": GripperVX300, "AllegroGripper": GripperAllegro, "LeapGripper": GripperLeap}
+_REGISTRY = {"PandaGripper": GripperPanda, "Robotiq2f85Gripper": GripperRobotiq2f85, "VXGripper": GripperVX300, "AllegroGripper": GripperAllegro, "LeapGripper": GripperLeap, "ShadowHand": GripperShadowRight}
 
 
 def get_gripper(cfg, default_pose=None):

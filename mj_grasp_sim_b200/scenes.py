@@ -60,6 +60,17 @@ GRIPPERS = {
                                                   ("rf", ("mcp", "rot", "pip", "dip")), ("th", ("cmc", "axl", "mcp", "ipl"))) for j in js],
                  close_ctrl=[0.576, 0.0, 1.43, 0.453, 0.856, 0.0, 0.68, 0.826, 0.945, 0.0, 1.3, 0.2, 1.81, 0.258, 0.505, 0.351],
                  open_pose=[0.785, 0, 0, 0] * 4, b2c_pos=[0, 0, 0], b2c_quat=[1.0, 0.0, 0.0, 0.0], repose=1),
+    # shadow.py:368-455; close ctrl = _qpos_to_qacc(22-vector) -> 18 actuators; pre-grasp joints of the reference's
+    # contact sampler (mgs/sampler/kin/shadow.py:200-227)
+    "shadow": dict(dir="shadow", freejoint="freejoint",
+                   joints=["rh_FFJ4", "rh_FFJ3", "rh_FFJ2", "rh_FFJ1", "rh_MFJ4", "rh_MFJ3", "rh_MFJ2", "rh_MFJ1", "rh_RFJ4", "rh_RFJ3",
+                           "rh_RFJ2", "rh_RFJ1", "rh_LFJ5", "rh_LFJ4", "rh_LFJ3", "rh_LFJ2", "rh_LFJ1", "rh_THJ5", "rh_THJ4", "rh_THJ3",
+                           "rh_THJ2", "rh_THJ1"],
+                   close_ctrl=[0.07708, 1.21, 0.2023, 0.6614, 0.0102, -0.3464, 1.253, 0.782494, 0.01103, 1.475, 0.6336, -0.2083, 1.45,
+                               0.75, 0.13, -0.4, 1.5, 1.3],
+                   open_pose=[-0.350, 0.425, 0.015, 0.005, -0.095, 0.415, 0.010, 0.0, -0.075, 0.435, 0.015, 0.005, 0.0, -0.220, 0.255,
+                              0.0, 0.0, -0.480, 1.05, -0.19, -0.080, 0.45],
+                   b2c_pos=[0, 0, 0], b2c_quat=[1.0, 0.0, 0.0, 0.0], repose=0),
 }
 
 
@@ -210,16 +221,25 @@ def workload(gripper: str, kind: str, seed: int, n: int, n_v: int = 32):
         T[:3, :3] = Rx
         T[:3, 3] = -Rx @ np.array([0.0, -0.035, -0.09])
         H = H @ T
+    if gripper == "shadow":
+        # same idea for the Shadow wrist frame: fingers extend along +z, the palm faces -y and the thumb
+        # opposes the fingers along z, closing around c = (0.01, -0.06, 0.12)
+        Rt = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
+        T = np.eye(4)
+        T[:3, :3] = Rt
+        T[:3, 3] = -Rt @ np.array([0.01, -0.06, 0.12])
+        H = H @ T
     pose7 = process_poses(H, gripper)
     if gripper == "panda":
         joints = panda_width_to_joints(width)
     elif gripper == "vx300":
         w = np.clip(np.clip(width + 0.045, 0.003, 0.114), 0.042, 0.114)  # _clamp_width then width_to_joints (vx300.py:284-294,337-339)
         joints = np.stack([np.clip(0.5 * w, 0.021, 0.057), np.clip(-0.5 * w, -0.057, -0.021)], axis=-1)
-    elif gripper in ("allegro", "leap"):
+    elif gripper in ("allegro", "leap", "shadow"):
         # pre-grasp posture + N(0, 0.05), clipped to the joint ranges
         rng = np.random.default_rng(3000 + seed)
-        joints = np.asarray(GRIPPERS[gripper]["open_pose"])[None] + rng.normal(scale=0.05, size=(n, 16))
+        op = np.asarray(GRIPPERS[gripper]["open_pose"])
+        joints = op[None] + rng.normal(scale=0.05, size=(n, len(op)))
         jid = [model.names["joint"][j] for j in GRIPPERS[gripper]["joints"]]
         joints = np.clip(joints, model.jnt_range[jid, 0], model.jnt_range[jid, 1])
     elif gripper == "robotiq2f85":

@@ -47,3 +47,9 @@ def allegro_hull():
 def leap_hull():
     from mj_grasp_sim_b200 import scenes
     return scenes.workload("leap", "hull", 0, 32)
+
+
+@pytest.fixture(scope="session")
+def shadow_hull():
+    from mj_grasp_sim_b200 import scenes
+    return scenes.workload("shadow", "hull", 0, 32)

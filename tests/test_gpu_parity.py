@@ -169,13 +169,13 @@ def test_mgs_env_api_and_cli_files(libs, tmp_path):
     assert (stable == olab).mean() >= 0.97
 
 
-@pytest.mark.parametrize("fixture,bar", [("allegro_hull", 0.9), ("leap_hull", 0.85)])
+@pytest.mark.parametrize("fixture,bar", [("allegro_hull", 0.9), ("leap_hull", 0.85), ("shadow_hull", 0.85)])
 def test_dexterous_hands_labels(libs, request, fixture, bar):
     """16-DoF hands (config 4): hand-object contact is far more chaotic than a parallel-jaw pinch, so the
     fp32 bar on a small batch is lower; tools/label_agreement.py reports the measured rates at scale."""
     mlib, orc = libs
     m, info, pose7, joints = request.getfixturevalue(fixture)
-    sched = (3000, 3000, 500, 1, 0.1, 0.02)
+    sched = (3000, 3000, 500, 0 if fixture == "shadow_hull" else 1, 0.1, 0.02)
     G = mlib.BatchSim(m)
     lab, steps = G.stability(pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], mlib.MgsRolloutCfg(*sched))
     olab, osteps = _oracle_batch(orc, m, info, 1, pose7, joints, sched)

@@ -96,6 +96,20 @@ def test_other_grippers_first_steps_and_labels(request, fixture, qtol):
     assert (lab == olab).mean() >= 5 / 6
 
 
+def test_shadow_hand_short_rollouts(shadow_hull):
+    """Shadow hand: nv = 34 > 32 lanes (rows are strided over lanes), 18 actuators of which 4 drive fixed
+    tendons, cylinders / capsules / spheres / meshes, impratio 10."""
+    m, info, pose7, joints = shadow_hull
+    assert (m.nq, m.nv, m.nu, int(m.arr["ntendon"])) == (36, 34, 18, 4)
+    n = 6
+    sched = (400, 120, 20, 0, 0.02, 0.02)
+    L = lane1.sim(m, f64=True)
+    lab, steps = L.stability(pose7[:n], joints[:n], info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], MgsRolloutCfg(*sched))
+    olab, osteps = batch(m, 1, pose7[:n].astype(np.float64), info["base_qposadr"], joints[:n].astype(np.float64), info["joint_qposadr"],
+                         info["close_ctrl"], RolloutCfg(*sched), 4)
+    assert (lab == olab).mean() >= 5 / 6
+
+
 @pytest.mark.parametrize("fixture", ["allegro_hull", "leap_hull"])
 def test_dexterous_hands_short_rollouts(request, fixture):
     """Allegro (capsules + boxes, 16 hinge actuators, geom-derived inertias) and LEAP (67 boxes + 4 tip

@@ -59,7 +59,7 @@ def test_selectors_reject_unknown():
 
 def test_robotiq_and_vx300_mirror_classes():
     from mj_grasp_sim_b200 import scenes
-    for name, key in (("Robotiq2f85Gripper", "robotiq2f85"), ("VXGripper", "vx300"), ("AllegroGripper", "allegro"), ("LeapGripper", "leap")):
+    for name, key in (("Robotiq2f85Gripper", "robotiq2f85"), ("VXGripper", "vx300"), ("AllegroGripper", "allegro"), ("LeapGripper", "leap"), ("ShadowHand", "shadow")):
         g = get_gripper(name)
         env = GravitylessObjectGrasping(g, get_object("hull:0"))
         m2, info, _, _ = scenes.workload(key, "hull", 0, 2)

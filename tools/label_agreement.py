@@ -11,7 +11,7 @@ from oracle.oracle import RolloutCfg, batch
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 rows = []
 for gripper, kind, seeds in (("panda", "cube", [0]), ("panda", "hull", [0, 1]), ("vx300", "hull", [0, 1]), ("robotiq2f85", "hull", [0, 1]),
-                             ("allegro", "hull", [0]), ("leap", "hull", [0])):
+                             ("allegro", "hull", [0]), ("leap", "hull", [0]), ("shadow", "hull", [0])):
     for seed in seeds:
         m, info, pose7, joints = scenes.workload(gripper, kind, seed, n)
         rep = scenes.GRIPPERS[gripper]["repose"]
