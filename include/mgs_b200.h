@@ -68,6 +68,27 @@ int mgs_rollout_device(MgsModel *model, int mode, int n, const float *d_pose7, c
                        const int *joint_qposadr, int base_qposadr, const double *close_ctrl,
                        const MgsRolloutCfg *cfg, uint8_t *d_labels, int *d_steps, void *stream);
 
+/* Clutter table (reference: mgs/env/clutter_table.py).  `scene` is the settled scene every candidate starts
+ * from - what the reference restores with mj_setState(..., mjSTATE_INTEGRATION) at the top of each iteration
+ * (:291, :356) - as one state record of MgsModelInfo.state_stride values:
+ * qpos[nq] qvel[nv] qacc_warmstart[nv] ctrl[nu] mocap_pos[3] mocap_quat[4].
+ *   mgs_clutter_collision_mask  the loop body of ClutterTableEnv.grasp_collision_mask (:356-364); the workspace
+ *                               bounds test on the unprocessed pose (:344-354) stays on the host
+ *   mgs_clutter_stable_mask     the loop body of ClutterTableEnv.grasp_stable_mask (:288-317): close nstep_close,
+ *                               lift lift_dist over nstep_lift with check_gripper_contact every 100 steps
+ *                               (cfg.shake_* are ignored)
+ * The model's ground_geomid must be the id of "geom:table". */
+int mgs_clutter_collision_mask(MgsModel *model, int n, const double *scene, const float *pose7, const float *joints, int nj,
+                               const int *joint_qposadr, int base_qposadr, uint8_t *collision_free_out);
+int mgs_clutter_stable_mask(MgsModel *model, int n, const double *scene, const float *pose7, const float *joints, int nj,
+                            const int *joint_qposadr, int base_qposadr, const double *close_ctrl, const MgsRolloutCfg *cfg,
+                            uint8_t *stable_out, int *steps_out);
+/* device-pointer variant: mode 3 = clutter collision mask, 4 = clutter stable mask; d_scene holds the record
+ * in the library's compute type (float, or double in the ablation build) */
+int mgs_clutter_device(MgsModel *model, int mode, int n, const void *d_scene, const float *d_pose7, const float *d_joints, int nj,
+                       const int *joint_qposadr, int base_qposadr, const double *close_ctrl, const MgsRolloutCfg *cfg,
+                       uint8_t *d_labels, int *d_steps, void *stream);
+
 /* Batched mj_step on explicit states.  State record (state_stride reals, env-major):
  * qpos[nq] qvel[nv] qacc_warmstart[nv] ctrl[nu] mocap_pos[3] mocap_quat[4].  nstep = 0 runs
  * mj_forward only.  diag (may be NULL) receives diag_stride reals per env: header

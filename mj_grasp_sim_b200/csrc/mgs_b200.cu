@@ -191,7 +191,7 @@ static int fill_params(const MgsModel *M, RolloutParams &prm, int mode, int n, i
     if (joint_qposadr[k] < 0 || joint_qposadr[k] >= M->dm.nq) return fail("bad joint_qposadr");
     prm.joint_qposadr[k] = joint_qposadr[k];
   }
-  if (mode == MGS_MODE_STABILITY) {
+  if (mode == MGS_MODE_STABILITY || mode == MGS_MODE_CLUTTER_STABLE) {
     if (!cfg || !close_ctrl) return fail("stability rollout needs cfg and close_ctrl");
     prm.nstep_close = cfg->nstep_close; prm.nstep_lift = cfg->nstep_lift; prm.shake_steps = cfg->shake_steps;
     prm.repose_on_close = cfg->repose_on_close; prm.lift_dist = (real)cfg->lift_dist; prm.shake_dist = (real)cfg->shake_dist;
@@ -214,6 +214,22 @@ extern "C" int mgs_rollout_device(MgsModel *M, int mode, int n, const float *d_p
   return launch(M, prm, io, (cudaStream_t)stream);
 }
 
+extern "C" int mgs_clutter_device(MgsModel *M, int mode, int n, const void *d_scene, const float *d_pose7, const float *d_joints, int nj,
+                                  const int *joint_qposadr, int base_qposadr, const double *close_ctrl, const MgsRolloutCfg *cfg,
+                                  uint8_t *d_labels, int *d_steps, void *stream) {
+  if (!M) return fail("null model");
+  if (mode != MGS_MODE_CLUTTER_COLLISION && mode != MGS_MODE_CLUTTER_STABLE) return fail("bad mode");
+  if (!d_scene) return fail("clutter rollouts need the scene state record");
+  CU(cudaSetDevice(M->device));
+  RolloutParams prm;
+  if (fill_params(M, prm, mode, n, nj, joint_qposadr, base_qposadr, close_ctrl, cfg)) return -1;
+  BatchIO io;
+  memset(&io, 0, sizeof(io));
+  io.pose7 = d_pose7; io.joints = d_joints; io.labels = d_labels; io.steps = d_steps;
+  io.state_in = (const real *)d_scene; io.state_stride = M->state_stride;
+  return launch(M, prm, io, (cudaStream_t)stream);
+}
+
 static int ensure_stage(MgsModel *M, size_t bytes) {
   if (bytes <= M->stage_bytes) return 0;
   if (M->d_stage) cudaFree(M->d_stage);
@@ -229,19 +245,25 @@ static int ensure_stage(MgsModel *M, size_t bytes) {
 static size_t up256(size_t x) { return (x + 255) & ~size_t(255); }
 
 static int rollout_host(MgsModel *M, int mode, int n, const float *pose7, const float *joints, int nj, const int *joint_qposadr,
-                        int base_qposadr, const double *close_ctrl, const MgsRolloutCfg *cfg, uint8_t *labels, int *steps) {
+                        int base_qposadr, const double *close_ctrl, const MgsRolloutCfg *cfg, uint8_t *labels, int *steps,
+                        const double *scene = nullptr) {
   if (!M) return fail("null model");
   if (n <= 0) return 0;
   CU(cudaSetDevice(M->device));
-  size_t o_pose = 0, o_joint = up256(o_pose + (size_t)n * 7 * 4), o_lab = up256(o_joint + (size_t)n * (nj > 0 ? nj : 1) * 4),
-         o_steps = up256(o_lab + (size_t)n), total = up256(o_steps + (size_t)n * 4);
+  const size_t scene_bytes = scene ? (size_t)M->state_stride * sizeof(real) : 0;
+  size_t o_pose = 0, o_joint = up256(o_pose + (size_t)n * 7 * 4), o_scene = up256(o_joint + (size_t)n * (nj > 0 ? nj : 1) * 4),
+         o_lab = up256(o_scene + scene_bytes), o_steps = up256(o_lab + (size_t)n), total = up256(o_steps + (size_t)n * 4);
   if (ensure_stage(M, total)) return -1;
   char *h = (char *)M->h_stage, *d = (char *)M->d_stage;
   memcpy(h + o_pose, pose7, (size_t)n * 7 * 4);
   memcpy(h + o_joint, joints, (size_t)n * nj * 4);
+  if (scene) { real *sr = (real *)(h + o_scene); for (int i = 0; i < M->state_stride; i++) sr[i] = (real)scene[i]; }
   CU(cudaMemcpyAsync(d + o_pose, h + o_pose, o_lab, cudaMemcpyHostToDevice, M->stream));
-  int rc = mgs_rollout_device(M, mode, n, (const float *)(d + o_pose), (const float *)(d + o_joint), nj, joint_qposadr, base_qposadr,
-                              close_ctrl, cfg, (uint8_t *)(d + o_lab), (int *)(d + o_steps), M->stream);
+  int rc;
+  if (scene) rc = mgs_clutter_device(M, mode, n, d + o_scene, (const float *)(d + o_pose), (const float *)(d + o_joint), nj, joint_qposadr,
+                                     base_qposadr, close_ctrl, cfg, (uint8_t *)(d + o_lab), (int *)(d + o_steps), M->stream);
+  else rc = mgs_rollout_device(M, mode, n, (const float *)(d + o_pose), (const float *)(d + o_joint), nj, joint_qposadr, base_qposadr,
+                               close_ctrl, cfg, (uint8_t *)(d + o_lab), (int *)(d + o_steps), M->stream);
   if (rc) return rc;
   CU(cudaMemcpyAsync(h + o_lab, d + o_lab, total - o_lab, cudaMemcpyDeviceToHost, M->stream));
   CU(cudaStreamSynchronize(M->stream));
@@ -259,6 +281,20 @@ extern "C" int mgs_grasp_stability(MgsModel *M, int n, const float *pose7, const
                                    int base_qposadr, const double *close_ctrl, const MgsRolloutCfg *cfg, uint8_t *stable_out,
                                    int *steps_out) {
   return rollout_host(M, MGS_MODE_STABILITY, n, pose7, joints, nj, joint_qposadr, base_qposadr, close_ctrl, cfg, stable_out, steps_out);
+}
+
+extern "C" int mgs_clutter_collision_mask(MgsModel *M, int n, const double *scene, const float *pose7, const float *joints, int nj,
+                                          const int *joint_qposadr, int base_qposadr, uint8_t *collision_free_out) {
+  if (!scene) return fail("null scene");
+  return rollout_host(M, MGS_MODE_CLUTTER_COLLISION, n, pose7, joints, nj, joint_qposadr, base_qposadr, nullptr, nullptr, collision_free_out,
+                      nullptr, scene);
+}
+
+extern "C" int mgs_clutter_stable_mask(MgsModel *M, int n, const double *scene, const float *pose7, const float *joints, int nj,
+                                       const int *joint_qposadr, int base_qposadr, const double *close_ctrl, const MgsRolloutCfg *cfg,
+                                       uint8_t *stable_out, int *steps_out) {
+  if (!scene) return fail("null scene");
+  return rollout_host(M, MGS_MODE_CLUTTER_STABLE, n, pose7, joints, nj, joint_qposadr, base_qposadr, close_ctrl, cfg, stable_out, steps_out, scene);
 }
 
 extern "C" int mgs_step_device(MgsModel *M, int n, int nstep, const void *d_state_in, void *d_state_out, void *d_diag_out, void *stream) {

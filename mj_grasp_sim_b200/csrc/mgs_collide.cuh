@@ -419,13 +419,16 @@ MGS_DEVN void collision_w(Env &e) {
 
 // gripper <-> object contact test (reference check_contact_with_object,
 // gravityless_object_grasping.py:309-321): a contact whose geom ids straddle the ground geom's id
-MGS_DEVN int contact_with_object_w(const Env &e) {
+// include_ground != 0: also count gripper <-> ground/table contacts (check_gripper_collision of the clutter
+// table, clutter_table.py:237-252)
+MGS_DEVN int contact_with_object_w(const Env &e, int include_ground) {
   int hit = 0, g = MD.ground_geomid;
   #pragma unroll 1
   PFOR(c, e.ncon) {
     int p = IARR(EF(con_pair))[c];
     int a = LDG(MD.cgeom_geomid + LDG(MD.pair_geom1 + p)), b = LDG(MD.cgeom_geomid + LDG(MD.pair_geom2 + p));
     if ((a < g && b > g) || (a > g && b < g)) hit = 1;
+    if (include_ground && ((a == g && b < g) || (a < g && b == g))) hit = 1;
   }
   return wany(hit);
 }

@@ -67,15 +67,15 @@ enum { GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_CYLINDER = 5, GEOM_BOX = 6, GEOM_
 enum { EQ_CONNECT = 0, EQ_WELD = 1, EQ_JOINT = 2 };
 enum { CT_EQUALITY = 0, CT_FRICTION_DOF = 1, CT_LIMIT = 2, CT_CONTACT = 3 };
 enum { ST_SATISFIED = 0, ST_QUADRATIC = 1, ST_LINEARNEG = 2, ST_LINEARPOS = 3, ST_CONE = 4 };
-enum { MGS_MODE_STEP = 0, MGS_MODE_COLLISION = 1, MGS_MODE_STABILITY = 2 };
+enum { MGS_MODE_STEP = 0, MGS_MODE_COLLISION = 1, MGS_MODE_STABILITY = 2, MGS_MODE_CLUTTER_COLLISION = 3, MGS_MODE_CLUTTER_STABLE = 4 };
 
 // Model constants on the device (all pointers into one read-only blob).
 struct DevModel {
   int nq, nv, nu, nbody, njnt, neq, nmocap, ntendon, nwrap, ncgeom, npair, nhull;
-  int maxdepth, max_tree_dofs, ne_rows, cone_elliptic, iterations, ls_iterations, noslip_iterations, mpr_iterations, ground_geomid;
+  int maxdepth, max_tree_dofs, ne_rows, ngravcomp, cone_elliptic, iterations, ls_iterations, noslip_iterations, mpr_iterations, ground_geomid;
   real timestep, impratio, tolerance, ls_tolerance, noslip_tolerance, mpr_tolerance, meaninertia, gravity[3];
   const int *body_parentid, *body_rootid, *body_mocapid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_depth;
-  const real *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0, *body_subtreemass;
+  const real *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0, *body_subtreemass, *body_gravcomp;
   const int *jnt_type, *jnt_bodyid, *jnt_qposadr, *jnt_dofadr, *jnt_limited;
   const real *jnt_pos, *jnt_axis, *jnt_range, *jnt_stiffness, *jnt_solref, *jnt_solimp, *jnt_margin, *qpos0, *qpos_spring;
   const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_treeadr, *dof_treenum;

@@ -70,6 +70,8 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
   PR_(body_pos, 3 * nb); PR_(body_quat, 4 * nb); PR_(body_ipos, 3 * nb); PR_(body_iquat, 4 * nb); PR_(body_mass, nb); PR_(body_inertia, 3 * nb);
   PR_(body_invweight0, 2 * nb);
   m.body_subtreemass = put<real>(b, stm.data(), nb);
+  PR_(body_gravcomp, nb);
+  for (int i = 0; i < nb; i++) m.ngravcomp += (d->body_gravcomp[i] != 0 && d->body_mass[i] != 0);
   PI_(jnt_type, nj); PI_(jnt_bodyid, nj); PI_(jnt_qposadr, nj); PI_(jnt_dofadr, nj); PI_(jnt_limited, nj);
   PR_(jnt_pos, 3 * nj); PR_(jnt_axis, 3 * nj); PR_(jnt_range, 2 * nj); PR_(jnt_stiffness, nj); PR_(jnt_solref, 2 * nj); PR_(jnt_solimp, 5 * nj);
   PR_(jnt_margin, nj); PR_(qpos0, nq); PR_(qpos_spring, nq);

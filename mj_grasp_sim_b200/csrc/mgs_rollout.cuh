@@ -53,7 +53,7 @@ MGS_DEVN int ramp_w(Env &e, const real *start, const real *target, int n, int ch
     PFOR(k, 3) EF(mocap)[k] = start[k] + (target[k] - start[k]) * f;
     WSYNC();
     if (step_w(e, 1, steps)) return 1;
-    if (check_every > 0 && t > 0 && t % check_every == 0 && !contact_with_object_w(e)) return 1;
+    if (check_every > 0 && t > 0 && t % check_every == 0 && !contact_with_object_w(e, 0)) return 1;
   }
   return 0;
 }
@@ -71,7 +71,7 @@ MGS_DEVN int stability_program_w(Env &e, const float *pose7, const float *joints
   PFOR(u, MD.nu) EF(ctrl)[u] = PRM.close_ctrl[u];
   WSYNC();
   if (step_w(e, PRM.nstep_close, steps)) return 0;
-  if (!contact_with_object_w(e)) return 0;
+  if (!contact_with_object_w(e, 0)) return 0;
   // lift (:205-226)
   real start[3], target[3];
   copy3(start, EF(mocap));
@@ -79,7 +79,7 @@ MGS_DEVN int stability_program_w(Env &e, const float *pose7, const float *joints
   target[2] = start[2] + PRM.lift_dist;
   WSYNC();
   if (ramp_w(e, start, target, PRM.nstep_lift, 100, steps)) return 0;
-  if (!contact_with_object_w(e)) return 0;
+  if (!contact_with_object_w(e, 0)) return 0;
   // shake (:229-276); current_mocap_pose passes through SE3Pose => float32 pos/quat/rotation
   real p32[3], q32[4], Rm[9], tb[3], tr[3], tl[3];
   for (int k = 0; k < 3; k++) p32[k] = round32(EF(mocap)[k]);
@@ -91,16 +91,61 @@ MGS_DEVN int stability_program_w(Env &e, const float *pose7, const float *joints
   copy3(start, EF(mocap));
   WSYNC();
   if (ramp_w(e, start, tb, PRM.shake_steps, 0, steps)) return 0;
-  if (!contact_with_object_w(e)) return 0;
+  if (!contact_with_object_w(e, 0)) return 0;
   for (int k = 0; k < 3; k++) tr[k] = tb[k] + Rm[3 * k + 1] * PRM.shake_dist;  // right = R (0,1,0)
   copy3(start, EF(mocap));
   WSYNC();
   if (ramp_w(e, start, tr, PRM.shake_steps, 0, steps)) return 0;
-  if (!contact_with_object_w(e)) return 0;
+  if (!contact_with_object_w(e, 0)) return 0;
   // left: restarts from the START of the right move (reference quirk: ~2 cm mocap jump at t=0)
   for (int k = 0; k < 3; k++) tl[k] = start[k] - Rm[3 * k + 1] * (2 * PRM.shake_dist);
   if (ramp_w(e, start, tl, 2 * PRM.shake_steps, 0, steps)) return 0;
-  if (!contact_with_object_w(e)) return 0;
+  if (!contact_with_object_w(e, 0)) return 0;
+  return 1;
+}
+
+// load a scene record (qpos | qvel | qacc_warmstart | ctrl | mocap) from global memory
+MGS_DEVN void load_record_w(Env &e, const real *in) {
+  e.bad = 0; e.overflow = 0; e.ncon = 0; e.nefc = 0;
+  #pragma unroll 1
+  PFOR(i, MD.nq) EF(qpos)[i] = in[i];
+  #pragma unroll 1
+  PFOR(i, MD.nv) { EF(qvel)[i] = in[MD.nq + i]; EF(qacc_ws)[i] = in[MD.nq + MD.nv + i]; }
+  #pragma unroll 1
+  PFOR(i, MD.nu) EF(ctrl)[i] = in[MD.nq + 2 * MD.nv + i];
+  #pragma unroll 1
+  PFOR(i, 7 * MD.nmocap) EF(mocap)[i] = in[MD.nq + 2 * MD.nv + MD.nu + i];
+  WSYNC();
+}
+
+// ClutterTableEnv.grasp_stable_mask body (clutter_table.py:288-317): restore the scene, place, close, lift with
+// the gripper-contact test at (t+1) % 100 == 0 (early break); label = lift survived
+MGS_DEVN int clutter_stable_program_w(Env &e, const float *pose7, const float *joints, int *steps) {
+  load_record_w(e, IO.state_in);
+  place_w(e, pose7, joints);
+  forward_w(e);
+  MGS_STAGE_BARRIER(5);
+  if (PRM.repose_on_close) place_w(e, pose7, (const float *)0);
+  #pragma unroll 1
+  PFOR(k, 7) EF(mocap)[k] = (real)LDG(pose7 + k);
+  #pragma unroll 1
+  PFOR(u, MD.nu) EF(ctrl)[u] = PRM.close_ctrl[u];
+  WSYNC();
+  if (step_w(e, PRM.nstep_close, steps)) return 0;
+  real start[3], target[3];
+  copy3(start, EF(mocap));
+  copy3(target, start);
+  target[2] = start[2] + PRM.lift_dist;
+  WSYNC();
+  #pragma unroll 1
+  for (int t = 0; t < PRM.nstep_lift; t++) {
+    const real f = (real)t / (real)PRM.nstep_lift;
+    #pragma unroll 1
+    PFOR(k, 3) EF(mocap)[k] = start[k] + (target[k] - start[k]) * f;
+    WSYNC();
+    if (step_w(e, 1, steps)) return 0;
+    if ((t + 1) % 100 == 0 && !contact_with_object_w(e, 0)) return 0;
+  }
   return 1;
 }
 
@@ -141,17 +186,7 @@ MGS_DEVN void write_diag_w(const Env &e, real *o) {
 MGS_DEVN void run_env_w(Env &e, int env) {
   int steps = 0;
   if (PRM.mode == MGS_MODE_STEP) {
-    const real *in = IO.state_in + (size_t)env * IO.state_stride;
-    e.bad = 0; e.overflow = 0;
-    #pragma unroll 1
-    PFOR(i, MD.nq) EF(qpos)[i] = in[i];
-    #pragma unroll 1
-    PFOR(i, MD.nv) { EF(qvel)[i] = in[MD.nq + i]; EF(qacc_ws)[i] = in[MD.nq + MD.nv + i]; }
-    #pragma unroll 1
-    PFOR(i, MD.nu) EF(ctrl)[i] = in[MD.nq + 2 * MD.nv + i];
-    #pragma unroll 1
-    PFOR(i, 7 * MD.nmocap) EF(mocap)[i] = in[MD.nq + 2 * MD.nv + MD.nu + i];
-    WSYNC();
+    load_record_w(e, IO.state_in + (size_t)env * IO.state_stride);
     if (PRM.nstep > 0) step_w(e, PRM.nstep, &steps);
     else { forward_w(e); MGS_STAGE_BARRIER(5); }
     real *out = IO.state_out + (size_t)env * IO.state_stride;
@@ -177,6 +212,15 @@ MGS_DEVN void run_env_w(Env &e, int env) {
     forward_w(e);
     MGS_STAGE_BARRIER(5);
     label = (e.ncon == 0);  // collision-free mask: no contact of any kind (check_contact, :306-307)
+  } else if (PRM.mode == MGS_MODE_CLUTTER_COLLISION) {
+    // ClutterTableEnv.grasp_collision_mask body (clutter_table.py:356-364); bounds test done by the host
+    load_record_w(e, IO.state_in);
+    place_w(e, pose7, joints);
+    forward_w(e);
+    MGS_STAGE_BARRIER(5);
+    label = !contact_with_object_w(e, 1);
+  } else if (PRM.mode == MGS_MODE_CLUTTER_STABLE) {
+    label = clutter_stable_program_w(e, pose7, joints, &steps);
   } else {
     label = stability_program_w(e, pose7, joints, &steps);
   }

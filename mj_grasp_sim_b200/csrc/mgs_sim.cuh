@@ -591,5 +591,31 @@ MGS_DEVN void smooth_forces_w(Env &e) {
     EF(qfrc_smooth)[d] = f;
   }
   WSYNC();
+  if (MD.ngravcomp > 0) {
+    // gravity compensation (clutter scenes: the camera body): -gravity * mass * gravcomp at the body CoM.
+    // Rare and tiny, so one lane walks the dof chains.
+    #pragma unroll 1
+    PFOR(one, 1) {
+      #pragma unroll 1
+      for (int b = 1; b < nb; b++) {
+        const real gc = LDG(MD.body_gravcomp + b), mass = LDG(MD.body_mass + b);
+        if (gc == 0 || mass == 0) continue;
+        real off[3], f[3] = {-MD.gravity[0] * mass * gc, -MD.gravity[1] * mass * gc, -MD.gravity[2] * mass * gc};
+        // body CoM relative to the tree origin: cinert holds mass * offset
+        off[0] = EF(cinert)[10 * b + 6] / mass; off[1] = EF(cinert)[10 * b + 7] / mass; off[2] = EF(cinert)[10 * b + 8] / mass;
+        int bb = b;
+        while (bb > 0 && LDG(MD.body_dofnum + bb) == 0) bb = LDG(MD.body_parentid + bb);
+        if (bb == 0) continue;
+        #pragma unroll 1
+        for (int d = LDG(MD.body_dofadr + bb) + LDG(MD.body_dofnum + bb) - 1; d >= 0; d = LDG(MD.dof_parentid + d)) {
+          const real *c = EF(cdof) + 6 * d;
+          real lin[3];
+          cross3(lin, c, off);
+          EF(qfrc_smooth)[d] += (lin[0] + c[3]) * f[0] + (lin[1] + c[4]) * f[1] + (lin[2] + c[5]) * f[2];
+        }
+      }
+    }
+    WSYNC();
+  }
   matvec_w(EF(qacc_smooth), EF(Minv), EF(qfrc_smooth), nv);
 }

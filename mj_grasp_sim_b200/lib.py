@@ -66,11 +66,14 @@ def bind(L, prefix="mgs_"):
         L.mgs_grasp_stability.argtypes = [vp, C.c_int, fp, fp, C.c_int, ip, C.c_int, dp, C.POINTER(MgsRolloutCfg), u8p, ip]
         L.mgs_rollout_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, ip, C.c_int, dp, C.POINTER(MgsRolloutCfg), vp, vp, vp]
         L.mgs_step_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
+        L.mgs_clutter_collision_mask.argtypes = [vp, C.c_int, dp, fp, fp, C.c_int, ip, C.c_int, u8p]
+        L.mgs_clutter_stable_mask.argtypes = [vp, C.c_int, dp, fp, fp, C.c_int, ip, C.c_int, dp, C.POINTER(MgsRolloutCfg), u8p, ip]
         L.mgs_launch_count.restype = C.c_longlong
         L.mgs_overflow_count.argtypes = [vp]
     else:
         L.l1_model_create.argtypes = [C.POINTER(MgsModelDesc), C.POINTER(vp)]
         L.l1_rollout_host.argtypes = [vp, C.c_int, C.c_int, fp, fp, C.c_int, ip, C.c_int, dp, C.POINTER(MgsRolloutCfg), u8p, ip]
+        L.l1_clutter_host.argtypes = [vp, C.c_int, C.c_int, dp, fp, fp, C.c_int, ip, C.c_int, dp, C.POINTER(MgsRolloutCfg), u8p, ip]
     return L
 
 
@@ -100,11 +103,12 @@ class BatchSim:
     through the same wrapper; product code always uses the defaults (the CUDA library).
     """
 
-    def __init__(self, model, device: int = 0, f64: bool = False, lib=None, prefix: str = "mgs_", ncon_max: int = 0, nefc_max: int = 0):
+    def __init__(self, model, device: int = 0, f64: bool = False, lib=None, prefix: str = "mgs_", ncon_max: int = 0, nefc_max: int = 0,
+                 ground_name: str = "geom:ground"):
         self.model = model
         self.L = lib if lib is not None else load(f64)
         self.p = prefix
-        self.desc, self._keep = make_desc(model)
+        self.desc, self._keep = make_desc(model, ground_name)
         h = C.c_void_p()
         if prefix == "mgs_":
             ncon_max = ncon_max or int(os.environ.get("MGS_NCON_MAX", "0"))
@@ -217,6 +221,39 @@ class BatchSim:
                                             C.byref(cfg), _u8(out), _ip(steps))
         else:
             rc = self.L.l1_rollout_host(self.h, 2, n, _fp(pose7), _fp(joints), joints.shape[1], _ip(jadr), int(base_qposadr), _dp(cc),
+                                        C.byref(cfg), _u8(out), _ip(steps))
+        self._check(rc)
+        return out.astype(bool), steps
+
+    # ---- clutter table ---------------------------------------------------------------------
+    def clutter_collision_mask(self, scene, pose7, joints, joint_qposadr, base_qposadr):
+        pose7, joints, jadr = self._prep(pose7, joints, joint_qposadr)
+        sc = np.ascontiguousarray(scene, dtype=np.float64)
+        n = len(pose7)
+        out = np.zeros(n, dtype=np.uint8)
+        if n == 0:
+            return out.astype(bool)
+        if self.p == "mgs_":
+            rc = self.L.mgs_clutter_collision_mask(self.h, n, _dp(sc), _fp(pose7), _fp(joints), joints.shape[1], _ip(jadr), int(base_qposadr), _u8(out))
+        else:
+            rc = self.L.l1_clutter_host(self.h, 3, n, _dp(sc), _fp(pose7), _fp(joints), joints.shape[1], _ip(jadr), int(base_qposadr), None, None, _u8(out), None)
+        self._check(rc)
+        return out.astype(bool)
+
+    def clutter_stable_mask(self, scene, pose7, joints, joint_qposadr, base_qposadr, close_ctrl, cfg: MgsRolloutCfg):
+        pose7, joints, jadr = self._prep(pose7, joints, joint_qposadr)
+        sc = np.ascontiguousarray(scene, dtype=np.float64)
+        cc = np.ascontiguousarray(close_ctrl, dtype=np.float64)
+        n = len(pose7)
+        out = np.zeros(n, dtype=np.uint8)
+        steps = np.zeros(n, dtype=np.int32)
+        if n == 0:
+            return out.astype(bool), steps
+        if self.p == "mgs_":
+            rc = self.L.mgs_clutter_stable_mask(self.h, n, _dp(sc), _fp(pose7), _fp(joints), joints.shape[1], _ip(jadr), int(base_qposadr), _dp(cc),
+                                                C.byref(cfg), _u8(out), _ip(steps))
+        else:
+            rc = self.L.l1_clutter_host(self.h, 4, n, _dp(sc), _fp(pose7), _fp(joints), joints.shape[1], _ip(jadr), int(base_qposadr), _dp(cc),
                                         C.byref(cfg), _u8(out), _ip(steps))
         self._check(rc)
         return out.astype(bool), steps

@@ -1,0 +1,168 @@
+"""ClutterTableEnv - drop-in for the grasp-evaluation part of /root/reference/mgs/env/clutter_table.py.
+
+Same constructor and the same evaluation methods:
+  grasp_collision_mask(poses, joints) -> bool[N]                                        (reference :330-367)
+  grasp_stable_mask(poses, joints, env_state, nstep_lift, lift_dist, enough_stable)     (reference :272-321)
+plus get_state / set_state in MuJoCo's mjSTATE_INTEGRATION layout (core/simualtion.py:51-61), gen_clutter /
+settle / is_stable (:157-222, run as single-environment launches of the same kernel) and to_dict / from_dict
+(:369-399).  Rendering (MjScanEnv) is out of scope.  All candidates of a call run in one batched launch.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+
+import numpy as np
+
+from ... import scenes
+from ...compiler.mjcf import compile_mjcf
+from ...lib import BatchSim, MgsRolloutCfg
+from ...shard import apply_enough_stable
+from ..core.simualtion import MjSimulation
+from ..util.geo.transforms import SE3Pose
+
+XML = scenes.CLUTTER_XML  # same options / body order as the reference template (:41-79), lights and camera element dropped
+
+
+class ClutterTableEnv(MjSimulation):
+    def __init__(self, gripper, objects, scene_randomization=True, device: int | None = None, ncon_max: int = 0, nefc_max: int = 0):
+        self.gripper, self.objects = gripper, objects
+        self.gripper_xml, self.gripper_assets = gripper.to_xml()
+        self.object_names = [o.name for o in objects]
+        self.object_ids = [o.object_id for o in objects]
+        self.objs_xml_concat, self.objs_assets = "", {}
+        for o in objects:
+            x, a = o.to_xml()
+            self.objs_xml_concat += x
+            self.objs_assets.update(a)
+        self.model_xml = XML.format(gripper=self.gripper_xml, objects=self.objs_xml_concat)
+        self.env_defintion = {"model_xml": self.model_xml, "assets": {**self.gripper_assets, **self.objs_assets}}
+        self.model = compile_mjcf(self.model_xml, self.env_defintion["assets"])
+        self._device, self._caps, self._sim = device, (ncon_max, nefc_max), None
+        self._record = scenes.record_from_model(self.model)
+        self._time = 0.0
+
+    @property
+    def sim(self) -> BatchSim:
+        if self._sim is None:
+            dev = self._device
+            if dev is None:
+                import torch
+                dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
+            self._sim = BatchSim(self.model, device=dev, ncon_max=self._caps[0], nefc_max=self._caps[1], ground_name="geom:table")
+        return self._sim
+
+    # ---- state in MuJoCo's mjSTATE_INTEGRATION layout ---------------------------------------
+    def _layout(self):
+        m = self.model
+        nq, nv, nu, nb, neq = m.nq, m.nv, m.nu, m.nbody, int(m.arr["neq"])
+        o_qpos, o_qvel = 1, 1 + nq
+        o_ws = o_qvel + nv  # act is empty
+        o_ctrl = o_ws + nv
+        o_applied = o_ctrl + nu
+        o_xfrc = o_applied + nv
+        o_eq = o_xfrc + 6 * nb
+        o_mpos = o_eq + neq
+        return dict(qpos=o_qpos, qvel=o_qvel, ws=o_ws, ctrl=o_ctrl, eq=o_eq, mpos=o_mpos, size=o_mpos + 7)
+
+    def get_state(self) -> np.ndarray:
+        m, L = self.model, self._layout()
+        nq, nv, nu = m.nq, m.nv, m.nu
+        st = np.zeros(L["size"])
+        st[0] = self._time
+        r = self._record
+        st[L["qpos"]:L["qpos"] + nq] = r[:nq]
+        st[L["qvel"]:L["qvel"] + nv] = r[nq:nq + nv]
+        st[L["ws"]:L["ws"] + nv] = r[nq + nv:nq + 2 * nv]
+        st[L["ctrl"]:L["ctrl"] + nu] = r[nq + 2 * nv:nq + 2 * nv + nu]
+        st[L["eq"]:L["eq"] + int(m.arr["neq"])] = 1.0
+        st[L["mpos"]:L["mpos"] + 7] = r[nq + 2 * nv + nu:]
+        return st
+
+    def _record_from_state(self, state) -> np.ndarray:
+        m, L = self.model, self._layout()
+        nq, nv, nu = m.nq, m.nv, m.nu
+        state = np.asarray(state, dtype=np.float64)
+        if state.shape != (L["size"],):
+            raise ValueError(f"state has {state.shape} entries, mjSTATE_INTEGRATION of this model has {L['size']}")
+        return np.concatenate([state[L["qpos"]:L["qpos"] + nq], state[L["qvel"]:L["qvel"] + nv], state[L["ws"]:L["ws"] + nv],
+                               state[L["ctrl"]:L["ctrl"] + nu], state[L["mpos"]:L["mpos"] + 7]])
+
+    def set_state(self, state):
+        self._record = self._record_from_state(state)
+        self._time = float(np.asarray(state)[0])
+
+    # ---- scene generation (single-environment launches) -------------------------------------
+    def _step(self, rec, nstep):
+        out = self.sim.step(rec[None].astype(self.sim.real), nstep)
+        self._time += nstep * float(self.model.opt["timestep"])
+        return out[0].astype(np.float64)
+
+    def set_gripper_pose(self, pos):
+        """park the gripper (what gen_scene does through gripper.set_pose before generating the clutter)"""
+        m = self.model
+        b = self.gripper.get_freejoint_idxs(self)[0]
+        mo = m.nq + 2 * m.nv + m.nu
+        self._record[b:b + 3] = pos
+        self._record[mo:mo + 3] = pos
+
+    def gen_clutter(self, seed: int | None = None):
+        info = dict(base_qposadr=self.gripper.get_freejoint_idxs(self)[0],
+                    object_qposadr=[int(self.model.jnt_qposadr[self.model.names["joint"][f"{n}:joint"]]) for n in self.object_names])
+        sd = int(np.random.randint(1 << 30)) if seed is None else seed
+        self._record = scenes.gen_clutter(self.model, info, self._step, sd)
+
+    def settle(self):
+        self._record = self._step(self._record, 10000)
+
+    def is_stable(self):
+        adr = [int(self.model.jnt_qposadr[self.model.names["joint"][f"{n}:joint"]]) for n in self.object_names]
+        stats = np.zeros(len(adr))
+        for _ in range(10):
+            start = np.array([self._record[a:a + 3] for a in adr])
+            self._record = self._step(self._record, 100)
+            stats += np.abs(np.array([self._record[a:a + 3] for a in adr]) - start).sum(axis=1)
+        return bool(stats.max() < 5e-3) if len(adr) else True
+
+    # ---- grasp evaluation ---------------------------------------------------------------------
+    def _process(self, poses: SE3Pose, joints):
+        names = self.gripper.get_actuator_joint_names()
+        joints = np.asarray(joints)
+        if len(poses) != len(joints):
+            raise ValueError(f"Number of poses ({len(poses)}) must match number of joint configurations ({len(joints)}).")
+        processed = poses @ self.gripper.base_to_contact_transform()
+        pose7 = processed.to_vec(layout="pq", type="wxyz").astype(np.float32).reshape(-1, 7)
+        return pose7, joints.astype(np.float32).reshape(len(pose7), len(names)), np.array(self.get_joint_idxs(names), dtype=np.int32)
+
+    def grasp_collision_mask(self, poses: SE3Pose, joints: np.ndarray):
+        pose7, j32, jadr = self._process(poses, joints)
+        p = np.asarray(poses.pos).reshape(-1, 3)
+        in_bound = (p[:, 0] < 0.25) & (p[:, 0] > -0.25) & (p[:, 1] < 0.25) & (p[:, 1] > -0.25) & (p[:, 2] < 1.0) & (p[:, 2] > 0.0)  # :344-354
+        out = np.zeros(len(pose7), dtype=bool)
+        idx = np.nonzero(in_bound)[0]
+        base = self.gripper.get_freejoint_idxs(self)[0]
+        out[idx] = self.sim.clutter_collision_mask(self._record, pose7[idx], j32[idx], jadr, base)
+        return out
+
+    def grasp_stable_mask(self, poses: SE3Pose, joints: np.ndarray, env_state, nstep_lift: int = 3000, lift_dist: float = 0.3, enough_stable=None):
+        pose7, j32, jadr = self._process(poses, joints)
+        scene = self._record_from_state(env_state)
+        base = self.gripper.get_freejoint_idxs(self)[0]
+        cfg = MgsRolloutCfg(self.gripper.NSTEP_CLOSE, nstep_lift, 0, self.gripper.REPOSE_ON_CLOSE, lift_dist, 0.0)
+        labels, _ = self.sim.clutter_stable_mask(scene, pose7, j32, jadr, base, self.gripper.close_ctrl(), cfg)
+        return apply_enough_stable(labels, enough_stable)
+
+    # ---- persistence (scene.npz payload) --------------------------------------------------------
+    def to_dict(self):
+        m = self.model
+        state = {"geom_conaffinity": deepcopy(m.geom_conaffinity), "geom_contype": deepcopy(m.geom_contype),
+                 "geom_rgba": np.ones((int(m.arr["ngeom"]), 4)), "body_gravcomp": deepcopy(m.body_gravcomp), "state": self.get_state()}
+        return {"gripper": deepcopy(self.gripper), "objects": deepcopy(self.objects), "env_state": state}
+
+    @classmethod
+    def from_dict(cls, state_dict):
+        env = cls(state_dict["gripper"], state_dict["objects"], scene_randomization=False)
+        env.set_state(state_dict["env_state"]["state"])
+        st = state_dict["env_state"]
+        if not (np.array_equal(st["geom_contype"], env.model.geom_contype) and np.array_equal(st["geom_conaffinity"], env.model.geom_conaffinity)):
+            raise NotImplementedError("scenes with removed objects (edited geom masks) are not supported yet")
+        return env

@@ -247,3 +247,113 @@ def workload(gripper: str, kind: str, seed: int, n: int, n_v: int = 32):
     else:
         raise NotImplementedError(gripper)
     return model, info, pose7, joints.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Clutter table (reference: /root/reference/mgs/env/clutter_table.py:41-79).  Same options, same body and
+# geom order: gripper, table, camera (free joint, gravcomp 1, parked under the table), base_origin, four
+# walls, then the objects - the contact tests compare geom ids with geom:table's.
+CLUTTER_XML = """<mujoco>
+  <compiler angle="radian" autolimits="true" discardvisual="false"/>
+  <option integrator="implicitfast" timestep="0.001" cone="elliptic" gravity="0 0 -9.81" impratio="3" noslip_iterations="3"
+          noslip_tolerance="1e-10" tolerance="1e-10"><flag multiccd="enable"/></option>
+  {gripper}
+  <worldbody>
+    <body name="body:table" pos="0.0 0 -0.02">
+      <geom name="geom:table" pos="0 0 0" size="10 10 0.02" type="box" density="500" friction="1.0 0.1 0.1"/>
+    </body>
+    <body name="body:camera" pos="0.0 0.0 -1.0" quat="1.0 0.0 0 0" gravcomp="1">
+      <freejoint name="camera:joint"/>
+      <geom name="geom:camera" size="0.01"/>
+    </body>
+    <body name="base_origin" pos="0.0 0.0 -0.025" quat="1.0 0.0 0 0"><geom name="geom:base_origin" size="0.01"/></body>
+    <body name="body:wall_top" pos="0.0 1.0 0.1"><geom name="geom:wall_top" size="1.0 0.02 0.2" type="box" density="500"/></body>
+    <body name="body:wall_right" pos="1.0 0.0 0.1"><geom name="geom:wall_right" size="0.02 1.0 0.2" type="box" density="500"/></body>
+    <body name="body:wall_bottom" pos="0.0 -1.0 0.1"><geom name="geom:wall_bottom" size="1.0 0.02 0.2" type="box" density="500"/></body>
+    <body name="body:wall_left" pos="-1.0 0.0 0.1"><geom name="geom:wall_left" size="0.02 1.0 0.2" type="box" density="500"/></body>
+  </worldbody>
+  {objects}
+</mujoco>"""
+
+
+def clutter_object_fragment(seed: int, index: int, n_v: int = 24):
+    """Hull object `index` of a clutter scene, parked on the reference's far-away grid (obj/selector.py:207-246)."""
+    pts, mass = random_hull_points(seed, n_v)
+    h = meshlib.build_hull(pts)
+    name = f"obj{index}"
+    fn = f"{name}_hull.obj"
+    x, y = -8.0 + 0.5 * (index // 10), -8.0 + 0.5 * (index % 10)
+    xml = f"""<asset><mesh name="{name}_coll_0" file="{fn}"/></asset>
+<worldbody><body name="{name}" pos="{x} {y} 0.06" quat="1 0 0 0">
+<geom mesh="{name}_coll_0" mass="{mass}" group="3" type="mesh" conaffinity="1" contype="1" condim="4"
+      friction="1.0 0.3 0.1" solimp="0.998 0.998 0.001" solref="0.001 1"/>
+<joint damping="0.0001" name="{name}:joint" type="free"/></body></worldbody>"""
+    return xml, {fn: meshlib.write_obj(h.verts, h.tri)}, name
+
+
+def build_clutter_scene(gripper: str, object_seeds):
+    gx, ga = gripper_fragment(gripper)
+    oxml, oassets, names = "", {}, []
+    for i, sd in enumerate(object_seeds):
+        x, a, nm = clutter_object_fragment(sd, i)
+        oxml += x
+        oassets.update(a)
+        names.append(nm)
+    model = compile_mjcf(CLUTTER_XML.format(gripper=gx, objects=oxml), {**ga, **oassets})
+    g = GRIPPERS[gripper]
+    info = dict(base_qposadr=int(model.jnt_qposadr[model.names["joint"][g["freejoint"]]]),
+                joint_qposadr=np.array([model.jnt_qposadr[model.names["joint"][j] if j is not None else -1] for j in g["joints"]], dtype=np.int32),
+                close_ctrl=np.array(g["close_ctrl"], dtype=np.float64), repose=g["repose"], gripper=gripper, ground_name="geom:table",
+                object_qposadr=[int(model.jnt_qposadr[model.names["joint"][f"{n}:joint"]]) for n in names],
+                object_dofadr=[int(model.jnt_dofadr[model.names["joint"][f"{n}:joint"]]) for n in names])
+    return model, info
+
+
+def record_from_model(model):
+    """Initial scene record (mj_resetData): qpos0 | qvel 0 | qacc_warmstart 0 | ctrl 0 | mocap pose."""
+    return np.concatenate([model.qpos0, np.zeros(2 * model.nv + model.nu), model.mocap_pos0.reshape(-1), model.mocap_quat0.reshape(-1)])
+
+
+def gen_clutter(model, info, step_fn, seed: int, park_gripper=(0.0, 0.0, 1.5)):
+    """ClutterTableEnv.gen_clutter (clutter_table.py:197-222): drop the objects one by one from (0, 0, 0.8) with
+    a random orientation, 900 steps each with qvel clipped to +-50, then 9000 settling steps.  `step_fn(record,
+    nstep) -> record` advances a scene record (the oracle in tests, the GPU library in the mgs mirror).  The
+    gripper is parked above the workspace, as gen_scene does before generating (gen_scene.py:28-45)."""
+    rng = np.random.default_rng(4000 + seed)
+    nq, nv = model.nq, model.nv
+    rec = record_from_model(model)
+    b = info["base_qposadr"]
+    rec[b:b + 3] = park_gripper
+    mo = nq + 2 * nv + model.nu
+    rec[mo:mo + 3] = park_gripper
+    q = R.random(random_state=np.random.RandomState(int(rng.integers(1 << 31)))).as_quat()
+    drop_quat = np.array([q[3], q[0], q[1], q[2]])
+    for a in info["object_qposadr"]:
+        rec[a:a + 3] = [0.0, 0.0, 0.8]
+        rec[a + 3:a + 7] = drop_quat
+        rec[nq:nq + nv] = 0.0
+        for _ in range(9):
+            rec[nq:nq + nv] = np.clip(rec[nq:nq + nv], -50.0, 50.0)
+            rec = step_fn(rec, 100)
+    for _ in range(90):
+        rec[nq:nq + nv] = np.clip(rec[nq:nq + nv], -50.0, 50.0)
+        rec = step_fn(rec, 100)
+    return rec
+
+
+def clutter_candidates(model, info, rec, n: int, seed: int):
+    """Top-down-ish grasp candidates over the settled objects: antipodal frames around each object's
+    position with the approach axis within ~35 degrees of straight down (harness-generated inputs)."""
+    rng = np.random.default_rng(5000 + seed)
+    H = np.zeros((n, 4, 4))
+    width = rng.uniform(0.02, 0.07, size=n)
+    for i in range(n):
+        a = info["object_qposadr"][int(rng.integers(len(info["object_qposadr"])))]
+        c = rec[a:a + 3] + rng.normal(scale=0.01, size=3)
+        z = np.array([0.0, 0.0, -1.0]) + rng.normal(scale=0.3, size=3)
+        z /= np.linalg.norm(z)
+        x = np.cross(rng.normal(size=3), z)
+        x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        H[i, :3, 0], H[i, :3, 1], H[i, :3, 2], H[i, :3, 3], H[i, 3, 3] = x, y, z, c, 1.0
+    return H, width

@@ -234,6 +234,7 @@ void orc_reset(OrcSim *s) {
 }
 
 /* ------------------------------------------------------------------ smooth dynamics */
+static void jac_point(const OrcSim *s, int body, const double *point, double *jacp, double *jacr);
 /* mj_kinematics (SURVEY 8(a-MJ) "Kinematics") */
 static void kinematics(OrcSim *s) {
   const MgsModelDesc *m = &s->m;
@@ -471,6 +472,14 @@ static void passive(OrcSim *s) {
     if (m->jnt_type[j] == JNT_FREE || m->jnt_stiffness[j] == 0) continue;
     int qa = m->jnt_qposadr[j];
     s->qfrc_passive[m->jnt_dofadr[j]] -= m->jnt_stiffness[j] * (s->qpos[qa] - m->qpos_spring[qa]);
+  }
+  /* gravity compensation: force -gravity * mass * gravcomp at the body CoM (clutter_table.py:56, camera body) */
+  for (int b = 1; b < m->nbody; b++) {
+    if (m->body_gravcomp[b] == 0 || m->body_mass[b] == 0) continue;
+    double *jp = s->jtmp;
+    jac_point(s, b, s->xipos + 3 * b, jp, NULL);
+    for (int d = 0; d < m->nv; d++)
+      for (int k = 0; k < 3; k++) s->qfrc_passive[d] += jp[k * m->nv + d] * (-m->gravity[k] * m->body_mass[b] * m->body_gravcomp[b]);
   }
 }
 
@@ -1602,12 +1611,78 @@ done:
   return label;
 }
 
+/* ------------------------------------------------------------------ clutter table (reference clutter_table.py) */
+/* check_gripper_collision (:237-252): gripper <-> table or anything numbered after the table */
+int orc_gripper_collision(const OrcSim *s) {
+  int g = s->m.ground_geomid;
+  for (int c = 0; c < s->ncon; c++) {
+    int a = s->con[c].geom1, b = s->con[c].geom2;
+    if ((a < g && b > g) || (a > g && b < g) || (a == g && b < g) || (a < g && b == g)) return 1;
+  }
+  return 0;
+}
+/* check_gripper_contact (:254-270): as written, `A or (B and not C)` reduces to gripper <-> anything after the table */
+int orc_gripper_contact(const OrcSim *s) { return orc_contact_with_object(s); }
+
+/* load the scene state record: qpos[nq] qvel[nv] qacc_warmstart[nv] ctrl[nu] mocap_pos[3] mocap_quat[4] */
+void orc_set_record(OrcSim *s, const double *rec) {
+  const MgsModelDesc *m = &s->m;
+  memcpy(s->qpos, rec, sizeof(double) * m->nq); rec += m->nq;
+  memcpy(s->qvel, rec, sizeof(double) * m->nv); rec += m->nv;
+  memcpy(s->qacc_warmstart, rec, sizeof(double) * m->nv); rec += m->nv;
+  memcpy(s->ctrl, rec, sizeof(double) * m->nu); rec += m->nu;
+  if (m->nmocap) { memcpy(s->mocap_pos, rec, sizeof(double) * 3); memcpy(s->mocap_quat, rec + 3, sizeof(double) * 4); }
+  s->bad = 0; s->nstep_done = 0; s->ncon = 0; s->nefc = 0;
+}
+void orc_get_record(const OrcSim *s, double *rec) {
+  const MgsModelDesc *m = &s->m;
+  memcpy(rec, s->qpos, sizeof(double) * m->nq); rec += m->nq;
+  memcpy(rec, s->qvel, sizeof(double) * m->nv); rec += m->nv;
+  memcpy(rec, s->qacc_warmstart, sizeof(double) * m->nv); rec += m->nv;
+  memcpy(rec, s->ctrl, sizeof(double) * m->nu); rec += m->nu;
+  if (m->nmocap) { memcpy(rec, s->mocap_pos, sizeof(double) * 3); memcpy(rec + 3, s->mocap_quat, sizeof(double) * 4); }
+}
+
+/* ClutterTableEnv.grasp_collision_mask body (:356-364); the workspace bound test (:344-354) is done by the caller */
+int orc_clutter_collision(OrcSim *s, const double *scene, const double *pose7, int base_qadr, const double *joints, const int *jadr, int nj) {
+  orc_set_record(s, scene);
+  orc_place(s, pose7, base_qadr, joints, jadr, nj);
+  orc_forward(s);
+  return orc_gripper_collision(s);
+}
+
+/* ClutterTableEnv.grasp_stable_mask body (:288-317): restore scene, place, close, lift with the check at (t+1) % 100 == 0 */
+int orc_clutter_stable(OrcSim *s, const double *scene, const double *pose7, int base_qadr, const double *joints, const int *jadr, int nj,
+                       const double *close_ctrl, const OrcRolloutCfg *cfg, long long *steps_out) {
+  int label = 0;
+  orc_set_record(s, scene);
+  orc_place(s, pose7, base_qadr, joints, jadr, nj);
+  orc_forward(s);
+  if (cfg->repose_on_close) orc_place(s, pose7, base_qadr, NULL, NULL, 0);
+  for (int k = 0; k < 3; k++) s->mocap_pos[k] = pose7[k];
+  for (int k = 0; k < 4; k++) s->mocap_quat[k] = pose7[3 + k];
+  for (int u = 0; u < s->m.nu; u++) s->ctrl[u] = close_ctrl[u];
+  if (orc_step(s, cfg->nstep_close)) goto done;
+  {
+    double z0 = s->mocap_pos[2], zt = z0 + cfg->lift_dist;
+    label = 1;
+    for (int t = 0; t < cfg->nstep_lift; t++) {
+      s->mocap_pos[2] = z0 + (zt - z0) * ((double)t / cfg->nstep_lift);
+      if (orc_step(s, 1)) { label = 0; break; }
+      if ((t + 1) % 100 == 0 && !orc_gripper_contact(s)) { label = 0; break; }
+    }
+  }
+done:
+  if (steps_out) *steps_out = s->nstep_done;
+  return label;
+}
+
 /* ------------------------------------------------------------------ threaded batch (CPU baseline) */
 #include <pthread.h>
 typedef struct {
   const MgsModelDesc *d; int n, nthreads, tid, base_qadr, nj, mode;
   const double *poses, *joints, *close_ctrl; const int *jadr; const OrcRolloutCfg *cfg;
-  unsigned char *labels; long long *steps;
+  unsigned char *labels; long long *steps; const double *scene;
 } BatchArg;
 static void *batch_worker(void *p) {
   BatchArg *a = (BatchArg *)p;
@@ -1616,6 +1691,14 @@ static void *batch_worker(void *p) {
     if (a->mode == 0) {
       a->labels[i] = (unsigned char)!orc_grasp_collision(s, a->poses + 7 * i, a->base_qadr, a->joints + (size_t)a->nj * i, a->jadr, a->nj);
       if (a->steps) a->steps[i] = 0;
+    } else if (a->mode == 2) {
+      a->labels[i] = (unsigned char)!orc_clutter_collision(s, a->scene, a->poses + 7 * i, a->base_qadr, a->joints + (size_t)a->nj * i, a->jadr, a->nj);
+      if (a->steps) a->steps[i] = 0;
+    } else if (a->mode == 3) {
+      long long st = 0;
+      a->labels[i] = (unsigned char)orc_clutter_stable(s, a->scene, a->poses + 7 * i, a->base_qadr, a->joints + (size_t)a->nj * i, a->jadr, a->nj,
+                                                       a->close_ctrl, a->cfg, &st);
+      if (a->steps) a->steps[i] = st;
     } else {
       long long st = 0;
       a->labels[i] = (unsigned char)orc_grasp_stability(s, a->poses + 7 * i, a->base_qadr, a->joints + (size_t)a->nj * i, a->jadr, a->nj,
@@ -1626,15 +1709,24 @@ static void *batch_worker(void *p) {
   orc_destroy(s);
   return NULL;
 }
-/* mode 0: collision-free mask; mode 1: stability labels.  One OrcSim per thread, candidates strided. */
+/* mode 0: collision-free mask; mode 1: stability labels; 2 / 3: the clutter-table versions (need `scene`).
+ * One OrcSim per thread, candidates strided. */
+int orc_batch_scene(const MgsModelDesc *d, int mode, int n, const double *poses, int base_qadr, const double *joints, const int *jadr,
+                    int nj, const double *close_ctrl, const OrcRolloutCfg *cfg, int nthreads, unsigned char *labels, long long *steps,
+                    const double *scene);
 int orc_batch(const MgsModelDesc *d, int mode, int n, const double *poses, int base_qadr, const double *joints, const int *jadr,
               int nj, const double *close_ctrl, const OrcRolloutCfg *cfg, int nthreads, unsigned char *labels, long long *steps) {
+  return orc_batch_scene(d, mode, n, poses, base_qadr, joints, jadr, nj, close_ctrl, cfg, nthreads, labels, steps, NULL);
+}
+int orc_batch_scene(const MgsModelDesc *d, int mode, int n, const double *poses, int base_qadr, const double *joints, const int *jadr,
+                    int nj, const double *close_ctrl, const OrcRolloutCfg *cfg, int nthreads, unsigned char *labels, long long *steps,
+                    const double *scene) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
   pthread_t th[256];
   BatchArg args[256];
   for (int t = 0; t < nthreads; t++) {
-    BatchArg a = {d, n, nthreads, t, base_qadr, nj, mode, poses, joints, close_ctrl, jadr, cfg, labels, steps};
+    BatchArg a = {d, n, nthreads, t, base_qadr, nj, mode, poses, joints, close_ctrl, jadr, cfg, labels, steps, scene};
     args[t] = a;
     pthread_create(&th[t], NULL, batch_worker, &args[t]);
   }

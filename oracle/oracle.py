@@ -62,6 +62,13 @@ def lib():
         L.orc_batch.argtypes = [C.POINTER(MgsModelDesc), C.c_int, C.c_int, dp, C.c_int, dp, ip, C.c_int, dp, C.POINTER(RolloutCfg),
                                 C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_longlong)]
         L.orc_batch.restype = C.c_int
+        L.orc_batch_scene.argtypes = L.orc_batch.argtypes + [dp]
+        L.orc_batch_scene.restype = C.c_int
+        L.orc_set_record.argtypes = [C.c_void_p, dp]
+        L.orc_get_record.argtypes = [C.c_void_p, dp]
+        for name in ("gripper_collision", "gripper_contact"):
+            getattr(L, "orc_" + name).argtypes = [C.c_void_p]
+            getattr(L, "orc_" + name).restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -77,9 +84,9 @@ def _ip(a):
 class OracleSim:
     """One fp64 environment.  Attribute names follow MuJoCo's mjData."""
 
-    def __init__(self, model):
+    def __init__(self, model, ground_name="geom:ground"):
         self.model = model
-        self.desc, self._keep = make_desc(model)
+        self.desc, self._keep = make_desc(model, ground_name)
         self.L = lib()
         self.h = C.c_void_p(self.L.orc_create(C.byref(self.desc)))
         m = model
@@ -137,6 +144,22 @@ class OracleSim:
     def kinematics(self): self.L.orc_kinematics_only(self.h)
     def contact_with_object(self): return bool(self.L.orc_contact_with_object(self.h))
 
+    def record_size(self):
+        m = self.model
+        return m.nq + 2 * m.nv + m.nu + 7 * int(m.arr["nmocap"])
+
+    def get_record(self):
+        r = np.zeros(self.record_size())
+        self.L.orc_get_record(self.h, _dp(r))
+        return r
+
+    def set_record(self, r):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        self.L.orc_set_record(self.h, _dp(r))
+
+    def gripper_collision(self): return bool(self.L.orc_gripper_collision(self.h))
+    def gripper_contact(self): return bool(self.L.orc_gripper_contact(self.h))
+
     def place(self, pose7, base_qadr, joints, jadr):
         pose7 = np.ascontiguousarray(pose7, dtype=np.float64)
         joints = np.ascontiguousarray(joints, dtype=np.float64)
@@ -144,9 +167,10 @@ class OracleSim:
         self.L.orc_place(self.h, _dp(pose7), int(base_qadr), _dp(joints), _ip(jadr), len(jadr))
 
 
-def batch(model, mode, poses7, base_qadr, joints, jadr, close_ctrl, cfg: RolloutCfg, nthreads=1):
-    """mode 0: collision-free mask, mode 1: stability labels.  Returns (labels bool[N], steps int64[N])."""
-    desc, keep = make_desc(model)
+def batch(model, mode, poses7, base_qadr, joints, jadr, close_ctrl, cfg: RolloutCfg, nthreads=1, scene=None, ground_name="geom:ground"):
+    """mode 0: collision-free mask, mode 1: stability labels, 2 / 3: clutter-table versions (scene = state
+    record qpos|qvel|qacc_warmstart|ctrl|mocap).  Returns (labels bool[N], steps int64[N])."""
+    desc, keep = make_desc(model, ground_name)
     poses7 = np.ascontiguousarray(poses7, dtype=np.float64)
     joints = np.ascontiguousarray(joints, dtype=np.float64)
     jadr = np.ascontiguousarray(jadr, dtype=np.int32)
@@ -154,6 +178,8 @@ def batch(model, mode, poses7, base_qadr, joints, jadr, close_ctrl, cfg: Rollout
     n = len(poses7)
     labels = np.zeros(n, dtype=np.uint8)
     steps = np.zeros(n, dtype=np.int64)
-    lib().orc_batch(C.byref(desc), mode, n, _dp(poses7), int(base_qadr), _dp(joints), _ip(jadr), joints.shape[1], _dp(close_ctrl),
-                    C.byref(cfg), nthreads, labels.ctypes.data_as(C.POINTER(C.c_ubyte)), steps.ctypes.data_as(C.POINTER(C.c_longlong)))
+    sc = np.ascontiguousarray(scene, dtype=np.float64) if scene is not None else None
+    lib().orc_batch_scene(C.byref(desc), mode, n, _dp(poses7), int(base_qadr), _dp(joints), _ip(jadr), joints.shape[1], _dp(close_ctrl),
+                          C.byref(cfg), nthreads, labels.ctypes.data_as(C.POINTER(C.c_ubyte)), steps.ctypes.data_as(C.POINTER(C.c_longlong)),
+                          _dp(sc) if sc is not None else None)
     return labels.astype(bool), steps

@@ -68,6 +68,28 @@ extern "C" int l1_step_host(L1Model *M, int n, int nstep, const void *state_in, 
   return 0;
 }
 
+extern "C" int l1_clutter_host(L1Model *M, int mode, int n, const double *scene, const float *pose7, const float *joints, int nj,
+                               const int *joint_qposadr, int base_qposadr, const double *close_ctrl, const MgsRolloutCfg *cfg, uint8_t *labels,
+                               int *steps) {
+  RolloutParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.mode = mode; prm.n = n; prm.nj = nj; prm.base_qposadr = base_qposadr;
+  for (int k = 0; k < nj; k++) prm.joint_qposadr[k] = joint_qposadr[k];
+  if (cfg) {
+    prm.nstep_close = cfg->nstep_close; prm.nstep_lift = cfg->nstep_lift; prm.shake_steps = cfg->shake_steps;
+    prm.repose_on_close = cfg->repose_on_close; prm.lift_dist = (real)cfg->lift_dist; prm.shake_dist = (real)cfg->shake_dist;
+  }
+  if (close_ctrl) for (int u = 0; u < M->dm.nu; u++) prm.close_ctrl[u] = (real)close_ctrl[u];
+  std::vector<real> rec(M->state_stride);
+  for (int i = 0; i < M->state_stride; i++) rec[i] = (real)scene[i];
+  BatchIO io;
+  memset(&io, 0, sizeof(io));
+  io.pose7 = pose7; io.joints = joints; io.labels = labels; io.steps = steps;
+  io.state_in = rec.data(); io.state_stride = M->state_stride;
+  run_all(M, prm, io);
+  return 0;
+}
+
 extern "C" int l1_rollout_host(L1Model *M, int mode, int n, const float *pose7, const float *joints, int nj, const int *joint_qposadr,
                                int base_qposadr, const double *close_ctrl, const MgsRolloutCfg *cfg, uint8_t *labels, int *steps) {
   RolloutParams prm;

@@ -1,0 +1,84 @@
+"""Clutter table (config 5 path): oracle vs the kernel source (lane-1 build) on the
+restore-scene / place / close / lift program, and the mgs.env.ClutterTableEnv host logic."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from hostsim import lane1
+from mj_grasp_sim_b200 import lib as mlib
+from mj_grasp_sim_b200 import scenes
+from oracle.oracle import OracleSim, RolloutCfg, batch
+
+
+@pytest.fixture(scope="module")
+def clutter():
+    m, info = scenes.build_clutter_scene("panda", [0, 1, 2])
+    s = OracleSim(m, ground_name="geom:table")
+
+    def step_fn(rec, n):
+        s.set_record(rec)
+        s.step(n)
+        assert s.bad == 0
+        return s.get_record()
+
+    rec = scenes.gen_clutter(m, info, step_fn, 0)
+    H, w = scenes.clutter_candidates(m, info, rec, 12, 0)
+    return m, info, rec, scenes.process_poses(H, "panda"), scenes.panda_width_to_joints(w).astype(np.float32)
+
+
+def test_scene_layout_and_settling(clutter):
+    m, info, rec, _, _ = clutter
+    g = m.names["geom"]
+    # geom order the contact tests rely on: gripper < table < camera < origin < walls < objects
+    assert g["panda_col_12"] < g["geom:table"] < g["geom:camera"] < g["geom:base_origin"] < g["geom:wall_top"] < g["geom:wall_left"]
+    assert (m.nq, m.nv) == (9 + 7 + 21, 8 + 6 + 18)
+    assert m.body_gravcomp[m.names["body"]["body:camera"]] == 1.0
+    cam = m.jnt_qposadr[m.names["joint"]["camera:joint"]]
+    assert np.allclose(rec[cam:cam + 3], [0, 0, -1.0], atol=1e-6)           # gravity-compensated camera hovers
+    for a in info["object_qposadr"]:
+        assert 0.005 < rec[a + 2] < 0.06 and np.abs(rec[a:a + 2]).max() < 0.3  # objects rest on the table near the drop point
+    assert np.abs(rec[m.nq:m.nq + m.nv]).max() < 1e-3                        # settled
+    assert abs(rec[2] - 1.5) < 2e-3                                           # gripper hangs on its weld (sags < 2 mm)
+
+
+@pytest.mark.parametrize("f64", [True, False])
+def test_clutter_programs_lane1_vs_oracle(clutter, f64):
+    m, info, rec, pose7, joints = clutter
+    sched = (500, 300, 0, 0, 0.05, 0.0)
+    ofree, _ = batch(m, 2, pose7.astype(np.float64), info["base_qposadr"], joints.astype(np.float64), info["joint_qposadr"], info["close_ctrl"],
+                     RolloutCfg(*sched), 4, scene=rec, ground_name="geom:table")
+    olab, osteps = batch(m, 3, pose7.astype(np.float64), info["base_qposadr"], joints.astype(np.float64), info["joint_qposadr"], info["close_ctrl"],
+                         RolloutCfg(*sched), 4, scene=rec, ground_name="geom:table")
+    L = mlib.BatchSim(m, lib=mlib.bind(C.CDLL(lane1.build(f64)), prefix="l1_"), prefix="l1_", ground_name="geom:table")
+    free = L.clutter_collision_mask(rec, pose7, joints, info["joint_qposadr"], info["base_qposadr"])
+    lab, steps = L.clutter_stable_mask(rec, pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], mlib.MgsRolloutCfg(*sched))
+    assert (free == ofree).all()
+    assert (lab == olab).mean() >= (1.0 if f64 else 10 / 12)
+    assert set(np.unique(osteps)) <= {500 + 100 * k for k in range(1, 4)}  # early break only at (t+1) % 100 == 0
+
+
+def test_state_vector_roundtrip_and_bounds():
+    from mj_grasp_sim_b200.mgs.env.clutter_table import ClutterTableEnv
+    from mj_grasp_sim_b200.mgs.gripper.selector import get_gripper
+    from mj_grasp_sim_b200.mgs.obj.hull import ObjectConvexHull
+    from mj_grasp_sim_b200.mgs.util.geo.transforms import SE3Pose
+    objs = []
+    for i in range(2):
+        pts, mass = scenes.random_hull_points(i, 16)
+        objs.append(ObjectConvexHull(SE3Pose(np.array([-8.0, -8.0 + 0.5 * i, 0.06]), np.array([1.0, 0, 0, 0]), "wxyz"), f"o{i}", [pts], mass))
+    env = ClutterTableEnv(get_gripper("PandaGripper"), objs)
+    m = env.model
+    st = env.get_state()
+    # mjSTATE_INTEGRATION: time, qpos, qvel, act, qacc_warmstart, ctrl, qfrc_applied, xfrc_applied, eq_active, mocap_pos, mocap_quat
+    assert len(st) == 1 + m.nq + m.nv + m.nv + m.nu + m.nv + 6 * m.nbody + int(m.arr["neq"]) + 7
+    st2 = st.copy()
+    st2[1:4] = [0.1, 0.2, 0.9]
+    env.set_state(st2)
+    assert np.allclose(env.get_state(), st2)
+    with pytest.raises(ValueError):
+        env.set_state(st[:-1])
+    d = env.to_dict()
+    assert set(d) == {"gripper", "objects", "env_state"} and set(d["env_state"]) == {"geom_conaffinity", "geom_contype", "geom_rgba", "body_gravcomp", "state"}
+    env2 = ClutterTableEnv.from_dict(d)
+    assert np.allclose(env2.get_state(), st2)

@@ -181,3 +181,46 @@ def test_dexterous_hands_labels(libs, request, fixture, bar):
     olab, osteps = _oracle_batch(orc, m, info, 1, pose7, joints, sched)
     assert G.overflow_count() == 0
     assert (lab == olab).mean() >= bar
+
+
+def test_clutter_table_env_on_gpu(libs):
+    """ClutterTableEnv through the reference-facing API: gen_clutter (single-env launches), is_stable, the state
+    vector hand-off, grasp_collision_mask / grasp_stable_mask vs the oracle on the same settled scene."""
+    from mj_grasp_sim_b200 import scenes
+    from mj_grasp_sim_b200.mgs.env.clutter_table import ClutterTableEnv
+    from mj_grasp_sim_b200.mgs.gripper.selector import get_gripper
+    from mj_grasp_sim_b200.mgs.obj.hull import ObjectConvexHull
+    from mj_grasp_sim_b200.mgs.util.geo.transforms import SE3Pose
+    mlib, orc = libs
+    objs = []
+    for i in range(3):
+        pts, mass = scenes.random_hull_points(10 + i, 24)
+        objs.append(ObjectConvexHull(SE3Pose(np.array([-8.0, -8.0 + 0.5 * i, 0.06]), np.array([1.0, 0, 0, 0]), "wxyz"), f"o{i}", [pts], mass))
+    gripper = get_gripper("PandaGripper")
+    env = ClutterTableEnv(gripper, objs)
+    env.set_gripper_pose([0.0, 0.0, 1.5])
+    env.gen_clutter(seed=3)
+    assert env.is_stable()
+    state = env.get_state()
+    m = env.model
+    info = dict(object_qposadr=[int(m.jnt_qposadr[m.names["joint"][f"o{i}:joint"]]) for i in range(3)])
+    H, w = scenes.clutter_candidates(m, info, env._record, 48, 1)
+    H[:4, 0, 3] += 1.0  # out of the workspace bounds: must be labelled False without being simulated
+    poses = SE3Pose.from_mat(H)
+    joints = scenes.panda_width_to_joints(w)
+    free = env.grasp_collision_mask(poses, joints)
+    assert not free[:4].any()
+    stable = env.grasp_stable_mask(poses, joints, state, nstep_lift=1000, lift_dist=0.1)
+    # oracle on the same scene record
+    pose7, j32, jadr = env._process(poses, joints)
+    base = gripper.get_freejoint_idxs(env)[0]
+    sched = (3000, 1000, 0, 0, 0.1, 0.0)
+    ofree, _ = orc.batch(m, 2, pose7.astype(np.float64), base, j32.astype(np.float64), jadr, gripper.close_ctrl(), orc.RolloutCfg(*sched),
+                         os.cpu_count() or 1, scene=env._record, ground_name="geom:table")
+    olab, _ = orc.batch(m, 3, pose7.astype(np.float64), base, j32.astype(np.float64), jadr, gripper.close_ctrl(), orc.RolloutCfg(*sched),
+                        os.cpu_count() or 1, scene=env._record, ground_name="geom:table")
+    assert (free[4:] == ofree[4:]).mean() >= 0.97
+    assert (stable == olab).mean() >= 0.9
+    # scene.npz payload round trip
+    env2 = ClutterTableEnv.from_dict(env.to_dict())
+    assert np.array_equal(env2.grasp_collision_mask(poses, joints), free)
