@@ -219,8 +219,11 @@ def test_clutter_table_env_on_gpu(libs):
                          os.cpu_count() or 1, scene=env._record, ground_name="geom:table")
     olab, _ = orc.batch(m, 3, pose7.astype(np.float64), base, j32.astype(np.float64), jadr, gripper.close_ctrl(), orc.RolloutCfg(*sched),
                         os.cpu_count() or 1, scene=env._record, ground_name="geom:table")
-    assert (free[4:] == ofree[4:]).mean() >= 0.97
-    assert (stable == olab).mean() >= 0.9
+    p = np.asarray(poses.pos)
+    inb = (np.abs(p[:, 0]) < 0.25) & (np.abs(p[:, 1]) < 0.25) & (p[:, 2] > 0) & (p[:, 2] < 1.0)  # reference bounds test (:344-354)
+    assert not free[~inb].any()
+    assert (free[inb] == ofree[inb]).mean() >= 0.97
+    assert (stable == olab).mean() >= 0.9  # 48 candidates, fp32, objects jostling each other: see profiles/ for rates at scale
     # scene.npz payload round trip
     env2 = ClutterTableEnv.from_dict(env.to_dict())
     assert np.array_equal(env2.grasp_collision_mask(poses, joints), free)
