@@ -159,9 +159,36 @@ MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
   }
 }
 #else
-// GPU: lanes own rows (row i on lane i % 32); every diagonal block advances one pivot column per step
+// GPU: lanes own rows (row i on lane i % 32); every diagonal block advances one pivot column per step.
+// n <= 32 (every in-scope model except Shadow): one row per lane, pivots kept in registers.
 MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
   const int nsteps = blocked ? MD.max_tree_dofs : n;
+  if (n <= LANES) {
+    const int i = MGS_LANE;
+    int tadr = 0, tnum = n;
+    if (blocked && i < n) { tadr = LDG(MD.dof_treeadr + i); tnum = LDG(MD.dof_treenum + i); }
+    #pragma unroll 1
+    for (int t = 0; t < nsteps; t++) {
+      const int j = tadr + t;
+      const int live = (i < n) && (t < tnum);
+      WSYNC();
+      real d = 1;
+      if (live) { d = A[j * n + j]; d = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL); }
+      WSYNC();
+      if (live) {
+        if (i == j) A[j * n + j] = d;
+        else if (i > j) A[i * n + j] *= R_(1.0) / d;
+      }
+      WSYNC();
+      if (live && i > j) {
+        const real lij = A[i * n + j];
+        #pragma unroll 1
+        for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+      }
+    }
+    WSYNC();
+    return;
+  }
   #pragma unroll 1
   for (int t = 0; t < nsteps; t++) {
     WSYNC();
@@ -194,6 +221,37 @@ MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
 // x <- (L L')^-1 x (column-oriented substitution)
 MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
   const int nsteps = blocked ? MD.max_tree_dofs : n;
+  if (n <= LANES) {
+    const int i = MGS_LANE;
+    int tadr = 0, tnum = n;
+    if (blocked && i < n) { tadr = LDG(MD.dof_treeadr + i); tnum = LDG(MD.dof_treenum + i); }
+    #pragma unroll 1
+    for (int t = 0; t < nsteps; t++) {
+      const int k = tadr + t, live = (i < n) && (t < tnum);
+      WSYNC();
+      real xk = 0;
+      if (live) xk = x[k] / L[k * n + k];
+      WSYNC();
+      if (live) {
+        if (i == k) x[k] = xk;
+        else if (i > k) x[i] -= L[i * n + k] * xk;
+      }
+    }
+    #pragma unroll 1
+    for (int t = nsteps - 1; t >= 0; t--) {
+      const int k = tadr + t, live = (i < n) && (t < tnum);
+      WSYNC();
+      real xk = 0;
+      if (live) xk = x[k] / L[k * n + k];
+      WSYNC();
+      if (live) {
+        if (i == k) x[k] = xk;
+        else if (i < k) x[i] -= L[k * n + i] * xk;
+      }
+    }
+    WSYNC();
+    return;
+  }
   #pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {
     #pragma unroll 1
