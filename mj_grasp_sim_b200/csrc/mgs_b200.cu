@@ -91,7 +91,7 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
   rebase_model(M->dm, M->d_blob);
   CU(cudaMalloc(&M->d_counter, 2 * sizeof(unsigned int)));  // [0] work queue head, [1] environments that overflowed a capacity
   layout_compute(&M->L, desc->nq, desc->nv, desc->nu, desc->nbody, desc->njnt, desc->nmocap, desc->ntendon, desc->ncgeom, blob.ncon_max,
-                 blob.nefc_max);
+                 blob.nefc_max, desc->npair);
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   M->num_sms = prop.multiProcessorCount;

@@ -14,7 +14,7 @@
 #define MGS_MAXCLIP 12
 #define MGS_FACE_ALIGN_MIN R_(0.9990)
 
-struct SupPt { real v[3], v1[3], v2[3]; };
+struct SupPt { real v[3], v1[3], v2[3]; int ia, ib; };  // ia/ib: vertex ids of the two support points (-1: not a vertex)
 
 struct GeomRef {
   int cg, type, hull;
@@ -31,7 +31,7 @@ MGS_DEV void geomref_init(GeomRef &g, const Env &e, int cg) {
   g.cur = 0;
 }
 
-struct Sup { real x, y, z; int cur; };
+struct Sup { real x, y, z; int cur, vid; };
 
 // support point (world) of collision geom `cg` in world direction d.  Arguments and result travel in
 // registers (the function is deliberately NOT inlined: one copy of the code serves every call site,
@@ -40,10 +40,12 @@ MGS_DEVN Sup geom_support(const real *Rm, const real *gp, int cg, int type, int 
   real dl[3], p[3] = {0, 0, 0}, d[3] = {dx, dy, dz};
   mulmatTvec3(dl, Rm, d);
   real s0 = LDG(MD.cgeom_size + 3 * cg), s1 = LDG(MD.cgeom_size + 3 * cg + 1), s2 = LDG(MD.cgeom_size + 3 * cg + 2);
+  int vid = -1;
   if (type == GEOM_BOX) {
     p[0] = dl[0] >= 0 ? s0 : -s0;
     p[1] = dl[1] >= 0 ? s1 : -s1;
     p[2] = dl[2] >= 0 ? s2 : -s2;
+    vid = (dl[0] >= 0 ? 1 : 0) | (dl[1] >= 0 ? 2 : 0) | (dl[2] >= 0 ? 4 : 0);
   } else if (type == GEOM_MESH) {
     // hill climbing on the hull's vertex graph from the previous answer
     const int vadr = LDG(MD.hull_vertadr + hull), nvert = LDG(MD.hull_vertnum + hull);
@@ -62,6 +64,7 @@ MGS_DEVN Sup geom_support(const real *Rm, const real *gp, int cg, int type, int 
       cur = nxt;
     }
     ld3(p, V + 3 * cur);
+    vid = cur;
   } else if (type == GEOM_SPHERE) {
     scl3(p, dl, s0);
   } else if (type == GEOM_CAPSULE) {
@@ -75,7 +78,7 @@ MGS_DEVN Sup geom_support(const real *Rm, const real *gp, int cg, int type, int 
   real o[3];
   mulmatvec3(o, Rm, p);
   Sup r;
-  r.x = o[0] + gp[0]; r.y = o[1] + gp[1]; r.z = o[2] + gp[2]; r.cur = cur;
+  r.x = o[0] + gp[0]; r.y = o[1] + gp[1]; r.z = o[2] + gp[2]; r.cur = cur; r.vid = vid;
   return r;
 }
 
@@ -83,6 +86,30 @@ MGS_DEV void mink_support(GeomRef &g1, GeomRef &g2, const real *d, SupPt &o) {
   Sup a = geom_support(g1.R, g1.p, g1.cg, g1.type, g1.hull, g1.cur, d[0], d[1], d[2]);
   Sup b = geom_support(g2.R, g2.p, g2.cg, g2.type, g2.hull, g2.cur, -d[0], -d[1], -d[2]);
   g1.cur = a.cur; g2.cur = b.cur;
+  o.ia = a.vid; o.ib = b.vid;
+  o.v1[0] = a.x; o.v1[1] = a.y; o.v1[2] = a.z;
+  o.v2[0] = b.x; o.v2[1] = b.y; o.v2[2] = b.z;
+  sub3(o.v, o.v1, o.v2);
+}
+
+// world position of vertex `vid` of a box / hull geom (warm start of the portal)
+MGS_DEVN Sup geom_vertex(const real *Rm, const real *gp, int cg, int type, int hull, int vid) {
+  real p[3], o[3];
+  if (type == GEOM_BOX) {
+    const real s0 = LDG(MD.cgeom_size + 3 * cg), s1 = LDG(MD.cgeom_size + 3 * cg + 1), s2 = LDG(MD.cgeom_size + 3 * cg + 2);
+    p[0] = (vid & 1) ? s0 : -s0; p[1] = (vid & 2) ? s1 : -s1; p[2] = (vid & 4) ? s2 : -s2;
+  } else {
+    ld3(p, MD.hull_vert + 3 * (LDG(MD.hull_vertadr + hull) + vid));
+  }
+  mulmatvec3(o, Rm, p);
+  Sup r;
+  r.x = o[0] + gp[0]; r.y = o[1] + gp[1]; r.z = o[2] + gp[2]; r.cur = vid; r.vid = vid;
+  return r;
+}
+MGS_DEV void portal_point(const GeomRef &g1, const GeomRef &g2, int ia, int ib, SupPt &o) {
+  Sup a = geom_vertex(g1.R, g1.p, g1.cg, g1.type, g1.hull, ia);
+  Sup b = geom_vertex(g2.R, g2.p, g2.cg, g2.type, g2.hull, ib);
+  o.ia = ia; o.ib = ib;
   o.v1[0] = a.x; o.v1[1] = a.y; o.v1[2] = a.z;
   o.v2[0] = b.x; o.v2[1] = b.y; o.v2[2] = b.z;
   sub3(o.v, o.v1, o.v2);
@@ -145,7 +172,7 @@ MGS_DEVN void closest_on_triangle(const real *a, const real *b, const real *c, r
 // pass the origin), PEN (push the portal to the surface).  `active` = this lane has a pair to test.
 // Returns 1 when penetrating: depth > 0, dir from g1 to g2 (unit), pos.
 enum { MPR_V1 = 0, MPR_V2, MPR_V3, MPR_REFINE, MPR_PEN, MPR_DONE };
-MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, real *depth, real *dir, real *pos) {
+MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, int *cache, real *depth, real *dir, real *pos) {
   const real tol = MD.mpr_tolerance;
   SupPt p0, p1, p2, p3, s;
   real d[3] = {1, 0, 0}, va[3], vb[3];
@@ -156,6 +183,30 @@ MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, real *depth, 
     if (dot3(p0.v, p0.v) < R_(1e-28)) p0.v[0] += R_(1e-10);
     scl3(d, p0.v, -1); normalize3(d);
     state = MPR_V1;
+    // WARM START: a pair that was penetrating at the previous step remembers the vertex pairs of its final
+    // portal.  Rebuilt at the new poses, that triangle is almost always still a valid portal (the origin ray
+    // from v0 passes through it), so the search resumes in the refinement phase and needs 1-3 support
+    // queries instead of 20-30.  (MPR's answer is the boundary face of the Minkowski difference pierced by
+    // that ray: it does not depend on the starting portal beyond mpr_tolerance.)
+    if (cache && cache[2] >= 0 && (g1.type == GEOM_BOX || g1.type == GEOM_MESH) && (g2.type == GEOM_BOX || g2.type == GEOM_MESH)) {
+      portal_point(g1, g2, cache[0] & 0xffff, cache[0] >> 16, p1);
+      portal_point(g1, g2, cache[1] & 0xffff, cache[1] >> 16, p2);
+      portal_point(g1, g2, cache[2] & 0xffff, cache[2] >> 16, p3);
+      real a1[3], a2[3], a3[3], t[3];
+      sub3(a1, p1.v, p0.v); sub3(a2, p2.v, p0.v); sub3(a3, p3.v, p0.v);
+      cross3(t, a2, a3);
+      real T = dot3(a1, t);
+      if (T < 0) { SupPt sw = p2; p2 = p3; p3 = sw; T = -T; }
+      real s12, s23, s31;
+      cross3(t, p1.v, p2.v); s12 = -dot3(t, p0.v);
+      cross3(t, p2.v, p3.v); s23 = -dot3(t, p0.v);
+      cross3(t, p3.v, p1.v); s31 = -dot3(t, p0.v);
+      if (T > R_(1e-20) && s12 >= 0 && s23 >= 0 && s31 >= 0) {
+        portal_dir(p1, p2, p3, d);
+        state = (dot3(d, p1.v) >= 0) ? MPR_PEN : MPR_REFINE;
+        it = 0;
+      }
+    }
   }
   #pragma unroll 1
   for (;;) {
@@ -244,6 +295,13 @@ MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, real *depth, 
       }
     }
   }
+  if (cache && active) {
+    // remember the final portal of a penetrating pair (vertex ids fit 16 bits), forget it otherwise
+    if (hit && p1.ia >= 0 && p1.ib >= 0 && p2.ia >= 0 && p2.ib >= 0 && p3.ia >= 0 && p3.ib >= 0 &&
+        (p1.ia | p1.ib | p2.ia | p2.ib | p3.ia | p3.ib) < 32768) {
+      cache[0] = p1.ia | (p1.ib << 16); cache[1] = p2.ia | (p2.ib << 16); cache[2] = p3.ia | (p3.ib << 16);
+    } else cache[2] = -1;
+  }
   return hit;
 }
 
@@ -280,7 +338,7 @@ struct PairContacts { int n; real normal[3], pos[4][3], dist[4]; };
 
 // narrowphase for candidate pair `pair` (this lane's pair; pair < 0: lane idle); fills up to 4 contacts.
 // Called by all lanes of the warp together: the MPR stage inside is warp-converged.
-MGS_DEVN void collide_pair(const Env &e, int pair, PairContacts &out) {
+MGS_DEVN void collide_pair(Env &e, int pair, PairContacts &out) {
   out.n = 0;
   int active = 0, c1 = 0, c2 = 0;
   if (pair >= 0) {
@@ -294,7 +352,12 @@ MGS_DEVN void collide_pair(const Env &e, int pair, PairContacts &out) {
   geomref_init(g1, e, c1);
   geomref_init(g2, e, c2);
   real depth = 0, n[3], pos[3];
-  int hit = mpr_penetration(g1, g2, active, &depth, n, pos);
+  int *cache = (pair >= 0 && pair < LY.ncache) ? IARR(EF(mpr_cache)) + 3 * pair : (int *)0;
+#ifdef MGS_NO_MPR_WARMSTART
+  cache = (int *)0;
+#endif
+  if (cache && !active) cache[2] = -1;
+  int hit = mpr_penetration(g1, g2, active, cache, &depth, n, pos);
   if (!hit || !(depth > 0)) return;
   int poly1 = (g1.type == GEOM_BOX || g1.type == GEOM_MESH), poly2 = (g2.type == GEOM_BOX || g2.type == GEOM_MESH);
   if (poly1 && poly2) {

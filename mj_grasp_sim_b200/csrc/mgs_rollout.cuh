@@ -27,6 +27,8 @@ MGS_DEVN void reset_w(Env &e) {
     for (int k = 0; k < 4; k++) EF(mocap)[7 * i + 3 + k] = LDG(MD.mocap_quat0 + 4 * i + k);
   }
   e.bad = 0; e.overflow = 0; e.ncon = 0; e.nefc = 0;
+  #pragma unroll 1
+  PFOR(i, 3 * LY.ncache) IARR(EF(mpr_cache))[i] = -1;
   WSYNC();
 }
 
@@ -107,6 +109,8 @@ MGS_DEVN int stability_program_w(Env &e, const float *pose7, const float *joints
 // load a scene record (qpos | qvel | qacc_warmstart | ctrl | mocap) from global memory
 MGS_DEVN void load_record_w(Env &e, const real *in) {
   e.bad = 0; e.overflow = 0; e.ncon = 0; e.nefc = 0;
+  #pragma unroll 1
+  PFOR(i, 3 * LY.ncache) IARR(EF(mpr_cache))[i] = -1;
   #pragma unroll 1
   PFOR(i, MD.nq) EF(qpos)[i] = in[i];
   #pragma unroll 1
