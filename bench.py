@@ -31,7 +31,11 @@ sys.path.insert(0, ROOT)
 
 N_CAND = 4096
 ROLLOUT = dict(nstep_close=3000, nstep_lift=3000, shake_steps=500, repose_on_close=0, lift_dist=0.1, shake_dist=0.02)
-WORKLOAD = "panda gripper, 1 synthetic 32-vertex convex-hull object per GPU (ycb recipe), 4096 antipodal candidates, close3000+lift3000+shake2000"
+# --workload: gripper, explicit per-environment capacities (contacts, constraint rows; 0 = the model's default), description
+WORKLOADS = {
+    "robotiq": ("robotiq2f85", (0, 0), "configs[1]: robotiq 2f-85 gripper, 1 synthetic 32-vertex convex-hull object per GPU (ycb recipe), 4096 antipodal candidates per object, close3000+lift3000+shake2000"),
+    "panda": ("panda", (20, 90), "panda gripper, 1 synthetic 32-vertex convex-hull object per GPU (ycb recipe), 4096 antipodal candidates, close3000+lift3000+shake2000"),
+}
 
 
 def b_step(model):
@@ -98,7 +102,8 @@ def run_reference(args, rank, world):
     from mj_grasp_sim_b200 import scenes
     from oracle import oracle as orc
     orc.build()
-    model, info, pose7, joints = scenes.workload("panda", "hull", 0, N_CAND)
+    gripper, _, WORKLOAD = WORKLOADS[args.workload]
+    model, info, pose7, joints = scenes.workload(gripper, "hull", 0, N_CAND)
     threads = os.cpu_count() or 1
     for _ in range(args.warmup):
         cpu_arm(model, info, pose7[:threads], joints[:threads], 0.0, threads)
@@ -132,10 +137,11 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = load()
-    model, info, pose7, joints = scenes.workload("panda", "hull", rank, N_CAND)  # one object per rank (weak scaling)
-    # per-environment capacities for this workload: 20 contacts / 90 constraint rows (the oracle sees at
-    # most 16 / 72 on these hull objects; the library counts any environment that would need more)
-    sim = BatchSim(model, device=local_rank, ncon_max=20, nefc_max=90)
+    gripper, (ncon_max, nefc_max), WORKLOAD = WORKLOADS[args.workload]
+    model, info, pose7, joints = scenes.workload(gripper, "hull", rank, N_CAND)  # one object per rank (weak scaling)
+    # per-environment capacities: panda 20 contacts / 90 constraint rows (the oracle sees at most 16 / 72 on these
+    # hull objects); the library counts any environment that would need more (config.capacity.envs_overflowed)
+    sim = BatchSim(model, device=local_rank, ncon_max=ncon_max, nefc_max=nefc_max)
     cfg = MgsRolloutCfg(**ROLLOUT)
     dev = torch.device("cuda", local_rank)
     d_pose = torch.from_numpy(pose7).to(dev)
@@ -213,7 +219,7 @@ def run_ours(args, rank, world, local_rank):
                 "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "candidates_per_gpu": N_CAND, "l2": "flushed between timed iterations (256 MiB fill)",
-                           "stable_fraction": stable_frac, "capacity": {"ncon_max": 20, "nefc_max": 90, "envs_overflowed": overflowed},
+                           "stable_fraction": stable_frac, "capacity": {"ncon_max": sim.info.ncon_max, "nefc_max": sim.info.nefc_max, "envs_overflowed": overflowed},
                            "envs_per_sm": sim.info.warps_per_block * sim.info.blocks_per_sm, "smem_bytes_per_env": sim.info.smem_bytes_per_env},
                 "grasps_per_s": world * N_CAND * args.steps / dev_s,
                 "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(pose7.nbytes + joints.nbytes),
@@ -242,6 +248,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="panda", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -171,7 +171,7 @@ MGS_DEVN void closest_on_triangle(const real *a, const real *b, const real *c, r
 // Phases: V1, V2 (first two portal vertices), V3 (third vertex / portal discovery), REFINE (portal must
 // pass the origin), PEN (push the portal to the surface).  `active` = this lane has a pair to test.
 // Returns 1 when penetrating: depth > 0, dir from g1 to g2 (unit), pos.
-enum { MPR_V1 = 0, MPR_V2, MPR_V3, MPR_REFINE, MPR_PEN, MPR_DONE };
+enum { MPR_V1 = 0, MPR_V2, MPR_V3, MPR_REFINE, MPR_PEN, MPR_DONE, MPR_AXIS };
 MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, int *cache, real *depth, real *dir, real *pos) {
   const real tol = MD.mpr_tolerance;
   SupPt p0, p1, p2, p3, s;
@@ -207,16 +207,28 @@ MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, int *cache, r
         it = 0;
       }
     }
+    // SEPARATING-AXIS CACHE: a pair that was found separated remembers the direction that proved it (16-bit
+    // components).  One support query along it usually proves separation again; otherwise start cold.
+    if (cache && cache[2] == -2) {
+      const int w0 = cache[0], w1 = cache[1];
+      d[0] = (real)(short)(w0 & 0xffff); d[1] = (real)(short)((w0 >> 16) & 0xffff); d[2] = (real)(short)(w1 & 0xffff);
+      normalize3(d);
+      state = MPR_AXIS;
+    }
   }
+  int sep = 0;  // d is a direction with negative support of the Minkowski difference (proves separation)
   #pragma unroll 1
   for (;;) {
     // single warp-collective test per iteration; no lane leaves the body early (no `continue`), so all
     // lanes re-converge at the bottom of the loop
     if (!wany(state != MPR_DONE)) break;
     if (state != MPR_DONE) mink_support(g1, g2, d, s);  // the one (converged) support call site
-    if (state == MPR_V1) {
+    if (state == MPR_AXIS) {
+      if (dot3(s.v, d) <= 0) { state = MPR_DONE; sep = 1; }
+      else { scl3(d, p0.v, -1); normalize3(d); state = MPR_V1; }  // the old axis no longer separates: cold start
+    } else if (state == MPR_V1) {
       p1 = s;
-      if (dot3(p1.v, d) <= 0) state = MPR_DONE;
+      if (dot3(p1.v, d) <= 0) { state = MPR_DONE; sep = 1; }
       else {
         cross3(d, p0.v, p1.v);
         if (dot3(d, d) < R_(1e-28) * fmax(R_(1e-30), dot3(p0.v, p0.v) * dot3(p1.v, p1.v))) {
@@ -232,7 +244,7 @@ MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, int *cache, r
       }
     } else if (state == MPR_V2) {
       p2 = s;
-      if (dot3(p2.v, d) <= 0) state = MPR_DONE;
+      if (dot3(p2.v, d) <= 0) { state = MPR_DONE; sep = 1; }
       else {
         sub3(va, p1.v, p0.v); sub3(vb, p2.v, p0.v);
         cross3(d, va, vb); normalize3(d);
@@ -241,7 +253,8 @@ MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, int *cache, r
       }
     } else if (state == MPR_V3) {
       p3 = s;
-      if (dot3(p3.v, d) <= 0 || ++it > 100) state = MPR_DONE;
+      if (dot3(p3.v, d) <= 0) { state = MPR_DONE; sep = 1; }
+      else if (++it > 100) state = MPR_DONE;
       else {
         int cont = 0;
         cross3(va, p1.v, p3.v);
@@ -260,7 +273,8 @@ MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, int *cache, r
         }
       }
     } else if (state == MPR_REFINE) {
-      if (dot3(s.v, d) < 0 || reach_tolerance(p1, p2, p3, s, d, tol) || ++it > MD.mpr_iterations) state = MPR_DONE;
+      if (dot3(s.v, d) < 0) { state = MPR_DONE; sep = 1; }
+      else if (reach_tolerance(p1, p2, p3, s, d, tol) || ++it > MD.mpr_iterations) state = MPR_DONE;
       else {
         expand_portal(p0, p1, p2, p3, s);
         portal_dir(p1, p2, p3, d);
@@ -300,6 +314,9 @@ MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, int *cache, r
     if (hit && p1.ia >= 0 && p1.ib >= 0 && p2.ia >= 0 && p2.ib >= 0 && p3.ia >= 0 && p3.ib >= 0 &&
         (p1.ia | p1.ib | p2.ia | p2.ib | p3.ia | p3.ib) < 32768) {
       cache[0] = p1.ia | (p1.ib << 16); cache[1] = p2.ia | (p2.ib << 16); cache[2] = p3.ia | (p3.ib << 16);
+    } else if (!hit && sep) {
+      const int qx = (int)(d[0] * R_(32000.0)), qy = (int)(d[1] * R_(32000.0)), qz = (int)(d[2] * R_(32000.0));
+      cache[0] = (qx & 0xffff) | ((qy & 0xffff) << 16); cache[1] = qz & 0xffff; cache[2] = -2;
     } else cache[2] = -1;
   }
   return hit;
