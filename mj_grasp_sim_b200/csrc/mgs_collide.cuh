@@ -318,6 +318,7 @@ MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, int *cache, r
       const int qx = (int)(d[0] * R_(32000.0)), qy = (int)(d[1] * R_(32000.0)), qz = (int)(d[2] * R_(32000.0));
       cache[0] = (qx & 0xffff) | ((qy & 0xffff) << 16); cache[1] = qz & 0xffff; cache[2] = -2;
     } else cache[2] = -1;
+    cache[3] = (g1.cur & 0xffff) | ((g2.cur & 0xffff) << 16);
   }
   return hit;
 }
@@ -369,11 +370,14 @@ MGS_DEVN void collide_pair(Env &e, int pair, PairContacts &out) {
   geomref_init(g1, e, c1);
   geomref_init(g2, e, c2);
   real depth = 0, n[3], pos[3];
-  int *cache = (pair >= 0 && pair < LY.ncache) ? IARR(EF(mpr_cache)) + 3 * pair : (int *)0;
+  int *cache = (pair >= 0 && pair < LY.ncache) ? IARR(EF(mpr_cache)) + 4 * pair : (int *)0;
 #ifdef MGS_NO_MPR_WARMSTART
   cache = (int *)0;
 #endif
   if (cache && !active) cache[2] = -1;
+  // hull supports resume their hill climb from the vertices this pair ended on at the previous step (word 3:
+  // two 16-bit vertex ids, 0 after reset); poses change by micrometres per step, so the climb is 0-1 moves
+  if (cache && active) { g1.cur = cache[3] & 0xffff; g2.cur = (cache[3] >> 16) & 0xffff; }
   int hit = mpr_penetration(g1, g2, active, cache, &depth, n, pos);
   if (!hit || !(depth > 0)) return;
   int poly1 = (g1.type == GEOM_BOX || g1.type == GEOM_MESH), poly2 = (g2.type == GEOM_BOX || g2.type == GEOM_MESH);

@@ -107,7 +107,7 @@ struct DevModel {
   X(ten_length, ntendon) X(ten_J, ntendon * nv) X(act_moment, nu * nv) X(act_force, nu) X(act_length, nu)          \
   X(qfrc_smooth, nv) X(qacc_smooth, nv) X(qacc, nv) X(qfrc_constraint, nv) X(Ma, nv) X(grad, nv) X(search, nv)     \
   X(Mv, nv) X(wvec, nv) X(con_pos, 3 * ncon_max) X(con_normal, 3 * ncon_max) X(con_dist, ncon_max)                 \
-  X(con_mu, ncon_max) X(con_pair, ncon_max) X(con_efc, ncon_max) X(nsB, 3 * nv) X(nsS, 32) X(mpr_cache, 3 * ncache)
+  X(con_mu, ncon_max) X(con_pair, ncon_max) X(con_efc, ncon_max) X(nsB, 3 * nv) X(nsS, 32) X(mpr_cache, 4 * ncache)
 #define MGS_LAYOUT_TRANSIENT(X)                                                                                    \
   X(xipos, 3 * nbody) X(ximat, 9 * nbody) X(xanchor, 3 * njnt) X(xaxis, 3 * njnt) X(gxpos, 3 * ncgeom)             \
   X(gxmat, 9 * ncgeom) X(cinert, 10 * nbody) X(crb, 10 * nbody) X(cdof_dot, 6 * nv) X(cvel, 6 * nbody)             \
@@ -124,7 +124,8 @@ struct Layout {
   int total, ncon_max, nefc_max, ncache;
 };
 
-#define MGS_MPR_CACHE_MAX 64  // geom pairs (the first ones of the list: the object pairs) whose last MPR portal is remembered
+#define MGS_MPR_CACHE_MAX 128  // geom pairs (the first ones of the list: the object pairs) whose last MPR result is remembered:
+                               // 4 words per pair - portal vertex pairs or separating axis (words 0-2), hill-climb start vertices (3)
 static inline void layout_compute(Layout *L, int nq, int nv, int nu, int nbody, int njnt, int nmocap, int ntendon, int ncgeom,
                                   int ncon_max, int nefc_max, int npair) {
   int off = 0;

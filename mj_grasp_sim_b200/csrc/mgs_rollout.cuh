@@ -28,7 +28,7 @@ MGS_DEVN void reset_w(Env &e) {
   }
   e.bad = 0; e.overflow = 0; e.ncon = 0; e.nefc = 0;
   #pragma unroll 1
-  PFOR(i, 3 * LY.ncache) IARR(EF(mpr_cache))[i] = -1;
+  PFOR(i, 4 * LY.ncache) IARR(EF(mpr_cache))[i] = (i & 3) == 3 ? 0 : -1;
   WSYNC();
 }
 
@@ -110,7 +110,7 @@ MGS_DEVN int stability_program_w(Env &e, const float *pose7, const float *joints
 MGS_DEVN void load_record_w(Env &e, const real *in) {
   e.bad = 0; e.overflow = 0; e.ncon = 0; e.nefc = 0;
   #pragma unroll 1
-  PFOR(i, 3 * LY.ncache) IARR(EF(mpr_cache))[i] = -1;
+  PFOR(i, 4 * LY.ncache) IARR(EF(mpr_cache))[i] = (i & 3) == 3 ? 0 : -1;
   #pragma unroll 1
   PFOR(i, MD.nq) EF(qpos)[i] = in[i];
   #pragma unroll 1

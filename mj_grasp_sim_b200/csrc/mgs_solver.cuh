@@ -28,10 +28,12 @@ MGS_DEVN real impedance_f(const real *solimp, real pos) {
   return dmin + y * (dmax - dmin);
 }
 
-// accumulate sign * axis . (d point / d qdot) into row(s): walks the dof chain of `body`
-MGS_DEVN void jac_rows_point(const Env &e, int body, const real *point, real sign, const real *axes, int naxis_t,
-                            int naxis_r, real *Jrows) {
-  // axes: [naxis_t translational axes (3 each)] followed by [naxis_r rotational axes]; rows are consecutive in Jrows
+// accumulate sign * axis . (d point / d qdot) into row(s): walks the dof chain of `body`.
+// axes: three translational axes followed by three rotational axes (3 reals each); nt <= 3 translational and
+// nr <= 3 rotational rows are written, consecutive in Jrows.  Inlined with compile-time axis indices so that the
+// caller's axes/point arrays stay in registers (as a non-inlined function taking pointers they lived in local
+// memory: ncu r1_h, 4.3 % of all stall samples were long-scoreboard waits here).
+MGS_DEV void jac_rows_point(const Env &e, int body, const real *point, real sign, const real *axes, int nt, int nr, real *Jrows) {
   const int nv = MD.nv;
   real off[3];
   sub3(off, point, EF(rootcom) + 3 * LDG(MD.body_rootid + body));
@@ -40,13 +42,14 @@ MGS_DEVN void jac_rows_point(const Env &e, int body, const real *point, real sig
   #pragma unroll 1
   for (int d = LDG(MD.body_dofadr + body) + LDG(MD.body_dofnum + body) - 1; d >= 0; d = LDG(MD.dof_parentid + d)) {
     const real *c = EF(cdof) + 6 * d;
-    real lin[3];
-    cross3(lin, c, off);
-    lin[0] += c[3]; lin[1] += c[4]; lin[2] += c[5];
-    #pragma unroll 1
-    for (int k = 0; k < naxis_t; k++) Jrows[k * nv + d] += sign * dot3(axes + 3 * k, lin);
-    #pragma unroll 1
-    for (int k = 0; k < naxis_r; k++) Jrows[(naxis_t + k) * nv + d] += sign * dot3(axes + 3 * (naxis_t + k), c);
+    const real c0 = c[0], c1 = c[1], c2 = c[2];
+    real lin[3] = {c1 * off[2] - c2 * off[1] + c[3], c2 * off[0] - c0 * off[2] + c[4], c0 * off[1] - c1 * off[0] + c[5]};
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (k < nt) Jrows[k * nv + d] += sign * (axes[3 * k] * lin[0] + axes[3 * k + 1] * lin[1] + axes[3 * k + 2] * lin[2]);
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (k < nr) Jrows[(nt + k) * nv + d] += sign * (axes[9 + 3 * k] * c0 + axes[9 + 3 * k + 1] * c1 + axes[9 + 3 * k + 2] * c2);
   }
 }
 
@@ -214,6 +217,11 @@ MGS_DEVN void make_constraint_w(Env &e) {
     }
     nefc = base;
   }
+  // zero the equality, dof-friction and contact rows cooperatively (the limit rows are already written)
+  #pragma unroll 1
+  PFOR(k, (ne + nf) * nv) EF(J)[k] = 0;
+  #pragma unroll 1
+  PFOR(k, (nefc - row_con0) * nv) EF(J)[row_con0 * nv + k] = 0;
   WSYNC();
   // --- equality rows (lane per equality)
   #pragma unroll 1
@@ -226,8 +234,6 @@ MGS_DEVN void make_constraint_w(Env &e) {
       int j1 = LDG(MD.eq_obj1id + q), j2 = LDG(MD.eq_obj2id + q);
       int qa1 = LDG(MD.jnt_qposadr + j1), d1 = LDG(MD.jnt_dofadr + j1);
       real q1 = EF(qpos)[qa1] - LDG(MD.qpos0 + qa1), pos;
-      #pragma unroll 1
-      for (int d = 0; d < nv; d++) EF(J)[r0 * nv + d] = 0;
       EF(J)[r0 * nv + d1] = 1;
       if (j2 >= 0) {
         int qa2 = LDG(MD.jnt_qposadr + j2), d2 = LDG(MD.jnt_dofadr + j2);
@@ -247,9 +253,7 @@ MGS_DEVN void make_constraint_w(Env &e) {
     mulmatvec3(p2, EF(xmat) + 9 * b2, a2); add3(p2, p2, EF(xpos) + 3 * b2);
     sub3(cpos, p1, p2);
     int nrow = (type == EQ_WELD) ? 6 : 3;
-    #pragma unroll 1
-    for (int k = 0; k < nrow * nv; k++) EF(J)[r0 * nv + k] = 0;
-    const real eye[18] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const real eye[18] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 0, 0, 0, 1, 0, 0, 0, 1};  // compile-time indexed after inlining
     int nr_rot = (type == EQ_WELD) ? 3 : 0;
     jac_rows_point(e, b1, p1, R_(1.0), eye, 3, nr_rot, EF(J) + r0 * nv);
     jac_rows_point(e, b2, p2, R_(-1.0), eye, 3, nr_rot, EF(J) + r0 * nv);
@@ -281,8 +285,6 @@ MGS_DEVN void make_constraint_w(Env &e) {
     int r = ne;
     #pragma unroll 1
     for (int k = 0; k < d; k++) r += LDG(MD.dof_frictionloss + k) > 0;
-    #pragma unroll 1
-    for (int k = 0; k < nv; k++) EF(J)[r * nv + k] = 0;
     EF(J)[r * nv + d] = 1;
     tag_row(e, r, CT_FRICTION_DOF, d, fl);
   }
@@ -293,8 +295,6 @@ MGS_DEVN void make_constraint_w(Env &e) {
     if (r0 < 0) continue;
     int p = IARR(EF(con_pair))[c], dim = LDG(MD.pair_condim + p);
     int b1 = LDG(MD.cgeom_bodyid + LDG(MD.pair_geom1 + p)), b2 = LDG(MD.cgeom_bodyid + LDG(MD.pair_geom2 + p));
-    #pragma unroll 1
-    for (int k = 0; k < dim * nv; k++) EF(J)[r0 * nv + k] = 0;
     real axes[18];
     copy3(axes, EF(con_normal) + 3 * c);
     make_frame(axes);  // tangents are a pure function of the normal: not stored
@@ -621,42 +621,146 @@ MGS_DEVN void solve_newton_w(Env &e) {
   WSYNC();
 }
 
-// min 0.5 x'Ax + b'x  s.t. sum (x_j/d_j)^2 <= r^2 , n in {2,3}: Newton on the multiplier
-MGS_DEVN void qcqp_small(real *res, const real *A, const real *b, const real *d, real r, int n) {
-  real As[9], bs[3], v[3] = {0, 0, 0}, la = 0;
-  #pragma unroll 1
-  for (int i = 0; i < n; i++) { bs[i] = b[i] * d[i]; for (int j = 0; j < n; j++) As[i * n + j] = A[i * n + j] * d[i] * d[j]; }
+// min 0.5 x'Ax + b'x  s.t. sum (x_j/d_j)^2 <= r^2 , N in {2,3}: Newton on the multiplier.
+// Fully unrolled for a compile-time N and inlined into its caller: every array below is indexed with
+// compile-time constants and lives in registers (the pointer-argument version kept A, b, d and the result
+// in local memory: ncu r1_h showed 3.6 % of all stall samples as long-scoreboard waits on its first loads).
+template <int N>
+MGS_DEV void qcqp_small(real *res, const real *A, const real *b, const real *d, real r) {
+  real As[N * N], bs[N], v[N], la = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    bs[i] = b[i] * d[i];
+    v[i] = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) As[i * N + j] = A[i * N + j] * d[i] * d[j];
+  }
   #pragma unroll 1
   for (int iter = 0; iter < 20; iter++) {
-    real P[9], t[3];
-    if (n == 2) {
+    real P[N * N];
+    if (N == 2) {
       real a00 = As[0] + la, a01 = As[1], a11 = As[3] + la, det = a00 * a11 - a01 * a01;
-      if (det < R_(1e-10)) { res[0] = res[1] = 0; return; }
+      if (det < R_(1e-10)) {
+#pragma unroll
+        for (int i = 0; i < N; i++) res[i] = 0;
+        return;
+      }
       real id = R_(1.0) / det;
       P[0] = a11 * id; P[1] = -a01 * id; P[2] = -a01 * id; P[3] = a00 * id;
     } else {
-      real a00 = As[0] + la, a01 = As[1], a02 = As[2], a11 = As[4] + la, a12 = As[5], a22 = As[8] + la;
+      real a00 = As[0] + la, a01 = As[1], a02 = As[2], a11 = As[N + 1] + la, a12 = As[N + 2], a22 = As[2 * N + 2] + la;
       real c00 = a11 * a22 - a12 * a12, c01 = a02 * a12 - a01 * a22, c02 = a01 * a12 - a02 * a11;
       real det = a00 * c00 + a01 * c01 + a02 * c02;
-      if (det < R_(1e-10)) { res[0] = res[1] = res[2] = 0; return; }
+      if (det < R_(1e-10)) {
+#pragma unroll
+        for (int i = 0; i < N; i++) res[i] = 0;
+        return;
+      }
       real id = R_(1.0) / det;
       P[0] = c00 * id; P[1] = c01 * id; P[2] = c02 * id;
-      P[3] = P[1]; P[4] = (a00 * a22 - a02 * a02) * id; P[5] = (a01 * a02 - a00 * a12) * id;
-      P[6] = P[2]; P[7] = P[5]; P[8] = (a00 * a11 - a01 * a01) * id;
+      P[N] = P[1]; P[N + 1] = (a00 * a22 - a02 * a02) * id; P[N + 2] = (a01 * a02 - a00 * a12) * id;
+      P[2 * N] = P[2]; P[2 * N + 1] = P[N + 2]; P[2 * N + 2] = (a00 * a11 - a01 * a01) * id;
     }
     real val = -r * r;
-    #pragma unroll 1
-    for (int i = 0; i < n; i++) { real s = 0; for (int j = 0; j < n; j++) s -= P[i * n + j] * bs[j]; v[i] = s; val += s * s; }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      real s = 0;
+#pragma unroll
+      for (int j = 0; j < N; j++) s -= P[i * N + j] * bs[j];
+      v[i] = s; val += s * s;
+    }
     if (val < R_(1e-10)) break;
     real deriv = 0;
-    #pragma unroll 1
-    for (int i = 0; i < n; i++) { real s = 0; for (int j = 0; j < n; j++) s += P[i * n + j] * v[j]; t[i] = s; deriv -= 2 * v[i] * s; }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      real s = 0;
+#pragma unroll
+      for (int j = 0; j < N; j++) s += P[i * N + j] * v[j];
+      deriv -= 2 * v[i] * s;
+    }
     real delta = -val / deriv;
     if (delta < R_(1e-10)) break;
     la += delta;
   }
+#pragma unroll
+  for (int i = 0; i < N; i++) res[i] = v[i] * d[i];
+}
+
+// One Gauss-Seidel update of the N friction rows (N = 2: condim 3; N = 3: condim >= 4, torsion included) of
+// contact c (first row i).  Residuals: lanes split the dofs, butterfly sums; the small QCQP runs replicated in
+// registers on every lane; then wvec += M^-1 J_c' delta (M^-1 is block diagonal per kinematic tree).
+// Returns the cost decrease contribution (`change`, <= 0 when accepted).
+template <int N>
+MGS_DEV real noslip_contact_w(Env &e, int c, int i, int p, const real *AC, real *T) {
+  const int nv = MD.nv;
+  real res[N], Ac[N * N], old[N], bc[N], v[N], delta[N], fr[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) res[j] = 0;
   #pragma unroll 1
-  for (int i = 0; i < n; i++) res[i] = v[i] * d[i];
+  PFOR(d, nv) {
+    const real u = EF(qacc_smooth)[d] + EF(wvec)[d];
+#pragma unroll
+    for (int j = 0; j < N; j++) res[j] += EF(J)[(i + 1 + j) * nv + d] * u;
+  }
+  {
+    int q = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      res[j] = wsum(res[j]) - EF(efc_aref)[i + 1 + j];
+      old[j] = EF(efc_force)[i + 1 + j];
+      fr[j] = LDG(MD.pair_friction + 5 * p + j);
+#pragma unroll
+      for (int k = j; k < N; k++) { Ac[j * N + k] = Ac[k * N + j] = AC[6 * c + q]; q++; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    bc[j] = res[j];
+#pragma unroll
+    for (int k = 0; k < N; k++) bc[j] -= Ac[j * N + k] * old[k];
+  }
+  const real fnorm = EF(efc_force)[i];
+  if (fnorm < MGS_MINVAL) {
+#pragma unroll
+    for (int j = 0; j < N; j++) v[j] = 0;
+  } else qcqp_small<N>(v, Ac, bc, fr, fnorm);
+  real change = 0;
+#pragma unroll
+  for (int j = 0; j < N; j++) delta[j] = v[j] - old[j];
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    change += delta[j] * res[j];
+#pragma unroll
+    for (int k = 0; k < N; k++) change += R_(0.5) * delta[j] * Ac[j * N + k] * delta[k];
+  }
+  if (change > R_(1e-10)) {
+#pragma unroll
+    for (int j = 0; j < N; j++) { v[j] = old[j]; delta[j] = 0; }
+    change = 0;
+  }
+  // w += M^-1 (J_c' delta)
+  #pragma unroll 1
+  PFOR(d, nv) {
+    real t = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) t += EF(J)[(i + 1 + j) * nv + d] * delta[j];
+    T[d] = t;
+  }
+  if (MGS_LANE == 0) {
+#pragma unroll
+    for (int j = 0; j < N; j++) EF(efc_force)[i + 1 + j] = v[j];
+  }
+  WSYNC();
+  #pragma unroll 1
+  PFOR(d, nv) {
+    const int lo = LDG(MD.dof_treeadr + d), hi = lo + LDG(MD.dof_treenum + d);
+    real t = 0;
+    #pragma unroll 1
+    for (int k = lo; k < hi; k++) t += EF(Minv)[d * nv + k] * T[k];
+    EF(wvec)[d] += t;
+  }
+  WSYNC();
+  return change;
 }
 
 // mj_solNoSlip: Gauss-Seidel on the friction rows with the UNREGULARISED A = J M^-1 J'.
@@ -736,60 +840,7 @@ MGS_DEVN void solve_noslip_w(Env &e) {
       if (i < 0) continue;
       const int p = IARR(EF(con_pair))[c], dim = LDG(MD.pair_condim + p);
       if (dim < 3) continue;
-      int n = dim - 1;
-      if (n > 3) n = 3;
-      // residuals of the n friction rows: lane j does row j, then the values are shared
-      real myres = 0;
-      if (MGS_LANE < n || LANES == 1) {
-        #pragma unroll 1
-        for (int j = (LANES == 1 ? 0 : MGS_LANE); j < (LANES == 1 ? n : MGS_LANE + 1); j++) {
-          const real *Jj = EF(J) + (i + 1 + j) * nv;
-          real t = -EF(efc_aref)[i + 1 + j];
-          #pragma unroll 1
-          for (int d = 0; d < nv; d++) t += Jj[d] * (EF(qacc_smooth)[d] + EF(wvec)[d]);
-          if (LANES == 1) EF(nsS)[j] = t; else myres = t;
-        }
-      }
-      real res[3], Ac[9], old[3], bc[3], v[3], delta[3], fr[3];
-#ifdef MGS_HOST
-      for (int j = 0; j < n; j++) res[j] = EF(nsS)[j];
-      (void)myres;
-#else
-      res[0] = __shfl_sync(0xffffffffu, myres, 0); res[1] = __shfl_sync(0xffffffffu, myres, 1); res[2] = __shfl_sync(0xffffffffu, myres, 2);
-#endif
-      {
-        int q = 0;
-        for (int j = 0; j < 3; j++)
-          for (int k = j; k < 3; k++)
-            if (j < n && k < n) { Ac[j * n + k] = Ac[k * n + j] = AC[6 * c + q]; q++; }
-      }
-      for (int j = 0; j < 3; j++) if (j < n) { old[j] = EF(efc_force)[i + 1 + j]; fr[j] = LDG(MD.pair_friction + 5 * p + j); }
-      for (int j = 0; j < 3; j++) if (j < n) { bc[j] = res[j]; for (int k = 0; k < 3; k++) if (k < n) bc[j] -= Ac[j * n + k] * old[k]; }
-      const real fnorm = EF(efc_force)[i];
-      if (fnorm < MGS_MINVAL) { for (int j = 0; j < 3; j++) v[j] = 0; }
-      else qcqp_small(v, Ac, bc, fr, fnorm, n);
-      real change = 0;
-      for (int j = 0; j < 3; j++) delta[j] = (j < n) ? v[j] - old[j] : R_(0.0);
-      for (int j = 0; j < 3; j++) if (j < n) { change += delta[j] * res[j]; for (int k = 0; k < 3; k++) if (k < n) change += R_(0.5) * delta[j] * Ac[j * n + k] * delta[k]; }
-      if (change > R_(1e-10)) { for (int j = 0; j < 3; j++) { v[j] = (j < n) ? old[j] : R_(0.0); delta[j] = 0; } change = 0; }
-      // w += M^-1 (J_c' delta)
-      #pragma unroll 1
-      PFOR(d, nv) {
-        real t = 0;
-        for (int j = 0; j < 3; j++) if (j < n) t += EF(J)[(i + 1 + j) * nv + d] * delta[j];
-        T[d] = t;
-      }
-      PFOR(j, n) EF(efc_force)[i + 1 + j] = v[j];
-      WSYNC();
-      #pragma unroll 1
-      PFOR(d, nv) {
-        real t = 0;
-        #pragma unroll 1
-        for (int k = 0; k < nv; k++) t += EF(Minv)[d * nv + k] * T[k];
-        EF(wvec)[d] += t;
-      }
-      improvement -= change;
-      WSYNC();
+      improvement -= (dim == 3) ? noslip_contact_w<2>(e, c, i, p, AC, T) : noslip_contact_w<3>(e, c, i, p, AC, T);
     }
     if (improvement * scale < MD.noslip_tolerance) break;
   }

@@ -23,6 +23,8 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 srows = list(csv.reader(io.StringIO(src)))
 shdr = srows[1]
 ci, si, ti = shdr.index("Instructions Executed"), shdr.index("# Samples"), shdr.index("Thread Instructions Executed")
+stall_cols = {k: shdr.index(k) for k in ("stall_long_sb", "stall_wait", "stall_barrier", "stall_short_sb", "stall_branch_resolving", "stall_no_inst", "stall_math", "stall_lg", "stall_mio")}
+asp_i, op_i = shdr.index("Address Space"), shdr.index("Access Operation")
 data = srows[2:]
 with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=td, capture_output=True)
@@ -43,10 +45,18 @@ if len(seq) != len(data):
     print(f"WARNING: SASS length mismatch ({len(seq)} vs {len(data)}): the .so does not match the profiled build")
 byf = collections.defaultdict(lambda: [0, 0, 0])
 byl = collections.defaultdict(lambda: [0, 0, 0])
+stf = collections.defaultdict(lambda: collections.Counter())
+stl = collections.defaultdict(lambda: collections.Counter())
+memf = collections.defaultdict(lambda: collections.Counter())
 for (f, ln), r in zip(seq, data):
     n, s, t = int(r[ci]), int(r[si]), int(r[ti])
     for d, k in ((byf, f), (byl, ln)):
         d[k][0] += n; d[k][1] += s; d[k][2] += t
+    for k, i in stall_cols.items():
+        v = int(r[i] or 0)
+        stf[f][k] += v; stl[ln][k] += v
+    if r[asp_i]:
+        memf[f][r[asp_i] + ":" + r[op_i]] += n
 tot, tots = sum(v[0] for v in byf.values()), sum(v[1] for v in byf.values())
 print(f"== by function (total warp-instructions {tot}, samples {tots}): %inst %samples lane-efficiency")
 for k, v in sorted(byf.items(), key=lambda kv: -kv[1][1])[:28]:
@@ -55,3 +65,15 @@ for k, v in sorted(byf.items(), key=lambda kv: -kv[1][1])[:28]:
 print("== top source lines: %inst %samples lane-efficiency")
 for k, v in sorted(byl.items(), key=lambda kv: -kv[1][1])[:25]:
     print(f"{100*v[0]/tot:6.2f} {100*v[1]/tots:6.2f} {v[2]/max(1,v[0])/32:5.2f}  {k}")
+
+print("== stall mix by function (% of all samples): " + " ".join(k.replace("stall_", "") for k in stall_cols))
+for k, v in sorted(byf.items(), key=lambda kv: -kv[1][1])[:28]:
+    name = re.sub(r"^\$?_Z\d+mgs_rollout_kernelv\$", "", str(k))
+    print(" ".join(f"{100*stf[k][c]/tots:6.2f}" for c in stall_cols) + "  " + name)
+print("== stall mix, top source lines")
+for k, v in sorted(byl.items(), key=lambda kv: -kv[1][1])[:40]:
+    print(f"{100*v[1]/tots:6.2f} | " + " ".join(f"{100*stl[k][c]/tots:6.2f}" for c in stall_cols) + f"  {k}")
+print("== memory instructions by function (% of all warp-instructions): space:op")
+for k, v in sorted(byf.items(), key=lambda kv: -kv[1][1])[:28]:
+    name = re.sub(r"^\$?_Z\d+mgs_rollout_kernelv\$", "", str(k))
+    print("  " + name + "  " + "  ".join(f"{a} {100*c/tot:.2f}" for a, c in sorted(memf[k].items(), key=lambda ac: -ac[1])))
