@@ -19,7 +19,6 @@
 #define MGS_MAX_WARPS_PER_BLOCK 16
 #endif
 
-extern __shared__ __align__(16) unsigned char mgs_smem_raw[];
 
 __global__ void __launch_bounds__(MGS_MAX_WARPS_PER_BLOCK * 32)
 mgs_rollout_kernel() {

@@ -488,7 +488,7 @@ MGS_DEVN void collision_w(Env &e) {
     #pragma unroll 1
     for (int k = 0; k < pc.n; k++) {
       int c = base + off + k;
-      if (c >= e.ncon_max) break;
+      if (c >= LY.ncon_max) break;
       copy3(EF(con_pos) + 3 * c, pc.pos[k]);
       copy3(EF(con_normal) + 3 * c, pc.normal);
       EF(con_dist)[c] = pc.dist[k];
@@ -496,8 +496,8 @@ MGS_DEVN void collision_w(Env &e) {
     }
     base += total;
   }
-  if (base > e.ncon_max) { e.overflow += base - e.ncon_max; base = e.ncon_max; }
-  e.ncon = base;
+  if (base > LY.ncon_max) { if (MGS_LANE == 0) EH.overflow += base - LY.ncon_max; base = LY.ncon_max; }
+  EH.ncon = base;
   WSYNC();
 }
 
@@ -508,7 +508,7 @@ MGS_DEVN void collision_w(Env &e) {
 MGS_DEVN int contact_with_object_w(const Env &e, int include_ground) {
   int hit = 0, g = MD.ground_geomid;
   #pragma unroll 1
-  PFOR(c, e.ncon) {
+  PFOR(c, EH.ncon) {
     int p = IARR(EF(con_pair))[c];
     int a = LDG(MD.cgeom_geomid + LDG(MD.pair_geom1 + p)), b = LDG(MD.cgeom_geomid + LDG(MD.pair_geom2 + p));
     if ((a < g && b > g) || (a > g && b < g)) hit = 1;

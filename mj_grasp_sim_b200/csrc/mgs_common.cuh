@@ -59,6 +59,16 @@ typedef float real;
 #define MGS_STAGE_BARRIER(k) do { if ((MGS_BAR_MASK >> (k)) & 1) __syncthreads(); } while (0)
 #endif
 
+// Innermost multiply-accumulate loops: unrolled by MGS_INNER_UNROLL (the stage-level loops stay `#pragma unroll 1`
+// to keep the instruction footprint small; at unroll 1 an inner MAC costs 2 loads + FMA + 3-4 loop-control
+// instructions with a serial dependence - ncu r1_i: 20 % of stall samples were fixed-latency "wait").
+#ifndef MGS_INNER_UNROLL
+#define MGS_INNER_UNROLL 4
+#endif
+#define MGS_PRAGMA_(x) _Pragma(#x)
+#define MGS_PRAGMA(x) MGS_PRAGMA_(x)
+#define MGS_UNROLL_INNER MGS_PRAGMA(unroll MGS_INNER_UNROLL)
+
 // lane-strided loop: on the GPU lane L handles i = L, L+32, ...; on the host build one lane does all
 #define PFOR(i, n) for (int i = MGS_LANE; i < (n); i += LANES)
 
@@ -101,7 +111,7 @@ struct DevModel {
 // temporaries) and SOLVER (constraint rows) are never live at the same time, so they OVERLAY each
 // other - shared memory per environment is what bounds the number of resident warps per SM.
 #define MGS_LAYOUT_PERSIST(X)                                                                                      \
-  X(qpos, nq) X(qvel, nv) X(qacc_ws, nv) X(ctrl, nu) X(mocap, 7 * nmocap)                                          \
+  X(hdr, 8) X(qpos, nq) X(qvel, nv) X(qacc_ws, nv) X(ctrl, nu) X(mocap, 7 * nmocap)                                          \
   X(xpos, 3 * nbody) X(xquat, 4 * nbody) X(xmat, 9 * nbody) X(rootcom, 3 * nbody) X(cdof, 6 * nv)                  \
   X(M, nv * nv) X(Minv, nv * nv) X(H, nv * nv)                                                                     \
   X(ten_length, ntendon) X(ten_J, ntendon * nv) X(act_moment, nu * nv) X(act_force, nu) X(act_length, nu)          \

@@ -26,7 +26,7 @@ MGS_DEVN void reset_w(Env &e) {
     for (int k = 0; k < 3; k++) EF(mocap)[7 * i + k] = LDG(MD.mocap_pos0 + 3 * i + k);
     for (int k = 0; k < 4; k++) EF(mocap)[7 * i + 3 + k] = LDG(MD.mocap_quat0 + 4 * i + k);
   }
-  e.bad = 0; e.overflow = 0; e.ncon = 0; e.nefc = 0;
+  EH.bad = 0; EH.overflow = 0; EH.ncon = 0; EH.nefc = 0;
   #pragma unroll 1
   PFOR(i, 4 * LY.ncache) IARR(EF(mpr_cache))[i] = (i & 3) == 3 ? 0 : -1;
   WSYNC();
@@ -108,7 +108,7 @@ MGS_DEVN int stability_program_w(Env &e, const float *pose7, const float *joints
 
 // load a scene record (qpos | qvel | qacc_warmstart | ctrl | mocap) from global memory
 MGS_DEVN void load_record_w(Env &e, const real *in) {
-  e.bad = 0; e.overflow = 0; e.ncon = 0; e.nefc = 0;
+  EH.bad = 0; EH.overflow = 0; EH.ncon = 0; EH.nefc = 0;
   #pragma unroll 1
   PFOR(i, 4 * LY.ncache) IARR(EF(mpr_cache))[i] = (i & 3) == 3 ? 0 : -1;
   #pragma unroll 1
@@ -156,7 +156,7 @@ MGS_DEVN int clutter_stable_program_w(Env &e, const float *pose7, const float *j
 MGS_DEVN void write_diag_w(const Env &e, real *o) {
   const int nv = MD.nv;
   #pragma unroll 1
-  PFOR(k, 1) { o[0] = (real)e.ncon; o[1] = (real)e.nefc; o[2] = (real)e.niter; o[3] = (real)e.bad; o[4] = (real)e.overflow; o[5] = (real)e.ne; o[6] = (real)e.nf; o[7] = (real)e.nl; }
+  PFOR(k, 1) { o[0] = (real)EH.ncon; o[1] = (real)EH.nefc; o[2] = (real)EH.niter; o[3] = (real)EH.bad; o[4] = (real)EH.overflow; o[5] = (real)EH.ne; o[6] = (real)EH.nf; o[7] = (real)EH.nl; }
   real *p = o + MGS_DIAG_HEADER;
   #pragma unroll 1
   PFOR(d, nv) { p[d] = EF(qacc)[d]; p[nv + d] = EF(qacc_smooth)[d]; p[2 * nv + d] = EF(qfrc_smooth)[d]; }
@@ -171,16 +171,16 @@ MGS_DEVN void write_diag_w(const Env &e, real *o) {
   PFOR(i, 4 * MD.nbody) p[i] = EF(xquat)[i];
   p += 4 * MD.nbody;
   #pragma unroll 1
-  PFOR(c, e.ncon_max) {
-    int ok = c < e.ncon;
+  PFOR(c, LY.ncon_max) {
+    int ok = c < EH.ncon;
     p[5 * c] = ok ? EF(con_dist)[c] : 0;
     for (int k = 0; k < 3; k++) p[5 * c + 1 + k] = ok ? EF(con_pos)[3 * c + k] : 0;
     p[5 * c + 4] = ok ? (real)IARR(EF(con_pair))[c] : -1;
   }
-  p += 5 * e.ncon_max;
+  p += 5 * LY.ncon_max;
   #pragma unroll 1
-  PFOR(i, e.nefc_max) {
-    int ok = i < e.nefc;
+  PFOR(i, LY.nefc_max) {
+    int ok = i < EH.nefc;
     p[4 * i] = ok ? EF(efc_aref)[i] : 0; p[4 * i + 1] = ok ? EF(efc_D)[i] : 0;
     p[4 * i + 2] = ok ? EF(efc_force)[i] : 0; p[4 * i + 3] = ok ? EF(efc_jar)[i] : 0;
   }
@@ -204,7 +204,7 @@ MGS_DEVN void run_env_w(Env &e, int env) {
     PFOR(i, 7 * MD.nmocap) out[MD.nq + 2 * MD.nv + MD.nu + i] = EF(mocap)[i];
     if (IO.diag_out) write_diag_w(e, IO.diag_out + (size_t)env * IO.diag_stride);
     #pragma unroll 1
-    PFOR(k, 1) { if (IO.labels) IO.labels[env] = (uint8_t)(e.bad ? 0 : 1); if (IO.steps) IO.steps[env] = steps; }
+    PFOR(k, 1) { if (IO.labels) IO.labels[env] = (uint8_t)(EH.bad ? 0 : 1); if (IO.steps) IO.steps[env] = steps; }
     WSYNC();
     return;
   }
@@ -215,7 +215,7 @@ MGS_DEVN void run_env_w(Env &e, int env) {
     place_w(e, pose7, joints);
     forward_w(e);
     MGS_STAGE_BARRIER(5);
-    label = (e.ncon == 0);  // collision-free mask: no contact of any kind (check_contact, :306-307)
+    label = (EH.ncon == 0);  // collision-free mask: no contact of any kind (check_contact, :306-307)
   } else if (PRM.mode == MGS_MODE_CLUTTER_COLLISION) {
     // ClutterTableEnv.grasp_collision_mask body (clutter_table.py:356-364); bounds test done by the host
     load_record_w(e, IO.state_in);
@@ -233,7 +233,7 @@ MGS_DEVN void run_env_w(Env &e, int env) {
     IO.labels[env] = (uint8_t)label;
     if (IO.steps) IO.steps[env] = steps;
 #ifndef MGS_HOST
-    if (e.overflow) atomicAdd(IO.work_counter + 1, 1u);
+    if (EH.overflow) atomicAdd(IO.work_counter + 1, 1u);
 #endif
   }
   if (IO.state_out) {

@@ -109,17 +109,26 @@ __constant__ KernelConsts c_k;
 #define LY (MGS_K.L)
 #define PRM (MGS_K.prm)
 #define IO (MGS_K.io)
-// per-environment scratch arrays: slice base + constant offset
-#define EF(name) (e.base + LY.name)
-struct Env {
-  real *base;
-  int ncon, nefc, ne, nf, nl, niter, bad, ncon_max, nefc_max, overflow;
-};
+// per-environment scratch arrays: slice base + constant offset.  On the device the slice base is recomputed
+// from the warp index (two integer instructions) instead of being read from `Env`: the Env object is passed by
+// reference to the non-inlined stage functions, so every field access was a local-memory load (ncu r1_h:
+// ~1900 LDL per env-step).  The per-environment counters live in the slice itself (`hdr`), i.e. in shared
+// memory; every lane writes the same value, so no lane ever reads a counter it has not written itself or that
+// was not published by a WSYNC.
+struct EnvHdr { int ncon, nefc, ne, nf, nl, niter, bad, overflow; };
+struct Env { real *base; };
+#ifdef MGS_HOST
+#define EBASE (e.base)
+#else
+extern __shared__ __align__(16) unsigned char mgs_smem_raw[];
+#define EBASE (reinterpret_cast<real *>(mgs_smem_raw) + (size_t)(threadIdx.x >> 5) * LY.total)
+#endif
+#define EF(name) (EBASE + LY.name)
+#define EH (*reinterpret_cast<EnvHdr *>(EF(hdr)))
 MGS_DEV void env_bind(Env &e, real *base) {
   e.base = base;
-  e.ncon = e.nefc = e.ne = e.nf = e.nl = e.niter = e.bad = e.overflow = 0;
-  e.ncon_max = LY.ncon_max;
-  e.nefc_max = LY.nefc_max;
+  EH.ncon = EH.nefc = EH.ne = EH.nf = EH.nl = EH.niter = EH.bad = EH.overflow = 0;
+  WSYNC();
 }
 #define IARR(p) ((int *)(p))
 
@@ -182,7 +191,7 @@ MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
       WSYNC();
       if (live && i > j) {
         const real lij = A[i * n + j];
-        #pragma unroll 1
+        MGS_UNROLL_INNER
         for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
       }
     }
@@ -287,14 +296,14 @@ MGS_DEVN void chol_inverse_w(const real *L, real *Ainv, int n, int blocked) {
     #pragma unroll 1
     for (int i = lo; i < hi; i++) {
       real s = (i == c) ? R_(1.0) : R_(0.0);
-      #pragma unroll 1
+      MGS_UNROLL_INNER
       for (int k = lo; k < i; k++) s -= L[i * n + k] * Ainv[k * n + c];
       Ainv[i * n + c] = s / L[i * n + i];
     }
     #pragma unroll 1
     for (int i = hi - 1; i >= lo; i--) {
       real s = Ainv[i * n + c];
-      #pragma unroll 1
+      MGS_UNROLL_INNER
       for (int k = i + 1; k < hi; k++) s -= L[k * n + i] * Ainv[k * n + c];
       Ainv[i * n + c] = s / L[i * n + i];
     }
@@ -306,7 +315,7 @@ MGS_DEVN void matvec_w(real *y, const real *A, const real *x, int n) {
   #pragma unroll 1
   PFOR(i, n) {
     real t = 0;
-    #pragma unroll 1
+    MGS_UNROLL_INNER
     for (int j = 0; j < n; j++) t += A[i * n + j] * x[j];
     y[i] = t;
   }

@@ -79,7 +79,7 @@ MGS_DEV void tag_row(Env &e, int r, int type, int id, real aux) {
 MGS_DEVN void finalize_rows_w(Env &e) {
   const int nv = MD.nv;
   #pragma unroll 1
-  PFOR(r, e.nefc) {
+  PFOR(r, EH.nefc) {
     const int type = EFC_TYPE(r), id = EFC_ID(r);
     real sr[2], si[5], pos = 0, diagApprox, floss = 0;
     int friction_row = 0;
@@ -116,7 +116,7 @@ MGS_DEVN void finalize_rows_w(Env &e) {
     }
     real kk, b, imp, vel = 0;
     kbi_from_solref(sr, si, pos, friction_row, &kk, &b, &imp);
-    #pragma unroll 1
+    MGS_UNROLL_INNER
     for (int d = 0; d < nv; d++) vel += EF(J)[r * nv + d] * EF(qvel)[d];
     EF(efc_aux)[r] = floss;
     const real R = fmax(MGS_MINVAL, (1 - imp) * diagApprox / imp);
@@ -127,7 +127,7 @@ MGS_DEVN void finalize_rows_w(Env &e) {
   WSYNC();
   // elliptic cones: friction-row regularisation from the normal row and impratio; regularised mu
   #pragma unroll 1
-  PFOR(c, e.ncon) {
+  PFOR(c, EH.ncon) {
     const int r0 = IARR(EF(con_efc))[c];
     if (r0 < 0) continue;
     const int p = IARR(EF(con_pair))[c], dim = LDG(MD.pair_condim + p);
@@ -172,14 +172,14 @@ MGS_DEVN void make_constraint_w(Env &e) {
       int total, off = wscan_excl(cnt, &total);
       if (cnt) {
         int r = ne + nf + cnt_base + off, dof = LDG(MD.jnt_dofadr + j);
-        if (dist0 < mg && r < e.nefc_max) {
+        if (dist0 < mg && r < LY.nefc_max) {
           #pragma unroll 1
           for (int d = 0; d < nv; d++) EF(J)[r * nv + d] = 0;
           EF(J)[r * nv + dof] = 1;
           tag_row(e, r, CT_LIMIT, j, dist0 - mg);
           r++;
         }
-        if (dist1 < mg && r < e.nefc_max) {
+        if (dist1 < mg && r < LY.nefc_max) {
           #pragma unroll 1
           for (int d = 0; d < nv; d++) EF(J)[r * nv + d] = 0;
           EF(J)[r * nv + dof] = -1;
@@ -196,20 +196,20 @@ MGS_DEVN void make_constraint_w(Env &e) {
   {
     int base = row_con0;
     #pragma unroll 1
-    for (int c0 = 0; c0 < e.ncon; c0 += LANES) {
+    for (int c0 = 0; c0 < EH.ncon; c0 += LANES) {
       int c = c0 + MGS_LANE, dim = 0;
-      if (c < e.ncon) dim = LDG(MD.pair_condim + IARR(EF(con_pair))[c]);
+      if (c < EH.ncon) dim = LDG(MD.pair_condim + IARR(EF(con_pair))[c]);
       int total, off = wscan_excl(dim, &total);
-      if (c < e.ncon) IARR(EF(con_efc))[c] = (base + off + dim <= e.nefc_max) ? base + off : -1;
+      if (c < EH.ncon) IARR(EF(con_efc))[c] = (base + off + dim <= LY.nefc_max) ? base + off : -1;
       base += total;
     }
     WSYNC();
-    if (base > e.nefc_max) {
+    if (base > LY.nefc_max) {
       // drop the contacts that do not fit (flagged); rows of the kept ones stay contiguous
-      e.overflow += 1;
+      if (MGS_LANE == 0) EH.overflow += 1;
       int keep = row_con0;
       #pragma unroll 1
-      for (int c = 0; c < e.ncon; c++) {
+      for (int c = 0; c < EH.ncon; c++) {
         int r = IARR(EF(con_efc))[c];
         if (r >= 0) keep = r + LDG(MD.pair_condim + IARR(EF(con_pair))[c]);
       }
@@ -290,7 +290,7 @@ MGS_DEVN void make_constraint_w(Env &e) {
   }
   // --- contact rows (lane per contact)
   #pragma unroll 1
-  PFOR(c, e.ncon) {
+  PFOR(c, EH.ncon) {
     int r0 = IARR(EF(con_efc))[c];
     if (r0 < 0) continue;
     int p = IARR(EF(con_pair))[c], dim = LDG(MD.pair_condim + p);
@@ -305,7 +305,7 @@ MGS_DEVN void make_constraint_w(Env &e) {
     #pragma unroll 1
     for (int k = 0; k < dim; k++) tag_row(e, r0 + k, CT_CONTACT, c, 0);
   }
-  e.ne = ne; e.nf = nf; e.nl = nl; e.nefc = nefc;
+  EH.ne = ne; EH.nf = nf; EH.nl = nl; EH.nefc = nefc;
   WSYNC();
   finalize_rows_w(e);
 }
@@ -315,7 +315,7 @@ MGS_DEVN void make_constraint_w(Env &e) {
 MGS_DEVN real constraint_update_w(Env &e) {
   real cost = 0;
   #pragma unroll 1
-  PFOR(i, e.nefc) {
+  PFOR(i, EH.nefc) {
     int type = EFC_TYPE(i);
     real D = EF(efc_D)[i], jar = EF(efc_jar)[i];
     if (type == CT_EQUALITY) {
@@ -379,7 +379,7 @@ MGS_DEVN real constraint_update_w(Env &e) {
 MGS_DEVN void ls_eval_w(const Env &e, real alpha, real *d1, real *d2) {
   real a = 0, h = 0;
   #pragma unroll 1
-  PFOR(i, e.nefc) {
+  PFOR(i, EH.nefc) {
     int type = EFC_TYPE(i);
     real D = EF(efc_D)[i], jv = EF(efc_jv)[i], x = EF(efc_jar)[i] + alpha * jv;
     if (type == CT_EQUALITY) { a += D * x * jv; h += D * jv * jv; }
@@ -426,9 +426,9 @@ MGS_DEVN void ls_eval_w(const Env &e, real alpha, real *d1, real *d2) {
 MGS_DEVN void eval_point_w(Env &e, const real *qacc) {
   const int nv = MD.nv;
   #pragma unroll 1
-  PFOR(i, e.nefc) {
+  PFOR(i, EH.nefc) {
     real t = -EF(efc_aref)[i];
-    #pragma unroll 1
+    MGS_UNROLL_INNER
     for (int d = 0; d < nv; d++) t += EF(J)[i * nv + d] * qacc[d];
     EF(efc_jar)[i] = t;
   }
@@ -467,19 +467,25 @@ MGS_DEVN void cone_hessian(const Env &e, int c, int i, int dim, real *h) {
 }
 
 MGS_DEVN void newton_hessian_w(Env &e) {
-  const int nv = MD.nv, npairs = nv * (nv + 1) / 2;
+  const int nv = MD.nv, npairs = nv * (nv + 1) / 2, nefc = EH.nefc;
+  // row weights (D for rows in their quadratic zone, else 0) make the accumulation loop branch-free; efc_jv is
+  // free here (it is rewritten right after the Hessian solve)
+  real *W = EF(efc_jv);
+  #pragma unroll 1
+  PFOR(i, nefc) W[i] = (EFC_STATE(i) == ST_QUADRATIC) ? EF(efc_D)[i] : R_(0.0);
+  WSYNC();
   #pragma unroll 1
   PFOR(idx, npairs) {
     const int ab = LDG(MD.tri_ab + idx), a = ab >> 8, b = ab & 255;  // lower-triangle index table
     real s = EF(M)[a * nv + b];
-    #pragma unroll 1
-    for (int i = 0; i < e.nefc; i++)
-      if (EFC_STATE(i) == ST_QUADRATIC) s += EF(efc_D)[i] * EF(J)[i * nv + a] * EF(J)[i * nv + b];
+    const real *Ja = EF(J) + a, *Jb = EF(J) + b;
+    MGS_UNROLL_INNER
+    for (int i = 0; i < nefc; i++) s += W[i] * Ja[i * nv] * Jb[i * nv];
     EF(H)[a * nv + b] = s;
   }
   // contacts on the cone surface (usually few): every lane rebuilds the small block, lanes split (a,b)
   #pragma unroll 1
-  for (int c = 0; c < e.ncon; c++) {
+  for (int c = 0; c < EH.ncon; c++) {
     const int i = IARR(EF(con_efc))[c];
     if (i < 0 || EFC_STATE(i) != ST_CONE) continue;
     const int dim = LDG(MD.pair_condim + IARR(EF(con_pair))[c]);
@@ -507,7 +513,7 @@ MGS_DEVN void newton_hessian_w(Env &e) {
 MGS_DEVN void solve_newton_w(Env &e) {
   const int nv = MD.nv;
   const real scale = R_(1.0) / (MD.meaninertia * (nv > 1 ? nv : 1));
-  e.niter = 0;
+  EH.niter = 0;
   // warm start: cheaper of qacc_warmstart and qacc_smooth
   eval_point_w(e, EF(qacc_ws));
   real cw = wsum(constraint_update_w(e) + gauss_cost_w(e, EF(qacc_ws)));
@@ -528,8 +534,8 @@ MGS_DEVN void solve_newton_w(Env &e) {
     #pragma unroll 1
     PFOR(d, nv) {
       real t = EF(Ma)[d] - EF(qfrc_smooth)[d];
-      #pragma unroll 1
-      for (int i = 0; i < e.nefc; i++) t -= EF(J)[i * nv + d] * EF(efc_force)[i];
+      MGS_UNROLL_INNER
+      for (int i = 0; i < EH.nefc; i++) t -= EF(J)[i * nv + d] * EF(efc_force)[i];
       EF(grad)[d] = t;
       EF(search)[d] = t;
       gn += t * t;
@@ -537,7 +543,13 @@ MGS_DEVN void solve_newton_w(Env &e) {
     gn = wsum(gn);
     // fp32: the gradient cannot be resolved below ~eps * |force terms|; floor the tolerance accordingly
     real tol_eff = fmax(MD.tolerance, R_(20.0) * (real)REAL_EPS * scale * fabs(cost));
+    // (MuJoCo tests the gradient only after an iteration; a warm start that already meets the tolerance skips
+    // the Hessian here - the two answers differ by less than the solver tolerance.)
+#ifdef MGS_NO_EARLY_GRAD_EXIT
     if (iter > 0 && scale * sqrt(gn) < tol_eff) break;
+#else
+    if (scale * sqrt(gn) < tol_eff) break;
+#endif
     newton_hessian_w(e);
     chol_solve_w(EF(H), EF(search), nv, 0);
     #pragma unroll 1
@@ -552,9 +564,9 @@ MGS_DEVN void solve_newton_w(Env &e) {
       sn += EF(search)[d] * EF(search)[d];
     }
     #pragma unroll 1
-    PFOR(i, e.nefc) {
+    PFOR(i, EH.nefc) {
       real t = 0;
-      #pragma unroll 1
+      MGS_UNROLL_INNER
       for (int d = 0; d < nv; d++) t += EF(J)[i * nv + d] * EF(search)[d];
       EF(efc_jv)[i] = t;
     }
@@ -562,10 +574,18 @@ MGS_DEVN void solve_newton_w(Env &e) {
     WSYNC();
     real d1, d2;
     ls_eval_w(e, 0, &d1, &d2);
-    d1 = wsum(d1) + g1; d2 = wsum(d2) + g2;
+    const real a0 = wsum(d1);  // constraint part of the derivative at alpha = 0
+    d1 = a0 + g1; d2 = wsum(d2) + g2;
     if (!(d1 < 0) || sn < R_(1e-30)) break;
     const real d1_0 = d1;
+    // Stopping threshold on |d1|: MuJoCo's gtol, floored by what the arithmetic can resolve.  Near the optimum
+    // (warm-started steps) the Gauss part g1 and the constraint part a0 cancel, so the rounding noise of d1 is
+    // ~eps * (|g1| + |a0|) >> eps * |d1_0|; without this term the search ran to bracket collapse on the GPU
+    // (ncu r1_h: 16 derivative evaluations per Newton iteration, 11 % of all issued instructions).
     real gtol = fmax(MD.tolerance * MD.ls_tolerance * sqrt(sn) / scale, R_(50.0) * (real)REAL_EPS * fabs(d1_0));
+#ifndef MGS_NO_LS_NOISE_FLOOR
+    gtol = fmax(gtol, R_(16.0) * (real)REAL_EPS * (fabs(g1) + fabs(a0)));
+#endif
     // Exact line search on the convex, piecewise-smooth 1-D cost: zero of its monotone derivative.
     // Newton steps while they stay inside the bracket [lo, hi]; otherwise the secant of the end
     // derivatives; bisection when the same end moved twice in a row or two iterations did not halve the
@@ -598,7 +618,7 @@ MGS_DEVN void solve_newton_w(Env &e) {
     #pragma unroll 1
     PFOR(d, nv) { EF(qacc)[d] += alpha * EF(search)[d]; EF(Ma)[d] += alpha * EF(Mv)[d]; }
     #pragma unroll 1
-    PFOR(i, e.nefc) EF(efc_jar)[i] += alpha * EF(efc_jv)[i];
+    PFOR(i, EH.nefc) EF(efc_jar)[i] += alpha * EF(efc_jv)[i];
     WSYNC();
     real oldcost = cost;
     cost = wsum(constraint_update_w(e) + gauss_cost_w(e, EF(qacc)));
@@ -608,13 +628,13 @@ MGS_DEVN void solve_newton_w(Env &e) {
       #pragma unroll 1
       PFOR(d, nv) { EF(qacc)[d] -= alpha * EF(search)[d]; EF(Ma)[d] -= alpha * EF(Mv)[d]; }
       #pragma unroll 1
-      PFOR(i, e.nefc) EF(efc_jar)[i] -= alpha * EF(efc_jv)[i];
+      PFOR(i, EH.nefc) EF(efc_jar)[i] -= alpha * EF(efc_jv)[i];
       WSYNC();
       cost = wsum(constraint_update_w(e) + gauss_cost_w(e, EF(qacc)));
       WSYNC();
       break;
     }
-    e.niter = iter + 1;
+    EH.niter = iter + 1;
     tol_eff = fmax(MD.tolerance, R_(20.0) * (real)REAL_EPS * scale * fabs(cost));
     if (scale * (oldcost - cost) < tol_eff) break;
   }
@@ -755,8 +775,9 @@ MGS_DEV real noslip_contact_w(Env &e, int c, int i, int p, const real *AC, real 
   PFOR(d, nv) {
     const int lo = LDG(MD.dof_treeadr + d), hi = lo + LDG(MD.dof_treenum + d);
     real t = 0;
-    #pragma unroll 1
-    for (int k = lo; k < hi; k++) t += EF(Minv)[d * nv + k] * T[k];
+    const real *Mrow = EF(Minv) + d * nv;
+    MGS_UNROLL_INNER
+    for (int k = lo; k < hi; k++) t += Mrow[k] * T[k];
     EF(wvec)[d] += t;
   }
   WSYNC();
@@ -777,7 +798,7 @@ MGS_DEVN void solve_noslip_w(Env &e) {
   PFOR(d, nv) EF(wvec)[d] = EF(qacc)[d] - EF(qacc_smooth)[d];
   // one (contact, upper-triangle entry) per lane; M^-1 is block diagonal per kinematic tree
   #pragma unroll 1
-  PFOR(idx, 6 * e.ncon) {
+  PFOR(idx, 6 * EH.ncon) {
     const int c = idx / 6, q = idx - 6 * c;
     const int i = IARR(EF(con_efc))[c];
     if (i < 0) continue;
@@ -796,8 +817,9 @@ MGS_DEVN void solve_noslip_w(Env &e) {
       if (ja == 0) continue;
       const int lo = LDG(MD.dof_treeadr + a), hi = lo + LDG(MD.dof_treenum + a);
       real t = 0;
-      #pragma unroll 1
-      for (int b2 = lo; b2 < hi; b2++) t += EF(Minv)[a * nv + b2] * Jk[b2];
+      const real *Mrow = EF(Minv) + a * nv;
+      MGS_UNROLL_INNER
+      for (int b2 = lo; b2 < hi; b2++) t += Mrow[b2] * Jk[b2];
       acc += ja * t;
     }
     AC[6 * c + q] = acc;
@@ -809,7 +831,7 @@ MGS_DEVN void solve_noslip_w(Env &e) {
     if (iter == 0) {
       real t = 0;
       #pragma unroll 1
-      PFOR(i, e.nefc) {
+      PFOR(i, EH.nefc) {
         int type = EFC_TYPE(i);
         int fr = type == CT_FRICTION_DOF || (type == CT_CONTACT && IARR(EF(con_efc))[EFC_ID(i)] != i);
         if (fr) t += R_(0.5) * EF(efc_force)[i] * EF(efc_force)[i] * EF(efc_R)[i];
@@ -818,7 +840,7 @@ MGS_DEVN void solve_noslip_w(Env &e) {
     }
     // dry-friction rows: J_i is the unit vector of dof d, so everything is a table lookup
     #pragma unroll 1
-    for (int i = e.ne; i < e.ne + e.nf; i++) {
+    for (int i = EH.ne; i < EH.ne + EH.nf; i++) {
       const int d = EFC_ID(i);
       const real res = EF(qacc_smooth)[d] + EF(wvec)[d] - EF(efc_aref)[i], Aii = EF(Minv)[d * nv + d];
       const real old = EF(efc_force)[i], fl = EF(efc_aux)[i];
@@ -835,7 +857,7 @@ MGS_DEVN void solve_noslip_w(Env &e) {
     }
     // contact friction dims
     #pragma unroll 1
-    for (int c = 0; c < e.ncon; c++) {
+    for (int c = 0; c < EH.ncon; c++) {
       const int i = IARR(EF(con_efc))[c];
       if (i < 0) continue;
       const int p = IARR(EF(con_pair))[c], dim = LDG(MD.pair_condim + p);
@@ -866,7 +888,7 @@ MGS_DEVN void forward_w(Env &e) {
   smooth_forces_w(e);
   make_constraint_w(e);
   MGS_STAGE_BARRIER(3);
-  if (e.nefc == 0) {
+  if (EH.nefc == 0) {
     #pragma unroll 1
     PFOR(d, nv) { EF(qacc)[d] = EF(qacc_smooth)[d]; EF(qacc_ws)[d] = EF(qacc_smooth)[d]; EF(qfrc_constraint)[d] = 0; }
     WSYNC();
@@ -877,14 +899,14 @@ MGS_DEVN void forward_w(Env &e) {
     WSYNC();
   }
   MGS_STAGE_BARRIER(4);
-  if (e.nefc != 0) {
+  if (EH.nefc != 0) {
     if (MD.noslip_iterations > 0) solve_noslip_w(e);
     else {
       #pragma unroll 1
       PFOR(d, nv) {
         real t = 0;
         #pragma unroll 1
-        for (int i = 0; i < e.nefc; i++) t += EF(J)[i * nv + d] * EF(efc_force)[i];
+        for (int i = 0; i < EH.nefc; i++) t += EF(J)[i * nv + d] * EF(efc_force)[i];
         EF(qfrc_constraint)[d] = t;
       }
       WSYNC();
@@ -954,10 +976,10 @@ MGS_DEVN void integrate_w(Env &e) {
 MGS_DEVN int step_w(Env &e, int nstep, int *steps_done) {
   #pragma unroll 1
   for (int k = 0; k < nstep; k++) {
-    if (e.bad || bad_state_w(e, 0)) { e.bad = 1; return 1; }
+    if (EH.bad || bad_state_w(e, 0)) { EH.bad = 1; return 1; }
     forward_w(e);
     MGS_STAGE_BARRIER(5);
-    if (bad_state_w(e, 1)) { e.bad = 1; return 1; }
+    if (bad_state_w(e, 1)) { EH.bad = 1; return 1; }
     integrate_w(e);
     (*steps_done)++;
   }

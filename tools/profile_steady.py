@@ -27,8 +27,13 @@ st = G.pack_state(qpos, np.zeros((n, m.nv)), ctrl=np.tile(info["close_ctrl"], (n
 t = time.time()
 st = G.step(st, settle)
 print("settle", settle, "steps:", round(time.time() - t, 3), "s", flush=True)
-t = time.time()
-st2, d = G.step(st, nstep, want_diag=True)
-dt = time.time() - t
-print(f"steady {gripper} n={n} nstep={nstep}: {dt:.3f}s  env-steps/s {n * nstep / dt:.4g}  ncon mean {d['ncon'].mean():.2f} nefc mean {d['nefc'].mean():.1f} "
-      f"niter mean {d['niter'].mean():.2f} bad {int(d['bad'].sum())}  envs/SM {G.info.warps_per_block * G.info.blocks_per_sm}", flush=True)
+reps = int(os.environ.get("MGS_STEADY_REPS", "5"))  # under ncu use MGS_STEADY_REPS=1
+times = []
+for _ in range(reps):
+    t = time.time()
+    st2, d = G.step(st, nstep, want_diag=True)
+    times.append(time.time() - t)
+dt = min(times)
+print(f"steady {gripper} n={n} nstep={nstep}: best {dt:.3f}s of {[round(x, 3) for x in times]}  env-steps/s {n * nstep / dt:.4g}  ncon mean {d['ncon'].mean():.2f} "
+      f"nefc mean {d['nefc'].mean():.1f} niter mean {d['niter'].mean():.2f} max {d['niter'].max()} hist {np.bincount(d['niter'])[:8].tolist()} "
+      f"bad {int(d['bad'].sum())} overflowed {G.overflow_count()} caps {G.info.ncon_max}/{G.info.nefc_max}  envs/SM {G.info.warps_per_block * G.info.blocks_per_sm}", flush=True)
