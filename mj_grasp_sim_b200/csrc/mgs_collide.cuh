@@ -323,18 +323,40 @@ MGS_DEVN int mpr_penetration(GeomRef &g1, GeomRef &g2, int active, int *cache, r
   return hit;
 }
 
-MGS_DEVN int best_face(const GeomRef &g, const real *n, real *align) {
-  real nl[3], bd = R_(-1e30);
-  mulmatTvec3(nl, g.R, n);
-  int fa = LDG(MD.hull_faceadr + g.hull), fn = LDG(MD.hull_facenum + g.hull), best = 0;
+// Face of hull `hull` whose normal is most aligned with the LOCAL direction (nx, ny, nz); first maximum wins.
+// Warp-cooperative: every lane calls it with the same arguments and scans a strided share of the faces
+// (the per-lane sequential scan ran with 2 of 32 lanes active and was 6-10 % of all issued instructions).
+MGS_DEVN int best_face_w(int hull, real nx, real ny, real nz, real *align) {
+  const int fa = LDG(MD.hull_faceadr + hull), fn = LDG(MD.hull_facenum + hull);
   const real *FN = MD.hull_facenormal + 3 * fa;
-  #pragma unroll 1
-  for (int f = 0; f < fn; f++) {
-    real t = LDG(FN + 3 * f) * nl[0] + LDG(FN + 3 * f + 1) * nl[1] + LDG(FN + 3 * f + 2) * nl[2];
+  real bd = R_(-1e30);
+  int best = 0x7fffffff;
+  #pragma unroll 2
+  PFOR(f, fn) {
+    const real t = LDG(FN + 3 * f) * nx + LDG(FN + 3 * f + 1) * ny + LDG(FN + 3 * f + 2) * nz;
     if (t > bd) { bd = t; best = f; }
   }
+  wargmax(bd, best);
   *align = bd;
   return best;
+}
+// best faces for every lane with `want` set (its geom `g`, world direction `n`): lanes are served one after the other
+MGS_DEV void best_face_lanes(int want, const GeomRef &g, const real *n, int *face, real *align) {
+  real nl[3] = {0, 0, 0};
+  if (want) mulmatTvec3(nl, g.R, n);
+  unsigned m = wballot(want);
+  #pragma unroll 1
+  while (m) {
+#ifdef MGS_HOST
+    const int src = 0;
+#else
+    const int src = __ffs(m) - 1;
+#endif
+    m &= m - 1;
+    real al;
+    const int f = best_face_w(wbcasti(g.hull, src), wbcast(nl[0], src), wbcast(nl[1], src), wbcast(nl[2], src), &al);
+    if (MGS_LANE == src) { *face = f; *align = al; }
+  }
 }
 MGS_DEVN int face_polygon(const GeomRef &g, int f, real (*poly)[3], real *nw) {
   int gf = LDG(MD.hull_faceadr + g.hull) + f;
@@ -379,19 +401,27 @@ MGS_DEVN void collide_pair(Env &e, int pair, PairContacts &out) {
   // two 16-bit vertex ids, 0 after reset); poses change by micrometres per step, so the climb is 0-1 moves
   if (cache && active) { g1.cur = cache[3] & 0xffff; g2.cur = (cache[3] >> 16) & 0xffff; }
   int hit = mpr_penetration(g1, g2, active, cache, &depth, n, pos);
-  if (!hit || !(depth > 0)) return;
-  int poly1 = (g1.type == GEOM_BOX || g1.type == GEOM_MESH), poly2 = (g2.type == GEOM_BOX || g2.type == GEOM_MESH);
-  if (poly1 && poly2) {
-    real a1, a2, nn[3] = {-n[0], -n[1], -n[2]};
-    int f1 = best_face(g1, n, &a1), f2 = best_face(g2, nn, &a2);
-    if (fmax(a1, a2) >= MGS_FACE_ALIGN_MIN) {
-      const int ref_is_1 = a1 >= a2;
-      const GeomRef &rg = ref_is_1 ? g1 : g2;
-      const GeomRef &ig = ref_is_1 ? g2 : g1;
-      real ref[MGS_MAXPOLY][3], nref[3], ninc[3], A[MGS_MAXCLIP][3], B[MGS_MAXCLIP][3], dist[MGS_MAXCLIP];
-      int nr = face_polygon(rg, ref_is_1 ? f1 : f2, ref, nref);
-      real mn[3] = {-nref[0], -nref[1], -nref[2]}, al;
-      int incf = best_face(ig, mn, &al);
+  hit = hit && (depth > 0);
+  // polytope pairs: multi-point manifold from the two most-aligned faces.  The face searches are warp-cooperative,
+  // so no lane leaves before them (the clipping itself stays per lane).
+  const int poly = hit && (g1.type == GEOM_BOX || g1.type == GEOM_MESH) && (g2.type == GEOM_BOX || g2.type == GEOM_MESH);
+  real a1 = 0, a2 = 0, nn[3] = {-n[0], -n[1], -n[2]};
+  int f1 = 0, f2 = 0, incf = 0;
+  best_face_lanes(poly, g1, n, &f1, &a1);
+  best_face_lanes(poly, g2, nn, &f2, &a2);
+  const int clip = poly && fmax(a1, a2) >= MGS_FACE_ALIGN_MIN;
+  const int ref_is_1 = a1 >= a2;
+  const GeomRef &rg = ref_is_1 ? g1 : g2;
+  const GeomRef &ig = ref_is_1 ? g2 : g1;
+  real ref[MGS_MAXPOLY][3], nref[3] = {0, 0, 0}, mn[3], al;
+  int nr = 0;
+  if (clip) nr = face_polygon(rg, ref_is_1 ? f1 : f2, ref, nref);
+  mn[0] = -nref[0]; mn[1] = -nref[1]; mn[2] = -nref[2];
+  best_face_lanes(clip, ig, mn, &incf, &al);
+  if (!hit) return;
+  if (clip) {
+    {
+      real ninc[3], A[MGS_MAXCLIP][3], B[MGS_MAXCLIP][3], dist[MGS_MAXCLIP];
       int na = face_polygon(ig, incf, A, ninc);
       #pragma unroll 1
       for (int ed = 0; ed < nr && na > 0; ed++) {

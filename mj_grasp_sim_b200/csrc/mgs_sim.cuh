@@ -18,6 +18,10 @@ MGS_DEV real wsum(real x) { return x; }
 MGS_DEV int wsumi(int x) { return x; }
 MGS_DEV int wany(int p) { return p; }
 MGS_DEV int wscan_excl(int x, int *total) { *total = x; return 0; }
+MGS_DEV unsigned wballot(int p) { return p ? 1u : 0u; }
+MGS_DEV real wbcast(real x, int src) { (void)src; return x; }
+MGS_DEV int wbcasti(int x, int src) { (void)src; return x; }
+MGS_DEV void wargmax(real &v, int &idx) { (void)v; (void)idx; }
 #else
 MGS_DEV real wsum(real x) {
 #pragma unroll
@@ -30,6 +34,18 @@ MGS_DEV int wsumi(int x) {
   return x;
 }
 MGS_DEV int wany(int p) { return __any_sync(0xffffffffu, p); }
+MGS_DEV unsigned wballot(int p) { return __ballot_sync(0xffffffffu, p); }
+MGS_DEV real wbcast(real x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+MGS_DEV int wbcasti(int x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+// warp arg-max; ties go to the smaller index (= the first maximum of a sequential scan)
+MGS_DEV void wargmax(real &v, int &idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const real v2 = __shfl_xor_sync(0xffffffffu, v, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
+  }
+}
 MGS_DEV int wscan_excl(int x, int *total) {
   int lane = MGS_LANE, v = x;
 #pragma unroll

@@ -1,0 +1,24 @@
+"""filter_stable_grasps (/root/reference/mgs/cli/filter_stable_grasps.py:15-50): candidates_collision_free.npz ->
+stable_grasps.npz through one batched `grasp_stability_evaluation_from_joints` launch (no `enough_stable`, as in
+the reference's call on :36).
+
+  python -m mj_grasp_sim_b200.mgs.cli.filter_stable_grasps gripper=PandaGripper object=hull:0 [dir=...]
+"""
+import os
+
+from ._common import candidate_dir, load_candidates, parse_kv, save_grasps, single_object_env
+
+
+def run(gripper_name: str, object_id: str, file_dir: str | None = None):
+    env = single_object_env(gripper_name, object_id)
+    d = candidate_dir(gripper_name, object_id, file_dir)
+    poses, joints = load_candidates(os.path.join(d, "candidates_collision_free.npz"))
+    mask = env.grasp_stability_evaluation_from_joints(poses, joints)
+    print(sum(mask))
+    save_grasps(os.path.join(d, "stable_grasps.npz"), poses[mask], joints[mask])
+    return mask
+
+
+if __name__ == "__main__":
+    kv = parse_kv()
+    run(kv.get("gripper", "PandaGripper"), kv.get("object", "cube"), kv.get("dir"))

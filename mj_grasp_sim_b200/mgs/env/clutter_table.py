@@ -123,6 +123,11 @@ class ClutterTableEnv(MjSimulation):
             stats += np.abs(np.array([self._record[a:a + 3] for a in adr]) - start).sum(axis=1)
         return bool(stats.max() < 5e-3) if len(adr) else True
 
+    def get_obj_pose(self, object_name: str) -> SE3Pose:
+        """object free-joint pose in the world (reference :323-328)"""
+        a = int(self.model.jnt_qposadr[self.model.names["joint"][f"{object_name}:joint"]])
+        return SE3Pose(np.copy(self._record[a:a + 3]), np.copy(self._record[a + 3:a + 7]), "wxyz")
+
     # ---- grasp evaluation ---------------------------------------------------------------------
     def _process(self, poses: SE3Pose, joints):
         names = self.gripper.get_actuator_joint_names()

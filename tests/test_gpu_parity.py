@@ -227,3 +227,65 @@ def test_clutter_table_env_on_gpu(libs):
     # scene.npz payload round trip
     env2 = ClutterTableEnv.from_dict(env.to_dict())
     assert np.array_equal(env2.grasp_collision_mask(poses, joints), free)
+
+
+def test_split_filter_clis_match_filter_to_stable(libs, tmp_path):
+    """filter_collision_free_candidates + filter_stable_grasps (the reference's two-stage variant) write the same
+    files as the fused filter_to_stable on the same candidates."""
+    from mj_grasp_sim_b200 import scenes
+    from mj_grasp_sim_b200.mgs.cli import filter_collision_free_candidates, filter_stable_grasps, filter_to_stable
+    from mj_grasp_sim_b200.mgs.obj.selector import get_object
+    v, t = get_object("hull:2").mesh()
+    H, w = scenes.antipodal_candidates(v, t, 40, 2)
+    for root in ("a", "b"):
+        d = tmp_path / root / "PandaGripper" / "hull:2"
+        d.mkdir(parents=True)
+        np.savez(d / "candidates.npz", pose=H, joints=scenes.panda_width_to_joints(w))
+    free, stable = filter_to_stable.run("PandaGripper", "hull:2", str(tmp_path / "a"))
+    free2 = filter_collision_free_candidates.run("PandaGripper", "hull:2", str(tmp_path / "b"))
+    stable2 = filter_stable_grasps.run("PandaGripper", "hull:2", str(tmp_path / "b"))
+    assert np.array_equal(free, free2) and np.array_equal(stable, stable2)  # same kernel, same inputs: deterministic
+    for name in ("candidates_collision_free.npz", "stable_grasps.npz"):
+        fa, fb = np.load(tmp_path / "a" / "PandaGripper" / "hull:2" / name), np.load(tmp_path / "b" / "PandaGripper" / "hull:2" / name)
+        assert np.array_equal(fa["pose"], fb["pose"]) and np.array_equal(fa["joints"], fb["joints"])
+
+
+def test_gen_scene_and_eval_grasps_clis(libs, tmp_path):
+    """gen_scene (drop/settle, stability gate, per-scene filtering, scene.npz + per-object files) followed by eval_grasps on
+    the generated directory (inference_grasps.npz -> grasp_evaluation.json)."""
+    import json
+    from mj_grasp_sim_b200 import scenes
+    from mj_grasp_sim_b200.mgs.cli import eval_grasps, gen_scene
+    from mj_grasp_sim_b200.mgs.obj.selector import get_object
+    ids = ["hull:20:24", "hull:21:24", "hull:22:24"]
+    # object-frame grasps per object (harness-made: antipodal frames on each hull, wide-open fingers)
+    grasps = {}
+    for k, oid in enumerate(ids):
+        v, t = get_object(oid).mesh()
+        H, w = scenes.antipodal_candidates(v, t, 96, 30 + k)
+        grasps[oid] = (H, scenes.panda_width_to_joints(w))
+    scene = None
+    for seed in (5, 6, 7, 8):  # unstable scenes are refused with ValueError, as in the reference (gen_scene.py:42-43)
+        try:
+            scene = gen_scene.gen_stable_scene("PandaGripper", ids, seed=seed)
+            break
+        except ValueError:
+            continue
+    assert scene is not None
+    assert set(scene) == {"gripper", "objects", "env_state"}
+    valid, invalid = gen_scene.filter_grasps("PandaGripper", scene, grasps=grasps, only_collision_free=True, save_collision_grasps=True,
+                                             enough_collision_free=8, rng=np.random.default_rng(0))
+    assert valid and all(g["pose"].shape[1:] == (4, 4) and len(g["pose"]) == len(g["joints"]) for g in valid)
+    assert sum(len(g["pose"]) for g in valid) + sum(len(g["pose"]) for g in invalid) == 3 * 96
+    with pytest.raises(ValueError):
+        gen_scene.filter_grasps("PandaGripper", scene, grasps=grasps, enough_collision_free=10 ** 6)
+    # eval_grasps on the same scene: the grasps it receives are in the CONTACT frame; it applies inv(b2c) itself
+    d = tmp_path / "PandaGripper" / "scene0"
+    d.mkdir(parents=True)
+    np.savez(d / "scene.npz", scene_definition=scene)
+    allp = np.concatenate([g["pose"] for g in valid])[:32]
+    allj = np.concatenate([g["joints"] for g in valid])[:32]
+    np.savez(d / "inference_grasps.npz", pose=allp, joints=allj)
+    res = eval_grasps.run("PandaGripper", 0, input_dir=str(tmp_path))
+    assert res["scene_id"] == "scene0" and res["num_objects"] == 3 and 0.0 <= res["success_rate"] <= 1.0
+    assert json.load(open(d / "grasp_evaluation.json")) == res
