@@ -108,6 +108,19 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
   for (int a = 0; a < nv; a++)
     for (int c = 0; c <= a; c++) tri.push_back((a << 8) | c);
   m.tri_ab = put<int>(b, tri.data(), tri.size());
+  {
+    // ancestry masks: which dofs move a point fixed to body i (lane-per-dof Jacobian assembly)
+    const int words = (nv + 31) / 32 > 0 ? (nv + 31) / 32 : 1;
+    std::vector<unsigned int> mask((size_t)nb * words, 0u);
+    for (int i = 1; i < nb; i++) {
+      int bb = i;
+      while (bb > 0 && d->body_dofnum[bb] == 0) bb = d->body_parentid[bb];
+      if (bb == 0) continue;
+      for (int k = d->body_dofadr[bb] + d->body_dofnum[bb] - 1; k >= 0; k = d->dof_parentid[k]) mask[(size_t)i * words + (k >> 5)] |= 1u << (k & 31);
+    }
+    m.dofmask_words = words;
+    m.body_dofmask = put<unsigned int>(b, mask.data(), mask.size());
+  }
   PR_(eq_data, 11 * d->neq); PR_(eq_solref, 2 * d->neq); PR_(eq_solimp, 5 * d->neq);
   PR_(mocap_pos0, 3 * d->nmocap); PR_(mocap_quat0, 4 * d->nmocap);
 #undef PI_
