@@ -54,7 +54,7 @@ MGS_DEVN Sup geom_support(const real *Rm, const real *gp, int cg, int type, int 
 #pragma unroll 1
     for (int guard = 0; guard < nvert; guard++) {
       int na = LDG(MD.hull_nbradr + vadr + cur), nn = LDG(MD.hull_nbrnum + vadr + cur), nxt = cur;
-#pragma unroll 1
+      MGS_UNROLL_INNER  // the neighbour -> vertex loads of several neighbours overlap (they were one dependent chain each)
       for (int k = 0; k < nn; k++) {
         int v = LDG(MD.hull_nbr + na + k);
         real t = LDG(V + 3 * v) * dl[0] + LDG(V + 3 * v + 1) * dl[1] + LDG(V + 3 * v + 2) * dl[2];
@@ -406,92 +406,117 @@ MGS_DEVN void collide_pair(Env &e, int pair, PairContacts &out) {
   // so no lane leaves before them (the clipping itself stays per lane).
   const int poly = hit && (g1.type == GEOM_BOX || g1.type == GEOM_MESH) && (g2.type == GEOM_BOX || g2.type == GEOM_MESH);
   real a1 = 0, a2 = 0, nn[3] = {-n[0], -n[1], -n[2]};
-  int f1 = 0, f2 = 0, incf = 0;
+  int f1 = 0, f2 = 0;
   best_face_lanes(poly, g1, n, &f1, &a1);
   best_face_lanes(poly, g2, nn, &f2, &a2);
   const int clip = poly && fmax(a1, a2) >= MGS_FACE_ALIGN_MIN;
   const int ref_is_1 = a1 >= a2;
   const GeomRef &rg = ref_is_1 ? g1 : g2;
   const GeomRef &ig = ref_is_1 ? g2 : g1;
-  real ref[MGS_MAXPOLY][3], nref[3] = {0, 0, 0}, mn[3], al;
-  int nr = 0;
-  if (clip) nr = face_polygon(rg, ref_is_1 ? f1 : f2, ref, nref);
-  mn[0] = -nref[0]; mn[1] = -nref[1]; mn[2] = -nref[2];
-  best_face_lanes(clip, ig, mn, &incf, &al);
-  if (!hit) return;
-  if (clip) {
-    {
-      real ninc[3], A[MGS_MAXCLIP][3], B[MGS_MAXCLIP][3], dist[MGS_MAXCLIP];
+  // Clipping works on polygons with run-time indices; they live in per-lane slots of shared memory (the part of the
+  // solver overlay that is free during collision), not in local memory (ncu r1_k: the local-memory polygon copies were
+  // 4.7 % of all stall samples).  Lanes that clip take slots by rank; if there are more than slots, in rounds.
+  int nclipping, rank = wrank(clip, &nclipping), done = 0;
+  #pragma unroll 1
+  for (int base = 0; base < nclipping; base += LY.nclip) {
+    const int mine = clip && rank >= base && rank < base + LY.nclip;
+    real *slot = EF(clip_off) + (mine ? rank - base : 0) * MGS_CLIP_STRIDE;
+    real (*ref)[3] = reinterpret_cast<real (*)[3]>(slot);
+    real (*A)[3] = reinterpret_cast<real (*)[3]>(slot + 3 * MGS_MAXPOLY);
+    real (*B)[3] = reinterpret_cast<real (*)[3]>(slot + 3 * MGS_MAXPOLY + 3 * MGS_MAXCLIP);
+    real *dist = slot + 3 * MGS_MAXPOLY + 6 * MGS_MAXCLIP;
+    real nref[3] = {0, 0, 0}, mn[3], al;
+    int nr = 0, incf = 0;
+    if (mine) nr = face_polygon(rg, ref_is_1 ? f1 : f2, ref, nref);
+    mn[0] = -nref[0]; mn[1] = -nref[1]; mn[2] = -nref[2];
+    best_face_lanes(mine, ig, mn, &incf, &al);
+    if (mine) {
+      real ninc[3];
       int na = face_polygon(ig, incf, A, ninc);
       #pragma unroll 1
       for (int ed = 0; ed < nr && na > 0; ed++) {
-        real edge[3], sn[3];
+        real edge[3], sn[3], r0[3];
         int e2 = (ed + 1 == nr) ? 0 : ed + 1;
-        sub3(edge, ref[e2], ref[ed]);
+        copy3(r0, ref[ed]);
+        sub3(edge, ref[e2], r0);
         cross3(sn, edge, nref);
         int nb2 = 0;
+        real P[3], t0[3];
+        copy3(P, A[0]);
+        sub3(t0, P, r0);
+        real dp = dot3(t0, sn);
         #pragma unroll 1
         for (int i = 0; i < na; i++) {
-          const real *P = A[i], *Q = A[(i + 1 == na) ? 0 : i + 1];
-          real t0[3], t1[3];
-          sub3(t0, P, ref[ed]); sub3(t1, Q, ref[ed]);
-          real dp = dot3(t0, sn), dq = dot3(t1, sn);
+          real Q[3], t1[3];
+          copy3(Q, A[(i + 1 == na) ? 0 : i + 1]);
+          sub3(t1, Q, r0);
+          const real dq = dot3(t1, sn);
           if (dp <= 0 && nb2 < MGS_MAXCLIP) { copy3(B[nb2], P); nb2++; }
           if ((dp <= 0) != (dq <= 0) && nb2 < MGS_MAXCLIP) {
             real t = dp / (dp - dq);
             for (int k = 0; k < 3; k++) B[nb2][k] = P[k] + t * (Q[k] - P[k]);
             nb2++;
           }
+          copy3(P, Q);
+          dp = dq;
         }
         na = nb2;
-        #pragma unroll 1
-        for (int i = 0; i < na; i++) copy3(A[i], B[i]);
+        real (*T)[3] = A; A = B; B = T;  // ping-pong instead of copying back
       }
       int np = 0;
       #pragma unroll 1
       for (int i = 0; i < na; i++) {
-        real t[3];
-        sub3(t, A[i], ref[0]);
+        real t[3], a[3];
+        copy3(a, A[i]);
+        sub3(t, a, ref[0]);
         real dd = dot3(t, nref);
-        if (dd < 0) { copy3(A[np], A[i]); dist[np] = dd; np++; }
+        if (dd < 0) { copy3(A[np], a); dist[np] = dd; np++; }
       }
       if (np > 0) {
-        int sel[4], ns = 0, i0 = 0;
+        int i0 = 0, i1 = -1, i2 = -1, i3 = -1;
         #pragma unroll 1
         for (int i = 1; i < np; i++) if (dist[i] < dist[i0]) i0 = i;
-        sel[ns++] = i0;
         if (np > 1) {
-          int i1 = -1; real bd = -1;
+          real bd = -1, a0[3];
+          copy3(a0, A[i0]);
           #pragma unroll 1
-          for (int i = 0; i < np; i++) { real t[3]; sub3(t, A[i], A[i0]); real d2 = dot3(t, t); if (i != i0 && d2 > bd) { bd = d2; i1 = i; } }
+          for (int i = 0; i < np; i++) { real t[3]; sub3(t, A[i], a0); real d2 = dot3(t, t); if (i != i0 && d2 > bd) { bd = d2; i1 = i; } }
           if (i1 >= 0 && bd > R_(1e-12)) {
-            sel[ns++] = i1;
-            real e01[3]; sub3(e01, A[i1], A[i0]);
-            int i2 = -1, i3 = -1; real mx = R_(1e-12), mnv = R_(-1e-12);
+            real e01[3]; sub3(e01, A[i1], a0);
+            real mx = R_(1e-12), mnv = R_(-1e-12);
             #pragma unroll 1
             for (int i = 0; i < np; i++) {
               if (i == i0 || i == i1) continue;
-              real t[3], c[3]; sub3(t, A[i], A[i0]); cross3(c, e01, t);
+              real t[3], c[3]; sub3(t, A[i], a0); cross3(c, e01, t);
               real sa = dot3(c, nref);
               if (sa > mx) { mx = sa; i2 = i; }
               if (sa < mnv) { mnv = sa; i3 = i; }
             }
-            if (i2 >= 0) sel[ns++] = i2;
-            if (i3 >= 0) sel[ns++] = i3;
-          }
+          } else i1 = -1;
         }
         if (ref_is_1) copy3(out.normal, nref); else scl3(out.normal, nref, -1);
-        #pragma unroll 1
-        for (int k = 0; k < ns; k++) {
-          copy3(out.pos[k], A[sel[k]]);
-          addscl3(out.pos[k], nref, R_(-0.5) * dist[sel[k]]);
-          out.dist[k] = dist[sel[k]];
+        int ns = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int s = k == 0 ? i0 : (k == 1 ? i1 : (k == 2 ? i2 : i3));
+          if (s >= 0) {
+            const real ds = dist[s];
+            real a[3];
+            copy3(a, A[s]);
+            addscl3(a, nref, R_(-0.5) * ds);
+            // out.pos / out.dist are indexed with a run-time count: write through the unrolled slot index
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (q == ns) { copy3(out.pos[q], a); out.dist[q] = ds; }
+            ns++;
+          }
         }
         out.n = ns;
-        return;
+        done = 1;
       }
     }
+    WSYNC();
   }
+  if (!hit || done) return;
   out.n = 1;
   copy3(out.normal, n);
   copy3(out.pos[0], pos);

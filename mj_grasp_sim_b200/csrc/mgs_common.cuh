@@ -133,8 +133,12 @@ struct Layout {
   MGS_LAYOUT_FIELDS(X)
 #undef X
   int total, ncon_max, nefc_max, ncache;
+  int clip_off, nclip;  // face-clipping scratch: `nclip` slots of MGS_CLIP_STRIDE reals in the part of the SOLVER overlay that lies beyond the
+                        // TRANSIENT arrays (free during collision: the constraint rows are built afterwards)
 };
 
+// one clipping slot: reference polygon (8 x 3), two ping-pong polygons (12 x 3 each), depths (12); odd stride = no bank conflicts
+#define MGS_CLIP_STRIDE 109
 #define MGS_MPR_CACHE_MAX 128  // geom pairs (the first ones of the list: the object pairs) whose last MPR result is remembered:
                                // 4 words per pair - portal vertex pairs or separating axis (words 0-2), hill-climb start vertices (3)
 static inline void layout_compute(Layout *L, int nq, int nv, int nu, int nbody, int njnt, int nmocap, int ntendon, int ncgeom,
@@ -151,6 +155,10 @@ static inline void layout_compute(Layout *L, int nq, int nv, int nu, int nbody, 
   MGS_LAYOUT_SOLVER(X)
 #undef X
   L->total = off > end_t ? off : end_t;
+  L->clip_off = end_t;
+  L->nclip = (L->total - end_t) / MGS_CLIP_STRIDE;
+  if (L->nclip < 1) { L->nclip = 1; L->total = end_t + MGS_CLIP_STRIDE; }
+  if (L->nclip > 32) L->nclip = 32;
   L->ncon_max = ncon_max;
   L->nefc_max = nefc_max;
 }

@@ -22,6 +22,7 @@ MGS_DEV unsigned wballot(int p) { return p ? 1u : 0u; }
 MGS_DEV real wbcast(real x, int src) { (void)src; return x; }
 MGS_DEV int wbcasti(int x, int src) { (void)src; return x; }
 MGS_DEV void wargmax(real &v, int &idx) { (void)v; (void)idx; }
+MGS_DEV int wrank(int p, int *total) { *total = p ? 1 : 0; return 0; }
 #else
 MGS_DEV real wsum(real x) {
 #pragma unroll
@@ -37,6 +38,12 @@ MGS_DEV int wany(int p) { return __any_sync(0xffffffffu, p); }
 MGS_DEV unsigned wballot(int p) { return __ballot_sync(0xffffffffu, p); }
 MGS_DEV real wbcast(real x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 MGS_DEV int wbcasti(int x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+// number of lanes below this one with `p` set (and the warp total)
+MGS_DEV int wrank(int p, int *total) {
+  const unsigned m = __ballot_sync(0xffffffffu, p);
+  *total = __popc(m);
+  return __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+}
 // warp arg-max; ties go to the smaller index (= the first maximum of a sequential scan)
 MGS_DEV void wargmax(real &v, int &idx) {
 #pragma unroll
