@@ -149,6 +149,13 @@ def run_ours(args, rank, world, local_rank):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    # dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch of each workload, captured once with ncu
+    # (profiles/traffic_r1.json, written by tools/ncu_traffic.py from the ncu CSV)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+    except Exception:
+        pass
 
     def barrier():
         if dist is not None:
@@ -233,7 +240,10 @@ def run_ours(args, rank, world, local_rank):
                            "d2h_bytes_per_step": int(N_CAND * 5), "grasps_per_s": world * N_CAND * args.steps / e2e_s},
                    "gpu_launches": int(launches),
                    "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                "traffic": None, "kernel": "mgs_rollout_kernel", "bytes_per_env_step": bs,
+                                "traffic": traffic.get(key, {}).get("gbs"), "traffic_bytes_per_launch": traffic.get(key, {}).get("bytes_per_launch"),
+                                "algorithmic_bytes_per_launch": bs * per_rank_steps / args.steps,
+                                "traffic_source": traffic.get(key, {}).get("source"),
+                                "kernel": "mgs_rollout_kernel", "bytes_per_env_step": bs,
                                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
                                 "note": "state stays in shared memory for the whole rollout; the kernel is issue/latency bound, not HBM bound"},
                    "clocks": clk.summary(), "wall_s": t_wall}

@@ -139,7 +139,12 @@ MGS_DEV int reach_tolerance(const SupPt &p1, const SupPt &p2, const SupPt &p3, c
   return mn <= tol;
 }
 
-MGS_DEVN void closest_on_triangle(const real *a, const real *b, const real *c, real *out) {
+#ifdef MGS_INLINE_COT
+MGS_DEV
+#else
+MGS_DEVN
+#endif
+void closest_on_triangle(const real *a, const real *b, const real *c, real *out) {
   real ab[3], ac[3], ap[3] = {-a[0], -a[1], -a[2]};
   sub3(ab, b, a); sub3(ac, c, a);
   real d1 = dot3(ab, ap), d2 = dot3(ac, ap);
@@ -376,27 +381,21 @@ MGS_DEVN int face_polygon(const GeomRef &g, int f, real (*poly)[3], real *nw) {
 
 struct PairContacts { int n; real normal[3], pos[4][3], dist[4]; };
 
-// narrowphase for candidate pair `pair` (this lane's pair; pair < 0: lane idle); fills up to 4 contacts.
-// Called by all lanes of the warp together: the MPR stage inside is warp-converged.
+// narrowphase for candidate pair `pair`, which already passed the bounding-sphere test (pair < 0: lane idle); fills up
+// to 4 contacts.  Called by all lanes of the warp together: the MPR stage inside is warp-converged.
 MGS_DEVN void collide_pair(Env &e, int pair, PairContacts &out) {
   out.n = 0;
-  int active = 0, c1 = 0, c2 = 0;
-  if (pair >= 0) {
-    c1 = LDG(MD.pair_geom1 + pair); c2 = LDG(MD.pair_geom2 + pair);
-    real dc[3];
-    sub3(dc, EF(gxpos) + 3 * c1, EF(gxpos) + 3 * c2);
-    real rr = LDG(MD.cgeom_rbound + c1) + LDG(MD.cgeom_rbound + c2) + LDG(MD.pair_margin + pair);
-    active = dot3(dc, dc) <= rr * rr;
-  }
+  const int active = pair >= 0;
+  int c1 = 0, c2 = 0;
+  if (active) { c1 = LDG(MD.pair_geom1 + pair); c2 = LDG(MD.pair_geom2 + pair); }
   GeomRef g1, g2;
   geomref_init(g1, e, c1);
   geomref_init(g2, e, c2);
   real depth = 0, n[3], pos[3];
-  int *cache = (pair >= 0 && pair < LY.ncache) ? IARR(EF(mpr_cache)) + 4 * pair : (int *)0;
+  int *cache = (active && pair < LY.ncache) ? IARR(EF(mpr_cache)) + 4 * pair : (int *)0;
 #ifdef MGS_NO_MPR_WARMSTART
   cache = (int *)0;
 #endif
-  if (cache && !active) cache[2] = -1;
   // hull supports resume their hill climb from the vertices this pair ended on at the previous step (word 3:
   // two 16-bit vertex ids, 0 after reset); poses change by micrometres per step, so the climb is 0-1 moves
   if (cache && active) { g1.cur = cache[3] & 0xffff; g2.cur = (cache[3] >> 16) & 0xffff; }
@@ -532,24 +531,59 @@ MGS_DEV void make_frame(real *frame) {
   cross3(z, x, y);
 }
 
+// store this lane's contacts of pair p at the next free slots (pair order = deterministic contact order)
+MGS_DEV void emit_contacts(Env &e, const PairContacts &pc, int p, int &base) {
+  int total, off = wscan_excl(pc.n, &total);
+  #pragma unroll 1
+  for (int k = 0; k < pc.n; k++) {
+    int c = base + off + k;
+    if (c >= LY.ncon_max) break;
+    copy3(EF(con_pos) + 3 * c, pc.pos[k]);
+    copy3(EF(con_normal) + 3 * c, pc.normal);
+    EF(con_dist)[c] = pc.dist[k];
+    IARR(EF(con_pair))[c] = p;
+  }
+  base += total;
+}
+
+// Broadphase + narrowphase.  Pass 1 runs the bounding-sphere test one pair per lane and COMPACTS the survivors
+// (in pair order) into a 32-entry buffer; whenever the buffer cannot take the next group it is flushed through the
+// narrowphase.  The MPR state machine therefore runs once per 32 surviving pairs with all their lanes busy, instead
+// of once per 32 listed pairs with the few survivors of that group (Panda 63 pairs, Robotiq 95, LEAP 1764).
 MGS_DEVN void collision_w(Env &e) {
-  int base = 0;
+  int base = 0, nbuf = 0;
+  int *buf = IARR(EF(nsS));
   #pragma unroll 1
   for (int p0 = 0; p0 < MD.npair; p0 += LANES) {
-    int p = p0 + MGS_LANE;
-    PairContacts pc;
-    collide_pair(e, p < MD.npair ? p : -1, pc);
-    int total, off = wscan_excl(pc.n, &total);
-    #pragma unroll 1
-    for (int k = 0; k < pc.n; k++) {
-      int c = base + off + k;
-      if (c >= LY.ncon_max) break;
-      copy3(EF(con_pos) + 3 * c, pc.pos[k]);
-      copy3(EF(con_normal) + 3 * c, pc.normal);
-      EF(con_dist)[c] = pc.dist[k];
-      IARR(EF(con_pair))[c] = p;
+    const int p = p0 + MGS_LANE;
+    int active = 0;
+    if (p < MD.npair) {
+      const int c1 = LDG(MD.pair_geom1 + p), c2 = LDG(MD.pair_geom2 + p);
+      real dc[3];
+      sub3(dc, EF(gxpos) + 3 * c1, EF(gxpos) + 3 * c2);
+      const real rr = LDG(MD.cgeom_rbound + c1) + LDG(MD.cgeom_rbound + c2) + LDG(MD.pair_margin + p);
+      active = dot3(dc, dc) <= rr * rr;
+      if (!active && p < LY.ncache) IARR(EF(mpr_cache))[4 * p + 2] = -1;  // a culled pair forgets its portal / axis
     }
-    base += total;
+    int k, rank = wrank(active, &k);
+    if (k == 0) continue;
+    if (nbuf + k > LANES) {
+      PairContacts pc;
+      const int q = MGS_LANE < nbuf ? buf[MGS_LANE] : -1;
+      collide_pair(e, q, pc);
+      emit_contacts(e, pc, q, base);
+      nbuf = 0;
+      WSYNC();
+    }
+    if (active) buf[nbuf + rank] = p;
+    nbuf += k;
+    WSYNC();
+  }
+  if (nbuf > 0) {
+    PairContacts pc;
+    const int q = MGS_LANE < nbuf ? buf[MGS_LANE] : -1;
+    collide_pair(e, q, pc);
+    emit_contacts(e, pc, q, base);
   }
   if (base > LY.ncon_max) { if (MGS_LANE == 0) EH.overflow += base - LY.ncon_max; base = LY.ncon_max; }
   EH.ncon = base;

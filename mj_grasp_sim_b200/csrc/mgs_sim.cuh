@@ -199,24 +199,28 @@ MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
     const int i = MGS_LANE;
     int tadr = 0, tnum = n;
     if (blocked && i < n) { tadr = LDG(MD.dof_treeadr + i); tnum = LDG(MD.dof_treenum + i); }
+    WSYNC();
     #pragma unroll 1
     for (int t = 0; t < nsteps; t++) {
       const int j = tadr + t;
       const int live = (i < n) && (t < tnum);
-      WSYNC();
-      real d = 1;
-      if (live) { d = A[j * n + j]; d = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL); }
+      // the pivot A[j][j] is final (previous trailing update + WSYNC); every lane of the block reads it, the pivot
+      // lane writes its square root back only after the column has been scaled (second phase)
+      real d = 1, lij = 0;
+      if (live) {
+        d = A[j * n + j];
+        d = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL);
+        if (i > j) { lij = A[i * n + j] * (R_(1.0) / d); A[i * n + j] = lij; }
+      }
       WSYNC();
       if (live) {
         if (i == j) A[j * n + j] = d;
-        else if (i > j) A[i * n + j] *= R_(1.0) / d;
+        else if (i > j) {
+          MGS_UNROLL_INNER
+          for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+        }
       }
       WSYNC();
-      if (live && i > j) {
-        const real lij = A[i * n + j];
-        MGS_UNROLL_INNER
-        for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
-      }
     }
     WSYNC();
     return;
@@ -257,30 +261,31 @@ MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
     const int i = MGS_LANE;
     int tadr = 0, tnum = n;
     if (blocked && i < n) { tadr = LDG(MD.dof_treeadr + i); tnum = LDG(MD.dof_treenum + i); }
+    // the right-hand side lives in registers (lane i owns x[i]); x[k] travels by shuffle: no shared-memory
+    // round trip and no warp barrier per column
+    WSYNC();
+    real xi = (i < n) ? x[i] : R_(0.0);
     #pragma unroll 1
     for (int t = 0; t < nsteps; t++) {
       const int k = tadr + t, live = (i < n) && (t < tnum);
-      WSYNC();
-      real xk = 0;
-      if (live) xk = x[k] / L[k * n + k];
-      WSYNC();
+      const real xs = __shfl_sync(0xffffffffu, xi, live ? k : i);
       if (live) {
-        if (i == k) x[k] = xk;
-        else if (i > k) x[i] -= L[i * n + k] * xk;
+        const real xk = xs / L[k * n + k];
+        if (i == k) xi = xk;
+        else if (i > k) xi -= L[i * n + k] * xk;
       }
     }
     #pragma unroll 1
     for (int t = nsteps - 1; t >= 0; t--) {
       const int k = tadr + t, live = (i < n) && (t < tnum);
-      WSYNC();
-      real xk = 0;
-      if (live) xk = x[k] / L[k * n + k];
-      WSYNC();
+      const real xs = __shfl_sync(0xffffffffu, xi, live ? k : i);
       if (live) {
-        if (i == k) x[k] = xk;
-        else if (i < k) x[i] -= L[k * n + i] * xk;
+        const real xk = xs / L[k * n + k];
+        if (i == k) xi = xk;
+        else if (i < k) xi -= L[k * n + i] * xk;
       }
     }
+    if (i < n) x[i] = xi;
     WSYNC();
     return;
   }

@@ -111,6 +111,24 @@ class ClutterTableEnv(MjSimulation):
         sd = int(np.random.randint(1 << 30)) if seed is None else seed
         self._record = scenes.gen_clutter(self.model, info, self._step, sd)
 
+    def gen_clutter_batch(self, seeds, require_stable: bool = True):
+        """Beyond the reference (which generates one scene per process, gen_scene.py:28-45): generate len(seeds) scenes
+        of this gripper/object set in one batch of launches.  Returns a list of `to_dict()`-style scene dictionaries
+        (only the stable ones when `require_stable`)."""
+        info = dict(base_qposadr=self.gripper.get_freejoint_idxs(self)[0],
+                    object_qposadr=[int(self.model.jnt_qposadr[self.model.names["joint"][f"{n}:joint"]]) for n in self.object_names])
+        step = lambda r, k: self.sim.step(r.astype(self.sim.real), k).astype(np.float64)
+        recs = scenes.gen_clutter_batch(self.model, info, step, seeds)
+        ok, after = scenes.scenes_stable(self.model, info, step, recs.copy())
+        out, keep_rec, keep_time = [], self._record, self._time
+        for k in range(len(recs)):
+            if require_stable and not ok[k]:
+                continue
+            self._record, self._time = recs[k], 11.7
+            out.append(self.to_dict())
+        self._record, self._time = keep_rec, keep_time
+        return out
+
     def settle(self):
         self._record = self._step(self._record, 10000)
 

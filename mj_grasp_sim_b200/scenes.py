@@ -357,3 +357,47 @@ def clutter_candidates(model, info, rec, n: int, seed: int):
         y = np.cross(z, x)
         H[i, :3, 0], H[i, :3, 1], H[i, :3, 2], H[i, :3, 3], H[i, 3, 3] = x, y, z, c, 1.0
     return H, width
+
+
+def gen_clutter_batch(model, info, step_fn, seeds, park_gripper=(0.0, 0.0, 1.5)):
+    """Many clutter scenes of ONE model at once: the same drop / settle schedule as
+    `gen_clutter`, every scene with its own seed, all scenes advanced by the same batched launches.
+    `step_fn(records[n, stride], nstep) -> records`.  Scene k equals gen_clutter(..., seeds[k]) exactly: an
+    environment's trajectory does not depend on what else is in the batch."""
+    seeds = list(seeds)
+    n, nq, nv = len(seeds), model.nq, model.nv
+    rec = np.tile(record_from_model(model), (n, 1))
+    b = info["base_qposadr"]
+    mo = nq + 2 * nv + model.nu
+    rec[:, b:b + 3] = park_gripper
+    rec[:, mo:mo + 3] = park_gripper
+    quats = np.zeros((n, 4))
+    for k, sd in enumerate(seeds):
+        rng = np.random.default_rng(4000 + sd)
+        q = R.random(random_state=np.random.RandomState(int(rng.integers(1 << 31)))).as_quat()
+        quats[k] = [q[3], q[0], q[1], q[2]]
+
+    def advance(r, times):
+        for _ in range(times):
+            r[:, nq:nq + nv] = np.clip(r[:, nq:nq + nv], -50.0, 50.0)
+            r = step_fn(r, 100)
+        return r
+
+    for a in info["object_qposadr"]:
+        rec[:, a:a + 3] = [0.0, 0.0, 0.8]
+        rec[:, a + 3:a + 7] = quats
+        rec[:, nq:nq + nv] = 0.0
+        rec = advance(rec, 9)
+    return advance(rec, 90)
+
+
+def scenes_stable(model, info, step_fn, rec):
+    """ClutterTableEnv.is_stable (clutter_table.py:160-195) for a batch of scene records: summed |displacement| of every
+    object over 10 x 100 steps below 5 mm.  Returns (stable bool[n], records after the 1000 steps)."""
+    adr = info["object_qposadr"]
+    stats = np.zeros((len(rec), len(adr)))
+    for _ in range(10):
+        start = np.stack([rec[:, a:a + 3] for a in adr], axis=1)
+        rec = step_fn(rec, 100)
+        stats += np.abs(np.stack([rec[:, a:a + 3] for a in adr], axis=1) - start).sum(axis=2)
+    return (stats.max(axis=1) < 5e-3) if len(adr) else np.ones(len(rec), dtype=bool), rec

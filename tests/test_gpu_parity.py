@@ -258,13 +258,9 @@ def test_gen_scene_and_eval_grasps_clis(libs, tmp_path):
     from mj_grasp_sim_b200 import scenes
     from mj_grasp_sim_b200.mgs.cli import eval_grasps, gen_scene
     from mj_grasp_sim_b200.mgs.obj.selector import get_object
+    from mj_grasp_sim_b200.mgs.env.clutter_table import ClutterTableEnv
+    from mj_grasp_sim_b200.mgs.util.geo.transforms import SE3Pose
     ids = ["hull:20:24", "hull:21:24", "hull:22:24"]
-    # object-frame grasps per object (harness-made: antipodal frames on each hull, wide-open fingers)
-    grasps = {}
-    for k, oid in enumerate(ids):
-        v, t = get_object(oid).mesh()
-        H, w = scenes.antipodal_candidates(v, t, 96, 30 + k)
-        grasps[oid] = (H, scenes.panda_width_to_joints(w))
     scene = None
     for seed in (5, 6, 7, 8):  # unstable scenes are refused with ValueError, as in the reference (gen_scene.py:42-43)
         try:
@@ -273,10 +269,18 @@ def test_gen_scene_and_eval_grasps_clis(libs, tmp_path):
         except ValueError:
             continue
     assert scene is not None
+    # per-object grasps in the OBJECT frame (what stable_grasps.npz holds): harness-made top-down frames around each
+    # settled object, pulled back through the object's pose so that filter_grasps' o2w @ grasp restores them
+    env0 = ClutterTableEnv.from_dict(scene)
+    grasps = {}
+    for k, (name, oid) in enumerate(zip(env0.object_names, env0.object_ids)):
+        a = int(env0.model.jnt_qposadr[env0.model.names["joint"][f"{name}:joint"]])
+        H, w = scenes.clutter_candidates(env0.model, dict(object_qposadr=[a]), env0._record, 96, 30 + k)
+        o2w = env0.get_obj_pose(name).to_mat().astype(np.float64).reshape(4, 4)
+        grasps[oid] = (np.einsum("ij,njk->nik", np.linalg.inv(o2w), H), scenes.panda_width_to_joints(w))
     assert set(scene) == {"gripper", "objects", "env_state"}
-    # (objects lie flat on the table, so only the few frames that approach from above clear it)
     valid, invalid = gen_scene.filter_grasps("PandaGripper", scene, grasps=grasps, only_collision_free=True, save_collision_grasps=True,
-                                             enough_collision_free=2, rng=np.random.default_rng(0))
+                                             enough_collision_free=8, rng=np.random.default_rng(0))
     assert valid and all(g["pose"].shape[1:] == (4, 4) and len(g["pose"]) == len(g["joints"]) for g in valid)
     # per object with at least one valid grasp: valid + collision grasps = its 96 candidates (objects without any valid
     # grasp are not listed at all - the reference loops over the objects of the RESULT, gen_scene.py:133-155)
@@ -295,3 +299,21 @@ def test_gen_scene_and_eval_grasps_clis(libs, tmp_path):
     res = eval_grasps.run("PandaGripper", 0, input_dir=str(tmp_path))
     assert res["scene_id"] == "scene0" and res["num_objects"] == 3 and 0.0 <= res["success_rate"] <= 1.0
     assert json.load(open(d / "grasp_evaluation.json")) == res
+
+
+def test_batched_scene_generation_matches_single(libs):
+    """many clutter scenes per launch.  Scene k of the batch is bit-identical to generating it alone."""
+    from mj_grasp_sim_b200.mgs.env.clutter_table import ClutterTableEnv
+    from mj_grasp_sim_b200.mgs.gripper.selector import get_gripper
+    from mj_grasp_sim_b200.mgs.obj.selector import get_objects
+    env = ClutterTableEnv(get_gripper("PandaGripper"), get_objects(["hull:40:16", "hull:41:16"]))
+    env.set_gripper_pose([0.0, 0.0, 1.5])
+    seeds = [11, 12, 13, 14, 15, 16]
+    batch = env.gen_clutter_batch(seeds, require_stable=False)
+    assert len(batch) == len(seeds)
+    env.gen_clutter(seed=13)
+    single = env.get_state()
+    got = batch[2]["env_state"]["state"]
+    assert np.array_equal(got[1:], single[1:])  # everything but the time stamp
+    stable = env.gen_clutter_batch(seeds)
+    assert 1 <= len(stable) <= len(seeds)

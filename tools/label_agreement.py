@@ -9,9 +9,12 @@ from mj_grasp_sim_b200.lib import BatchSim, MgsRolloutCfg, SO_PATH_F64
 from oracle.oracle import RolloutCfg, batch
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+only = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None  # e.g. "shadow,leap"
 rows = []
 for gripper, kind, seeds in (("panda", "cube", [0]), ("panda", "hull", [0, 1]), ("vx300", "hull", [0, 1]), ("robotiq2f85", "hull", [0, 1]),
                              ("allegro", "hull", [0]), ("leap", "hull", [0]), ("shadow", "hull", [0])):
+    if only is not None and gripper not in only:
+        continue
     for seed in seeds:
         m, info, pose7, joints = scenes.workload(gripper, kind, seed, n)
         rep = scenes.GRIPPERS[gripper]["repose"]
@@ -36,4 +39,4 @@ for gripper, kind, seeds in (("panda", "cube", [0]), ("panda", "hull", [0, 1]), 
             G.close()
         rows.append(row)
         print(json.dumps(row), flush=True)
-json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "label_agreement.json"), "w"), indent=1)
+json.dump(rows, open(os.path.join(ROOT, "gpurun_out", os.environ.get("MGS_LABELS_OUT", "label_agreement.json")), "w"), indent=1)
