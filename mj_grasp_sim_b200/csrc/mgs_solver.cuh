@@ -536,20 +536,23 @@ MGS_DEVN void solve_newton_w(Env &e) {
   const int nv = MD.nv;
   const real scale = R_(1.0) / (MD.meaninertia * (nv > 1 ? nv : 1));
   EH.niter = 0;
-  // warm start: cheaper of qacc_warmstart and qacc_smooth
-  eval_point_w(e, EF(qacc_ws));
-  real cw = wsum(constraint_update_w(e) + gauss_cost_w(e, EF(qacc_ws)));
-  WSYNC();
+  // warm start: cheaper of qacc_warmstart and qacc_smooth.  The warm start is evaluated LAST: it wins on almost every
+  // step, and then the row states / forces / jar / Ma left behind are already those of the starting point.
   eval_point_w(e, EF(qacc_smooth));
-  real cs = wsum(constraint_update_w(e) + gauss_cost_w(e, EF(qacc_smooth)));
+  const real cs = wsum(constraint_update_w(e) + gauss_cost_w(e, EF(qacc_smooth)));
   WSYNC();
-  const int use_ws = cw < cs;
+  eval_point_w(e, EF(qacc_ws));
+  real cost = wsum(constraint_update_w(e) + gauss_cost_w(e, EF(qacc_ws)));
+  WSYNC();
+  const int use_ws = cost < cs;
   #pragma unroll 1
   PFOR(d, nv) EF(qacc)[d] = use_ws ? EF(qacc_ws)[d] : EF(qacc_smooth)[d];
   WSYNC();
-  eval_point_w(e, EF(qacc));
-  real cost = wsum(constraint_update_w(e) + gauss_cost_w(e, EF(qacc)));
-  WSYNC();
+  if (!use_ws) {
+    eval_point_w(e, EF(qacc));
+    cost = wsum(constraint_update_w(e) + gauss_cost_w(e, EF(qacc)));
+    WSYNC();
+  }
   #pragma unroll 1
   for (int iter = 0; iter < MD.iterations; iter++) {
     real gn = 0;
@@ -563,7 +566,9 @@ MGS_DEVN void solve_newton_w(Env &e) {
       gn += t * t;
     }
     gn = wsum(gn);
-    // fp32: the gradient cannot be resolved below ~eps * |force terms|; floor the tolerance accordingly
+    // fp32: the gradient cannot be resolved below ~eps * |force terms|; floor the tolerance accordingly.  (A per-step
+    // rounding-noise estimate of the gradient, K * eps * |terms| with K = 2..8, was tried as a further floor: it never
+    // binds - the warm starts that iterate are far above the noise - so it is not kept.)
     real tol_eff = fmax(MD.tolerance, R_(20.0) * (real)REAL_EPS * scale * fabs(cost));
     // (MuJoCo tests the gradient only after an iteration; a warm start that already meets the tolerance skips
     // the Hessian here - the two answers differ by less than the solver tolerance.)
