@@ -48,8 +48,8 @@ typedef struct MgsModelInfo {
 } MgsModelInfo;
 
 int mgs_model_create(const MgsModelDesc *desc, int device, MgsModel **out);
-/* Same, with explicit per-environment capacities (0 = default: 32 contacts, static rows + 96 contact
- * rows).  Shared memory per environment - and so the number of environments resident per SM - follows
+/* Same, with explicit per-environment capacities (0 = default: 32-64 contacts depending on the number of object
+ * pairs - 32 for models with more than 24 dofs - and static rows + 4 rows per contact slot).  Shared memory per environment - and so the number of environments resident per SM - follows
  * from them.  Contacts beyond capacity are dropped and counted in the diagnostics' overflow field. */
 int mgs_model_create_ex(const MgsModelDesc *desc, int device, int ncon_max, int nefc_max, MgsModel **out);
 void mgs_model_destroy(MgsModel *model);

@@ -144,6 +144,17 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
   }
   int nc = 2 * nobjpair;
   nc = nc < 32 ? 32 : (nc > 64 ? 64 : nc);
+  // many-dof models (the 16-dof hands: nv >= 28) pay nv reals per Jacobian row: 32 contacts were never exceeded on the
+  // round-1 workloads (tools/caps_sweep.py: Allegro / LEAP / Shadow, 1184 candidates each, 0 environments overflowed) and
+  // double the number of environments resident per SM (Shadow 2 -> 4, LEAP 3 -> 5)
+  // (single-object scenes only: every resting object of a clutter scene needs its own 3-4 table contacts)
+  int nfreeobj = 0;
+  for (int bd = 1; bd < nb; bd++) {
+    bool leaf = true;
+    for (int c = 0; c < nb; c++) if (d->body_parentid[c] == bd && c != bd) leaf = false;
+    if (d->body_parentid[bd] == 0 && d->body_dofnum[bd] == 6 && leaf && d->body_mocapid[bd] < 0) nfreeobj++;
+  }
+  if (nv > 24 && nfreeobj <= 1) nc = 32;
   nc = (nc + 3) & ~3;
   out.ncon_max = nc;
   out.nefc_max = ne + nfr + nlim + nc * (maxdim < 3 ? 3 : maxdim);  // every contact slot can hold the largest cone
