@@ -166,6 +166,8 @@ def run_ours(args, rank, world, local_rank):
         """One workload: W warm-up + K timed passes on device-resident inputs (CUDA events), then K passes through
         the host-pointer C ABI.  Returns the JSON fields of that workload (rank 0) or None."""
         gripper, (ncon_max, nefc_max), workload = WORKLOADS[key]
+        if args.caps and key == args.workload:
+            ncon_max, nefc_max = (int(x) for x in args.caps.split(","))
         model, info, pose7, joints = scenes.workload(gripper, "hull", rank, N_CAND)  # one object per rank (weak scaling)
         # per-environment capacities (contacts / constraint rows) bound shared memory per environment; the library
         # counts every environment that would have needed more (config.capacity.envs_overflowed)
@@ -279,6 +281,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="robotiq", choices=sorted(WORKLOADS), help="robotiq = BASELINE.json configs[1] (default)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary Panda-on-convex measurement")
+    ap.add_argument("--caps", default="", help="override the primary workload's per-environment capacities: ncon_max,nefc_max")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

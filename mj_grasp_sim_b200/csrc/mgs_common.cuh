@@ -82,7 +82,7 @@ enum { MGS_MODE_STEP = 0, MGS_MODE_COLLISION = 1, MGS_MODE_STABILITY = 2, MGS_MO
 // Model constants on the device (all pointers into one read-only blob).
 struct DevModel {
   int nq, nv, nu, nbody, njnt, neq, nmocap, ntendon, nwrap, ncgeom, npair, nhull;
-  int maxdepth, max_tree_dofs, ne_rows, ngravcomp, dofmask_words, cone_elliptic, iterations, ls_iterations, noslip_iterations, mpr_iterations, ground_geomid;
+  int maxdepth, max_tree_dofs, ne_rows, nf_rows, ngravcomp, dofmask_words, cone_elliptic, iterations, ls_iterations, noslip_iterations, mpr_iterations, ground_geomid;
   real timestep, impratio, tolerance, ls_tolerance, noslip_tolerance, mpr_tolerance, meaninertia, gravity[3];
   const int *body_parentid, *body_rootid, *body_mocapid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_depth;
   const real *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0, *body_subtreemass, *body_gravcomp;
@@ -102,6 +102,7 @@ struct DevModel {
   const int *actuator_trntype, *actuator_trnid, *actuator_ctrllimited, *actuator_forcelimited;
   const real *actuator_gainprm, *actuator_biasprm, *actuator_ctrlrange, *actuator_forcerange, *actuator_gear;
   const int *eq_type, *eq_obj1id, *eq_obj2id, *eq_active, *eq_rowadr, *tri_ab;
+  const int *dof_frictionrank;       // [nv]: rank of dof d among the dofs with frictionloss > 0 (its row is ne_rows + rank), -1 if none
   const unsigned int *body_dofmask;  // [nbody][dofmask_words]: bit d set = dof d is on the path from the body to its root
   const real *eq_data, *eq_solref, *eq_solimp;
   const real *mocap_pos0, *mocap_quat0;

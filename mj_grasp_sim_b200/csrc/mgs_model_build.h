@@ -109,6 +109,13 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
     for (int c = 0; c <= a; c++) tri.push_back((a << 8) | c);
   m.tri_ab = put<int>(b, tri.data(), tri.size());
   {
+    std::vector<int> rank(nv > 0 ? nv : 1, -1);
+    int nfr_rows = 0;
+    for (int i = 0; i < nv; i++) if (d->dof_frictionloss[i] > 0) rank[i] = nfr_rows++;
+    m.nf_rows = nfr_rows;
+    m.dof_frictionrank = put<int>(b, rank.data(), nv);
+  }
+  {
     // ancestry masks: which dofs move a point fixed to body i (lane-per-dof Jacobian assembly)
     const int words = (nv + 31) / 32 > 0 ? (nv + 31) / 32 : 1;
     std::vector<unsigned int> mask((size_t)nb * words, 0u);

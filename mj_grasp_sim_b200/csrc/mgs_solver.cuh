@@ -130,9 +130,7 @@ MGS_DEVN void finalize_rows_w(Env &e) {
 MGS_DEVN void make_constraint_w(Env &e) {
   const int nv = MD.nv;
   // --- row bookkeeping (warp-uniform)
-  int ne = MD.ne_rows, nf = 0, nl = 0;
-  #pragma unroll 1
-  for (int d = 0; d < nv; d++) nf += LDG(MD.dof_frictionloss + d) > 0;
+  int ne = MD.ne_rows, nf = MD.nf_rows, nl = 0;
   // limits: count with a scan so that rows come out in joint order
   {
     int cnt_base = 0;
@@ -283,9 +281,7 @@ MGS_DEVN void make_constraint_w(Env &e) {
   PFOR(d, nv) {
     real fl = LDG(MD.dof_frictionloss + d);
     if (fl <= 0) continue;
-    int r = ne;
-    #pragma unroll 1
-    for (int k = 0; k < d; k++) r += LDG(MD.dof_frictionloss + k) > 0;
+    const int r = ne + LDG(MD.dof_frictionrank + d);
     EF(J)[r * nv + d] = 1;
     tag_row(e, r, CT_FRICTION_DOF, d, fl);
   }
@@ -357,25 +353,27 @@ MGS_DEVN real constraint_update_w(Env &e) {
       if (dim < 3 || !MD.cone_elliptic) {
         if (jar < 0) { EF(efc_force)[i] = -D * jar; cost += R_(0.5) * D * jar * jar; EFC_SET_STATE(i, ST_QUADRATIC); }
         else { EF(efc_force)[i] = 0; EFC_SET_STATE(i, ST_SATISFIED); }
-        #pragma unroll 1
-        for (int j = 1; j < dim; j++) { EF(efc_force)[i + j] = 0; EFC_SET_STATE(i + j, ST_SATISFIED); }
+#pragma unroll
+        for (int j = 1; j < 4; j++) if (j < dim) { EF(efc_force)[i + j] = 0; EFC_SET_STATE(i + j, ST_SATISFIED); }
         continue;
       }
-      real mu = EF(con_mu)[c], fr[5], U[6], T = 0;
-      for (int k = 0; k < 5; k++) fr[k] = LDG(MD.pair_friction + 5 * p + k);
+      // condim is 1, 3 or 4 (checked when the model is built): all loops over the cone's rows are unrolled to 4
+      real mu = EF(con_mu)[c], fr[3], U[4] = {0, 0, 0, 0}, T = 0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) fr[k] = LDG(MD.pair_friction + 5 * p + k);
       U[0] = jar * mu;
-      #pragma unroll 1
-      for (int j = 1; j < dim; j++) { U[j] = EF(efc_jar)[i + j] * fr[j - 1]; T += U[j] * U[j]; }
+#pragma unroll
+      for (int j = 1; j < 4; j++) if (j < dim) { U[j] = EF(efc_jar)[i + j] * fr[j - 1]; T += U[j] * U[j]; }
       real N = U[0];
       T = sqrt(T);
       int st;
       if (N >= mu * T || (T <= 0 && N >= 0)) {
-        #pragma unroll 1
-        for (int j = 0; j < dim; j++) EF(efc_force)[i + j] = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j < dim) EF(efc_force)[i + j] = 0;
         st = ST_SATISFIED;
       } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-        #pragma unroll 1
-        for (int j = 0; j < dim; j++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j < dim) {
           real x = EF(efc_jar)[i + j], Dj = EF(efc_D)[i + j];
           EF(efc_force)[i + j] = -Dj * x;
           cost += R_(0.5) * Dj * x * x;
@@ -386,12 +384,13 @@ MGS_DEVN real constraint_update_w(Env &e) {
         cost += R_(0.5) * Dm * NmT * NmT;
         real f0 = -Dm * NmT * mu;
         EF(efc_force)[i] = f0;
-        #pragma unroll 1
-        for (int j = 1; j < dim; j++) EF(efc_force)[i + j] = -f0 / T * U[j] * fr[j - 1];
+        const real f0T = -f0 / T;
+#pragma unroll
+        for (int j = 1; j < 4; j++) if (j < dim) EF(efc_force)[i + j] = f0T * U[j] * fr[j - 1];
         st = ST_CONE;
       }
-      #pragma unroll 1
-      for (int j = 0; j < dim; j++) EFC_SET_STATE(i + j, st);
+#pragma unroll
+      for (int j = 0; j < 4; j++) if (j < dim) EFC_SET_STATE(i + j, st);
     }
   }
   return cost;
@@ -419,8 +418,8 @@ MGS_DEVN void ls_eval_w(const Env &e, real alpha, real *d1, real *d2) {
       if (dim < 3 || !MD.cone_elliptic) { if (x < 0) { a += D * x * jv; h += D * jv * jv; } continue; }
       real mu = EF(con_mu)[c], T = 0, UV = 0, VV = 0;
       real N = x * mu, N1 = jv * mu;
-      #pragma unroll 1
-      for (int j = 1; j < dim; j++) {
+#pragma unroll
+      for (int j = 1; j < 4; j++) if (j < dim) {
         real fj = LDG(MD.pair_friction + 5 * p + j - 1);
         real Uj = (EF(efc_jar)[i + j] + alpha * EF(efc_jv)[i + j]) * fj, Vj = EF(efc_jv)[i + j] * fj;
         T += Uj * Uj; UV += Uj * Vj; VV += Vj * Vj;
@@ -428,8 +427,8 @@ MGS_DEVN void ls_eval_w(const Env &e, real alpha, real *d1, real *d2) {
       T = sqrt(T);
       if (N >= mu * T || (T <= 0 && N >= 0)) {
       } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-        #pragma unroll 1
-        for (int j = 0; j < dim; j++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j < dim) {
           real xj = EF(efc_jar)[i + j] + alpha * EF(efc_jv)[i + j], vj = EF(efc_jv)[i + j], Dj = EF(efc_D)[i + j];
           a += Dj * xj * vj; h += Dj * vj * vj;
         }

@@ -82,3 +82,18 @@ def test_state_vector_roundtrip_and_bounds():
     assert set(d) == {"gripper", "objects", "env_state"} and set(d["env_state"]) == {"geom_conaffinity", "geom_contype", "geom_rgba", "body_gravcomp", "state"}
     env2 = ClutterTableEnv.from_dict(d)
     assert np.allclose(env2.get_state(), st2)
+
+
+def test_batched_scene_generation_equals_single(clutter):
+    """scenes.gen_clutter_batch on the 1-lane host build: scene k of a batch is bit-identical to
+    gen_clutter(seed k) - an environment's trajectory does not depend on what else is in the batch."""
+    m, info, _, _, _ = clutter
+    L = lane1.sim(m, f64=False)
+    single_step = lambda rec, n: L.step(rec[None].astype(np.float32), n)[0].astype(np.float64)
+    batch_step = lambda recs, n: L.step(recs.astype(np.float32), n).astype(np.float64)
+    seeds = [3, 4]
+    recs = scenes.gen_clutter_batch(m, info, batch_step, seeds)
+    one = scenes.gen_clutter(m, info, single_step, seeds[1])
+    assert recs.shape == (2, len(one)) and np.array_equal(recs[1], one)
+    ok, after = scenes.scenes_stable(m, info, batch_step, recs.copy())
+    assert ok.shape == (2,) and after.shape == recs.shape
