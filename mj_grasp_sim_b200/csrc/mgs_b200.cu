@@ -1,9 +1,5 @@
-// mgs_b200.cu - persistent warp-per-environment rollout kernel + the C ABI (include/mgs_b200.h).
-//
-// Launch shape: a persistent grid of (blocks_per_sm x 148) CTAs, each WARPS warps; every warp pulls
-// candidate indices from a global atomic work queue, so warps that finish early (most candidates
-// fail the post-close contact test after 3000 of 8000 steps) immediately start the next candidate
-// instead of idling until the slowest lane of a fixed assignment finishes.
+// mgs_b200.cu - the C ABI (include/mgs_b200.h) + the 16-warp variant of the persistent warp-per-environment rollout
+// kernel (mgs_kernel.cuh; the 12-warp variant lives in mgs_kernel_w12.cu).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -13,28 +9,11 @@
 
 #include "../../include/mgs_b200.h"
 #include "mgs_model_build.h"
-#include "mgs_rollout.cuh"
-
 #ifndef MGS_MAX_WARPS_PER_BLOCK
 #define MGS_MAX_WARPS_PER_BLOCK 16
 #endif
-
-
-__global__ void __launch_bounds__(MGS_MAX_WARPS_PER_BLOCK * 32)
-mgs_rollout_kernel() {
-  real *base = reinterpret_cast<real *>(mgs_smem_raw) + (size_t)(threadIdx.x >> 5) * LY.total;
-  const int lane = threadIdx.x & 31;
-  Env e;
-  for (;;) {
-    unsigned int env = 0;
-    if (lane == 0) env = atomicAdd(IO.work_counter, 1u);
-    env = __shfl_sync(0xffffffffu, env, 0);
-    if (env >= (unsigned int)PRM.n) break;
-    env_bind(e, base);
-    run_env_w(e, (int)env);
-  }
-  // a warp that runs out of work leaves; exited warps no longer count towards the CTA barrier
-}
+#define MGS_KERNEL_TAG w16
+#include "mgs_kernel.cuh"
 
 // ---------------------------------------------------------------------------------- host side
 static thread_local std::string g_err;
@@ -54,6 +33,7 @@ struct MgsModel {
   char *d_blob;
   unsigned int *d_counter;
   int num_sms, blocks_per_sm, smem_per_block, warps_per_block;
+  const MgsKernelOps *ops;  // the kernel variant this model runs on
   int state_stride, diag_stride;
   // staging for the host-pointer entry points (grown on demand)
   void *d_stage, *h_stage;
@@ -99,24 +79,31 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
     delete M;
     return fail("model needs more shared memory per environment than one CTA can have (env-per-block variant not built yet)");
   }
-  CU(cudaFuncSetAttribute(mgs_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  // CTA size = the warps-per-block that gives the most resident warps per SM (shared memory per
-  // environment and the per-CTA reservation decide)
+  // CTA size = the warps-per-block that gives the most resident warps per SM (shared memory per environment and the
+  // per-CTA reservation decide).  First with the 16-warp variant; if at most 12 environments fit per SM anyway, the
+  // 12-warp variant (more registers per thread) takes over.
+  const char *force_wpb = getenv("MGS_WARPS_PER_BLOCK");  // tuning knobs: force the CTA size / the variant
+  const char *force_var = getenv("MGS_KERNEL_VARIANT");
+  const MgsKernelOps *variants[2] = {mgs_kernel_ops_w16(), mgs_kernel_ops_w12()};
   int best_warps = 0;
-  const char *force_wpb = getenv("MGS_WARPS_PER_BLOCK");  // tuning knob: force the CTA size
-  for (int w = 1; w <= MGS_MAX_WARPS_PER_BLOCK; w++) {
-    if (force_wpb && atoi(force_wpb) != w) continue;
-    if ((size_t)env_bytes * w > prop.sharedMemPerBlockOptin) break;
-    CU(cudaFuncSetAttribute(mgs_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, env_bytes * w));
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgs_rollout_kernel, w * 32, (size_t)env_bytes * w));
-    if (occ * w >= best_warps && occ > 0) {  // ties go to the LARGER CTA: one CTA per SM keeps all resident warps stage-aligned
-       best_warps = occ * w; M->warps_per_block = w; M->blocks_per_sm = occ;
+  for (int v = 0; v < 2; v++) {
+    const MgsKernelOps *ops = variants[v];
+    if (force_var && std::string(force_var) != (v == 0 ? "w16" : "w12")) continue;
+    if (v == 1 && !force_var && (best_warps == 0 || best_warps > ops->max_warps || M->blocks_per_sm != 1)) break;
+    int vb = 0, vw = 0, vo = 0;
+    for (int w = 1; w <= ops->max_warps; w++) {
+      if (force_wpb && atoi(force_wpb) != w) continue;
+      if ((size_t)env_bytes * w > prop.sharedMemPerBlockOptin) break;
+      CU(ops->prepare(env_bytes * w));
+      int occ = 0;
+      CU(ops->occupancy(&occ, w * 32, (size_t)env_bytes * w));
+      if (occ * w >= vb && occ > 0) { vb = occ * w; vw = w; vo = occ; }  // ties go to the LARGER CTA: one CTA per SM keeps all resident warps stage-aligned
     }
+    if (vb >= best_warps && vb > 0) { best_warps = vb; M->warps_per_block = vw; M->blocks_per_sm = vo; M->ops = ops; }
   }
   if (best_warps == 0) { delete M; return fail("kernel does not fit on this device"); }
   M->smem_per_block = env_bytes * M->warps_per_block;
-  CU(cudaFuncSetAttribute(mgs_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, M->smem_per_block));
+  CU(M->ops->prepare(M->smem_per_block));
   M->state_stride = desc->nq + 2 * desc->nv + desc->nu + 7 * desc->nmocap;
   M->diag_stride = mgs_diag_stride(desc->nv, desc->nbody, blob.ncon_max, blob.nefc_max);
   CU(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
@@ -183,10 +170,8 @@ static int launch(MgsModel *M, const RolloutParams &prm, const BatchIO &io_in, c
   have_last[M->device] = true;
   KernelConsts kc;
   kc.m = M->dm; kc.L = M->L; kc.prm = prm; kc.io = io;
-  CU(cudaMemcpyToSymbolAsync(c_k, &kc, sizeof(kc), 0, cudaMemcpyHostToDevice, st));
-  mgs_rollout_kernel<<<grid, wpb * 32, (size_t)(M->smem_per_block / M->warps_per_block) * wpb, st>>>();
+  CU(M->ops->launch(&kc, grid, wpb * 32, (size_t)(M->smem_per_block / M->warps_per_block) * wpb, st));
   g_launches++;
-  CU(cudaGetLastError());
   CU(cudaEventRecord(last_done[M->device], st));
   return 0;
 }

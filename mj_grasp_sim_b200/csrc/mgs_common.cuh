@@ -37,7 +37,7 @@ typedef float real;
 #else
 #include <cuda_runtime.h>
 #define MGS_DEV __device__ __forceinline__
-#define MGS_DEVN __device__ __noinline__
+#define MGS_DEVN static __device__ __noinline__
 #define LANES 32
 #define MGS_LANE ((int)(threadIdx.x & 31))
 #define WSYNC() __syncwarp()

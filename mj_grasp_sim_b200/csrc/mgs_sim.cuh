@@ -125,7 +125,7 @@ struct KernelConsts { DevModel m; Layout L; RolloutParams prm; BatchIO io; };
 static KernelConsts g_k;
 #define MGS_K g_k
 #else
-__constant__ KernelConsts c_k;
+static __constant__ KernelConsts c_k;  // one copy per kernel variant (translation unit)
 #define MGS_K c_k
 #endif
 #define MD (MGS_K.m)

@@ -45,7 +45,9 @@ def build(force: bool = False, f64: bool = False) -> str:
     so = SO_PATH_F64 if f64 else SO_PATH
     if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in _sources()):
         return so
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-DMGS_REAL_DOUBLE"] if f64 else []) + ["-o", so, os.path.join(CSRC, "mgs_b200.cu")]
+    # two translation units = two variants of the rollout kernel (16 / 12 warps per CTA, see csrc/mgs_kernel_ops.h)
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-DMGS_REAL_DOUBLE"] if f64 else []) + ["-o", so, os.path.join(CSRC, "mgs_b200.cu"),
+                                                                             os.path.join(CSRC, "mgs_kernel_w12.cu")]
     subprocess.check_call(cmd)
     return so
 

@@ -28,8 +28,14 @@ asp_i, op_i = shdr.index("Address Space"), shdr.index("Access Operation")
 data = srows[2:]
 with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=td, capture_output=True)
-    cub = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout
+    # one cubin per kernel variant (translation unit): MGS_VARIANT=w16 (default) | w12 selects the profiled one
+    tag = "mgs_rollout_kernel_" + os.environ.get("MGS_VARIANT", "w16")
+    dis = ""
+    for cub in sorted(f for f in os.listdir(td) if f.endswith(".cubin")):
+        d = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout
+        if tag in d or "mgs_rollout_kernelv" in d:
+            dis = d
+            break
 func, line, seq = None, None, []
 for l in dis.split("\n"):
     m = re.match(r'\s*//## File "(.*?)", line (\d+)', l)
@@ -60,7 +66,7 @@ for (f, ln), r in zip(seq, data):
 tot, tots = sum(v[0] for v in byf.values()), sum(v[1] for v in byf.values())
 print(f"== by function (total warp-instructions {tot}, samples {tots}): %inst %samples lane-efficiency")
 for k, v in sorted(byf.items(), key=lambda kv: -kv[1][1])[:28]:
-    name = re.sub(r"^\$?_Z\d+mgs_rollout_kernelv\$", "", str(k))
+    name = re.sub(r"^\$?_Z\d+mgs_rollout_kernel\w*?v\$|_ZN\d+_INTERNAL_[0-9a-f]{8}_\d+_\w+?_cu_[0-9a-f]{8}\d+", "", str(k))
     print(f"{100*v[0]/tot:6.2f} {100*v[1]/tots:6.2f} {v[2]/max(1,v[0])/32:5.2f}  {name}")
 print("== top source lines: %inst %samples lane-efficiency")
 for k, v in sorted(byl.items(), key=lambda kv: -kv[1][1])[:25]:
@@ -68,12 +74,12 @@ for k, v in sorted(byl.items(), key=lambda kv: -kv[1][1])[:25]:
 
 print("== stall mix by function (% of all samples): " + " ".join(k.replace("stall_", "") for k in stall_cols))
 for k, v in sorted(byf.items(), key=lambda kv: -kv[1][1])[:28]:
-    name = re.sub(r"^\$?_Z\d+mgs_rollout_kernelv\$", "", str(k))
+    name = re.sub(r"^\$?_Z\d+mgs_rollout_kernel\w*?v\$|_ZN\d+_INTERNAL_[0-9a-f]{8}_\d+_\w+?_cu_[0-9a-f]{8}\d+", "", str(k))
     print(" ".join(f"{100*stf[k][c]/tots:6.2f}" for c in stall_cols) + "  " + name)
 print("== stall mix, top source lines")
 for k, v in sorted(byl.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{100*v[1]/tots:6.2f} | " + " ".join(f"{100*stl[k][c]/tots:6.2f}" for c in stall_cols) + f"  {k}")
 print("== memory instructions by function (% of all warp-instructions): space:op")
 for k, v in sorted(byf.items(), key=lambda kv: -kv[1][1])[:28]:
-    name = re.sub(r"^\$?_Z\d+mgs_rollout_kernelv\$", "", str(k))
+    name = re.sub(r"^\$?_Z\d+mgs_rollout_kernel\w*?v\$|_ZN\d+_INTERNAL_[0-9a-f]{8}_\d+_\w+?_cu_[0-9a-f]{8}\d+", "", str(k))
     print("  " + name + "  " + "  ".join(f"{a} {100*c/tot:.2f}" for a, c in sorted(memf[k].items(), key=lambda ac: -ac[1])))
