@@ -13,7 +13,7 @@
 #define MGS_STR(x) MGS_STR_(x)
 #define MGS_KERNEL MGS_CAT(mgs_rollout_kernel_, MGS_KERNEL_TAG)
 
-__global__ void __launch_bounds__(MGS_MAX_WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(MGS_MAX_WARPS_PER_BLOCK * 32, 1)
 MGS_KERNEL() {
   real *base = reinterpret_cast<real *>(mgs_smem_raw) + (size_t)(threadIdx.x >> 5) * LY.total;
   const int lane = threadIdx.x & 31;
