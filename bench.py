@@ -36,7 +36,7 @@ ROLLOUT = dict(nstep_close=3000, nstep_lift=3000, shake_steps=500, repose_on_clo
 # --workload: gripper, explicit per-environment capacities (contacts, constraint rows; 0 = the model's default), description
 WORKLOADS = {
     "robotiq": ("robotiq2f85", (24, 110), "configs[1]: robotiq 2f-85 gripper, 1 synthetic 32-vertex convex-hull object per GPU (ycb recipe), 4096 antipodal candidates per object, close3000+lift3000+shake2000"),
-    "panda": ("panda", (20, 90), "panda gripper, 1 synthetic 32-vertex convex-hull object per GPU (ycb recipe), 4096 antipodal candidates, close3000+lift3000+shake2000"),
+    "panda": ("panda", (24, 100), "panda gripper, 1 synthetic 32-vertex convex-hull object per GPU (ycb recipe), 4096 antipodal candidates, close3000+lift3000+shake2000"),
 }
 
 
