@@ -249,6 +249,15 @@ def run_ours(args, rank, world, local_rank):
                                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
                                 "note": "state stays in shared memory for the whole rollout; the kernel is issue/latency bound, not HBM bound"},
                    "clocks": clk.summary(), "wall_s": t_wall}
+            # secondary roofline: warp-instruction issue slots (the bound that actually applies).  Instructions per env-step are
+            # the ncu count of the steady hold phase (profiles/ncu_r1_m_*_steady.txt: smsp__inst_executed.sum / env-steps);
+            # peak = 148 SMs x 4 schedulers x 1 warp-instruction per cycle at the SM clock sampled during the run
+            ipe = {"panda": 26.1e3, "robotiq": 40.4e3}.get(key)
+            mhz = out["clocks"].get("sm_mhz") or 1965.0
+            if ipe:
+                peak_issue = 148 * 4 * mhz * 1e6
+                out["issue_slots"] = {"warp_instr_per_env_step": ipe, "source": "ncu r1_m steady capture", "achieved_ginst_s": ipe * value / world / 1e9,
+                                      "peak_ginst_s": peak_issue / 1e9, "frac": ipe * value / world / peak_issue}
             if with_cpu:
                 from oracle import oracle as orc
                 orc.build()
@@ -265,7 +274,7 @@ def run_ours(args, rank, world, local_rank):
     also = measure("panda", with_cpu) if (args.workload != "panda" and not args.no_also) else None
     if rank == 0:
         if also is not None:
-            line["also"] = {"panda_on_convex": {k: also[k] for k in ("value", "unit", "ms_per_step", "grasps_per_s", "e2e", "config", "roofline", "gpu_launches")
+            line["also"] = {"panda_on_convex": {k: also[k] for k in ("value", "unit", "ms_per_step", "grasps_per_s", "e2e", "config", "roofline", "issue_slots", "gpu_launches")
                                                  + (("cpu_baseline",) if "cpu_baseline" in also else ())}}
             line["gpu_launches"] += also["gpu_launches"]
         print(json.dumps(line), flush=True)
