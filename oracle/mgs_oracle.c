@@ -13,7 +13,9 @@
  *
  * PARITY STATUS: "parity unpinned" against real MuJoCo - the reference ships no golden vectors at
  * the mj_step boundary and MuJoCo cannot be run here.  The oracle is pinned instead by analytic
- * invariants (tests/test_oracle_*.py).  Known deliberate difference: convex narrowphase builds
+ * invariants (tests/test_oracle_invariants.py) and by the one MuJoCo-recorded vector the reference holds:
+ * the Robotiq closed-state mjSTATE_INTEGRATION record of mgs/cli/config/gripper/robotiq_2f_85.yaml:11
+ * (tests/golden/robotiq_2f85_state_close.json, tests/test_golden_robotiq.py).  Known deliberate difference: convex narrowphase builds
  * its multi-point manifold by MPR + face clipping instead of libccd MPR + multiccd perturbation.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
