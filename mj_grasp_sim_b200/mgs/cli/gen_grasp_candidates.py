@@ -1,0 +1,39 @@
+"""gen_grasp_candidates - producer of the hot path's input (/root/reference/mgs/cli/gen_grasp_candidates.py:17-83).
+
+Antipodal candidates for the parallel-jaw grippers the reference serves this way (Panda, VX300: `all_gripper`, :23-28):
+poses from `AntipodalGraspGenerator`, finger joints from the contact distance through `_clamp_width` + `width_to_joints`
+(:62-64), written as <MGS_OUTPUT_DIR>/<gripper name>/<object id>/candidates.npz {pose [N,4,4], joints [N,2]}.  The
+dexterous hands use the reference's differentiable contact sampler, which is out of scope.
+
+  python -m mj_grasp_sim_b200.mgs.cli.gen_grasp_candidates gripper=PandaGripper object=hull:0 [num_grasps=10000] [seed=0]
+"""
+import os
+
+import numpy as np
+
+from ..gripper.selector import get_gripper
+from ..obj.selector import get_object
+from ..sampler.antipodal import AntipodalGraspGenerator
+from ._common import parse_kv
+
+
+def run(gripper_name: str, object_id: str, num_grasps: int = 10000, output_dir: str | None = None, seed: int | None = None):
+    if gripper_name not in ("PandaGripper", "VXGripper"):
+        raise NotImplementedError(f"{gripper_name}: only PandaGripper and VXGripper have antipodal candidates (gen_grasp_candidates.py:23-28)")
+    print(f"Generating grasp candidates for gripper: {gripper_name}")
+    gripper = get_gripper(gripper_name)
+    obj = get_object(object_id)
+    Hs, aux = AntipodalGraspGenerator(obj, seed=seed).generate_grasps(num_grasps)
+    j1, j2 = gripper.width_to_joints(gripper._clamp_width(aux["width"]))
+    joints = np.stack([j1, j2], axis=-1)
+    out = os.path.join(output_dir or os.getenv("MGS_OUTPUT_DIR") or ".", gripper_name, object_id)
+    os.makedirs(out, exist_ok=True)
+    np.savez(os.path.join(out, "candidates.npz"), pose=Hs, joints=joints)
+    print("Done!")
+    return Hs, joints
+
+
+if __name__ == "__main__":
+    kv = parse_kv()
+    run(kv.get("gripper", "PandaGripper"), kv.get("object", "cube"), int(kv.get("num_grasps", 10000)), kv.get("dir"),
+        int(kv["seed"]) if "seed" in kv else None)

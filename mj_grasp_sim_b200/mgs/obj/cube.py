@@ -19,6 +19,12 @@ class ObjectCube(CollisionMeshObject):
         vec = pose.to_vec(layout="pq", type="wxyz")
         self.pos, self.quat, self.name, self.size, self.object_id = vec[:3], vec[3:], name, size, name
 
+    def mesh(self):
+        """(verts, triangles) of the box - what a candidate sampler is given"""
+        from ...compiler import mesh as meshlib
+        h = meshlib.box_hull([self.size, self.size, self.size])
+        return h.verts, h.tri
+
     def to_xml(self) -> Tuple[str, Dict[str, Any]]:
         return _TEMPLATE.format(position="{} {} {}".format(*self.pos), quaternion="{} {} {} {}".format(*self.quat),
                                 name=self.name, size=self.size), {}
