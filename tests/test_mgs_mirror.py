@@ -68,3 +68,33 @@ def test_robotiq_and_vx300_mirror_classes():
         b2c = g.base_to_contact_transform()
         assert np.allclose(b2c.pos, scenes.GRIPPERS[key]["b2c_pos"]) and np.allclose(b2c.quat, scenes.GRIPPERS[key]["b2c_quat"], atol=1e-6)
         assert np.allclose(g.close_ctrl(), scenes.GRIPPERS[key]["close_ctrl"])
+
+
+def test_cli_pipeline_end_to_end_on_the_host_build(tmp_path, monkeypatch):
+    """gen_grasp_candidates -> candidates.npz -> filter_to_stable -> candidates_collision_free.npz / stable_grasps.npz, the
+    reference's single-object flow (README 'gen_grasps' stages), with the env's simulator routed to the 1-lane HOST build of
+    the kernel source (test harness: the product path needs a CUDA device) and the labels checked against the oracle."""
+    import ctypes as C
+    import os
+    from hostsim import lane1
+    from mj_grasp_sim_b200 import lib as mlib
+    from mj_grasp_sim_b200.mgs.cli import filter_to_stable, gen_grasp_candidates
+    from mj_grasp_sim_b200.mgs.env import gravityless_object_grasping as gog
+    from oracle.oracle import RolloutCfg, batch
+    L = mlib.bind(C.CDLL(lane1.build(False)), prefix="l1_")
+    monkeypatch.setattr(gog, "BatchSim", lambda model, device=0, ncon_max=0, nefc_max=0: mlib.BatchSim(model, lib=L, prefix="l1_"))
+    H, joints = gen_grasp_candidates.run("PandaGripper", "hull:0", 6, str(tmp_path), seed=4)
+    free, stable = filter_to_stable.run("PandaGripper", "hull:0", str(tmp_path))
+    d = tmp_path / "PandaGripper" / "hull:0"
+    cf, st = np.load(d / "candidates_collision_free.npz"), np.load(d / "stable_grasps.npz")
+    assert cf["pose"].shape == (int(free.sum()), 4, 4) and st["pose"].shape == (int(stable.sum()), 4, 4) and st["joints"].shape[1] == 2
+    # oracle on the same candidates
+    env = gog.GravitylessObjectGrasping(get_gripper("PandaGripper"), get_object("hull:0"))
+    pose7, j32, jadr = env._process(SE3Pose.from_mat(H, type="wxyz"), joints)
+    base = env.gripper.get_freejoint_idxs(env)[0]
+    sched = RolloutCfg(3000, 3000, 500, 0, 0.1, 0.02)
+    ofree, _ = batch(env.model, 0, pose7.astype(np.float64), base, j32.astype(np.float64), jadr, env.gripper.close_ctrl(), sched, os.cpu_count() or 1)
+    assert np.array_equal(free, ofree)
+    olab, _ = batch(env.model, 1, pose7[free].astype(np.float64), base, j32[free].astype(np.float64), jadr, env.gripper.close_ctrl(), sched,
+                    os.cpu_count() or 1)
+    assert (stable == olab).mean() >= 0.8
