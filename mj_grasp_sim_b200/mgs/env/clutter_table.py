@@ -141,6 +141,39 @@ class ClutterTableEnv(MjSimulation):
             stats += np.abs(np.array([self._record[a:a + 3] for a in adr]) - start).sum(axis=1)
         return bool(stats.max() < 5e-3) if len(adr) else True
 
+    def get_object(self, object_name: str):
+        for obj in self.objects:
+            if obj.name == object_name:
+                return obj
+        return None
+
+    def _disable_bodies(self, body_ids):
+        """What the reference does by zeroing geom_contype / geom_conaffinity and setting body_gravcomp = 1 on the live
+        mjModel (remove_obj, :146-155): on the compiled model the candidate-pair list loses every pair that involves a
+        geom of those bodies, the masks are zeroed and gravity compensation is switched on; the device copy of the model is
+        rebuilt on next use."""
+        ar = self.model.arr
+        body_ids = set(int(b) for b in body_ids)
+        if not body_ids:
+            return
+        gone_c = np.array([int(b) in body_ids for b in ar["cgeom_bodyid"]])
+        keep = ~(gone_c[ar["pair_geom1"]] | gone_c[ar["pair_geom2"]])
+        for k in ("pair_geom1", "pair_geom2", "pair_condim", "pair_friction", "pair_solref", "pair_solimp", "pair_margin", "pair_gap"):
+            ar[k] = ar[k][keep]
+        ar["npair"] = int(keep.sum())
+        for g in np.nonzero(np.isin(ar["geom_bodyid"], list(body_ids)))[0]:
+            ar["geom_contype"][g] = 0
+            ar["geom_conaffinity"][g] = 0
+        for b in body_ids:
+            ar["body_gravcomp"][b] = 1.0
+        if self._sim is not None:
+            self._sim.close()
+            self._sim = None
+
+    def remove_obj(self, obj):
+        """ClutterTableEnv.remove_obj (reference :146-155): the object stops colliding and floats where it is."""
+        self._disable_bodies([self.model.names["body"][obj.name]])
+
     def get_obj_pose(self, object_name: str) -> SE3Pose:
         """object free-joint pose in the world (reference :323-328)"""
         a = int(self.model.jnt_qposadr[self.model.names["joint"][f"{object_name}:joint"]])
@@ -186,6 +219,16 @@ class ClutterTableEnv(MjSimulation):
         env = cls(state_dict["gripper"], state_dict["objects"], scene_randomization=False)
         env.set_state(state_dict["env_state"]["state"])
         st = state_dict["env_state"]
-        if not (np.array_equal(st["geom_contype"], env.model.geom_contype) and np.array_equal(st["geom_conaffinity"], env.model.geom_conaffinity)):
-            raise NotImplementedError("scenes with removed objects (edited geom masks) are not supported yet")
+        # restore edited masks (reference :394-397): bodies whose geoms were switched off (remove_obj) are switched off here too
+        off = (np.asarray(st["geom_contype"]) == 0) & (np.asarray(st["geom_conaffinity"]) == 0) & \
+              ((env.model.geom_contype != 0) | (env.model.geom_conaffinity != 0))
+        other = (np.asarray(st["geom_contype"]) != env.model.geom_contype) | (np.asarray(st["geom_conaffinity"]) != env.model.geom_conaffinity)
+        if (other & ~off).any():
+            raise NotImplementedError("only masks that switch whole geoms off (remove_obj) can be restored")
+        bodies = set(int(b) for b in env.model.geom_bodyid[off])
+        for b in bodies:
+            if not off[env.model.geom_bodyid == b].all():
+                raise NotImplementedError("partially disabled bodies are not supported")
+        env._disable_bodies(bodies)
+        env.model.arr["body_gravcomp"][:] = np.asarray(st["body_gravcomp"], dtype=np.float64)
         return env

@@ -97,3 +97,33 @@ def test_batched_scene_generation_equals_single(clutter):
     assert recs.shape == (2, len(one)) and np.array_equal(recs[1], one)
     ok, after = scenes.scenes_stable(m, info, batch_step, recs.copy())
     assert ok.shape == (2,) and after.shape == recs.shape
+
+
+def test_remove_obj_and_mask_roundtrip():
+    """ClutterTableEnv.remove_obj (reference :146-155) on the compiled model + from_dict restoring edited masks (:394-397):
+    the removed object stops colliding and floats (gravcomp 1) while the others keep falling; the scene dictionary carries it."""
+    from mj_grasp_sim_b200.mgs.env.clutter_table import ClutterTableEnv
+    from mj_grasp_sim_b200.mgs.gripper.selector import get_gripper
+    from mj_grasp_sim_b200.mgs.obj.selector import get_objects
+    env = ClutterTableEnv(get_gripper("PandaGripper"), get_objects(["hull:50:16", "hull:51:16"]))
+    m = env.model
+    npair0 = int(m.arr["npair"])
+    gone, kept = env.objects[0], env.objects[1]
+    env.remove_obj(env.get_object(gone.name))
+    bid = m.names["body"][gone.name]
+    assert int(m.arr["npair"]) < npair0 and m.body_gravcomp[bid] == 1.0
+    cg_gone = np.nonzero(m.cgeom_bodyid == bid)[0]
+    assert not np.isin(m.pair_geom1, cg_gone).any() and not np.isin(m.pair_geom2, cg_gone).any()
+    assert (m.geom_contype[m.geom_bodyid == bid] == 0).all()
+    s = OracleSim(m, ground_name="geom:table")
+    s.reset()
+    a_gone = int(m.jnt_qposadr[m.names["joint"][f"{gone.name}:joint"]])
+    a_kept = int(m.jnt_qposadr[m.names["joint"][f"{kept.name}:joint"]])
+    z0 = s.qpos[[a_gone + 2, a_kept + 2]].copy()
+    s.step(150)
+    assert abs(s.qpos[a_gone + 2] - z0[0]) < 1e-9          # compensated, nothing touches it
+    assert s.qpos[a_kept + 2] < z0[1] - 1e-3               # the other one falls onto the table
+    # scene dictionary round trip: masks, gravcomp and the reduced pair list come back
+    env2 = ClutterTableEnv.from_dict(env.to_dict())
+    assert int(env2.model.arr["npair"]) == int(m.arr["npair"]) and np.array_equal(env2.model.geom_contype, m.geom_contype)
+    assert np.array_equal(env2.model.body_gravcomp, m.body_gravcomp) and np.array_equal(env2.model.pair_geom1, m.pair_geom1)
