@@ -31,3 +31,31 @@ def load_candidates(path: str):
 
 def save_grasps(path: str, poses: SE3Pose, joints):
     np.savez(path, pose=poses.to_mat(), joints=joints)
+
+
+# ---- Hydra-style configs without Hydra ---------------------------------------------------------------------------
+# The reference's entry points take a DictConfig (`cfg.gripper.name`, `cfg.id`, ...) and map `cfg.id` to an object through
+# asset/mj-objects/fast_eta_objects.txt (1032 dataset ids, not shipped).  Any attribute- or dict-style object works here;
+# the id list is the synthetic stand-in: index 0 = the box primitive, index k = convex hull seed k - 1.
+SYNTHETIC_OBJECT_IDS = ["cube"] + [f"hull:{i}" for i in range(1031)]
+
+
+def cfg_get(cfg, path: str, default=None):
+    cur = cfg
+    for key in path.split("."):
+        if cur is None:
+            return default
+        cur = cur.get(key, None) if isinstance(cur, dict) else getattr(cur, key, None)
+    return default if cur is None else cur
+
+
+def gripper_name_from_cfg(cfg) -> str:
+    g = cfg_get(cfg, "gripper")
+    return g if isinstance(g, str) else cfg_get(cfg, "gripper.name")
+
+
+def object_id_from_cfg(cfg) -> str:
+    explicit = cfg_get(cfg, "object")
+    if isinstance(explicit, str):
+        return explicit
+    return SYNTHETIC_OBJECT_IDS[int(cfg_get(cfg, "id", 0))]

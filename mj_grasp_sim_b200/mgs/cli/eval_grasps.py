@@ -61,6 +61,14 @@ def run(gripper_name: str, scene_index: int = 0, env_name: str = "clutter_table"
     return report
 
 
+from ._common import cfg_get, gripper_name_from_cfg  # noqa: E402
+
+
+def main(cfg):
+    """Entry point with the reference's `main(cfg)` shape (a Hydra DictConfig there; any attribute/dict config here)."""
+    return run(gripper_name_from_cfg(cfg), int(cfg_get(cfg, "id", 0)), cfg_get(cfg, "env.name", "clutter_table"), cfg_get(cfg, "dir"))
+
+
 if __name__ == "__main__":
     kv = parse_kv()
     run(kv.get("gripper", "ShadowHand"), int(kv.get("id", 0)), kv.get("env", "clutter_table"), kv.get("dir"))

@@ -19,6 +19,14 @@ def run(gripper_name: str, object_id: str, file_dir: str | None = None):
     return mask
 
 
+from ._common import cfg_get, gripper_name_from_cfg, object_id_from_cfg  # noqa: E402
+
+
+def main(cfg):
+    """Entry point with the reference's `main(cfg)` shape (a Hydra DictConfig there; any attribute/dict config here)."""
+    return run(gripper_name_from_cfg(cfg), object_id_from_cfg(cfg), cfg_get(cfg, "dir"))
+
+
 if __name__ == "__main__":
     kv = parse_kv()
     run(kv.get("gripper", "PandaGripper"), kv.get("object", "cube"), kv.get("dir"))

@@ -33,6 +33,14 @@ def run(gripper_name: str, object_id: str, num_grasps: int = 10000, output_dir: 
     return Hs, joints
 
 
+from ._common import cfg_get, gripper_name_from_cfg, object_id_from_cfg  # noqa: E402
+
+
+def main(cfg):
+    """Entry point with the reference's `main(cfg)` shape (a Hydra DictConfig there; any attribute/dict config here)."""
+    return run(gripper_name_from_cfg(cfg), object_id_from_cfg(cfg), int(cfg_get(cfg, "num_grasps", 10000)), cfg_get(cfg, "dir"), cfg_get(cfg, "seed"))
+
+
 if __name__ == "__main__":
     kv = parse_kv()
     run(kv.get("gripper", "PandaGripper"), kv.get("object", "cube"), int(kv.get("num_grasps", 10000)), kv.get("dir"),

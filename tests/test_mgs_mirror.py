@@ -98,3 +98,19 @@ def test_cli_pipeline_end_to_end_on_the_host_build(tmp_path, monkeypatch):
     olab, _ = batch(env.model, 1, pose7[free].astype(np.float64), base, j32[free].astype(np.float64), jadr, env.gripper.close_ctrl(), sched,
                     os.cpu_count() or 1)
     assert (stable == olab).mean() >= 0.8
+
+
+def test_cli_main_accepts_hydra_style_configs(monkeypatch):
+    """`main(cfg)` of every CLI mirror maps the reference's config fields (cfg.gripper.name, cfg.id, ...) to `run`."""
+    from types import SimpleNamespace as NS
+    from mj_grasp_sim_b200.mgs.cli import (_common, eval_grasps, filter_collision_free_candidates, filter_stable_grasps, filter_to_stable,
+                                           gen_grasp_candidates)
+    cfg = NS(gripper=NS(name="VXGripper"), id=3, env=NS(name="clutter_table"), num_grasps=17)
+    assert _common.object_id_from_cfg(cfg) == "hull:2" and _common.object_id_from_cfg(NS(id=0)) == "cube"
+    assert _common.object_id_from_cfg({"object": "hull:9", "id": 1}) == "hull:9"
+    seen = {}
+    for mod in (filter_to_stable, filter_stable_grasps, filter_collision_free_candidates, gen_grasp_candidates, eval_grasps):
+        monkeypatch.setattr(mod, "run", lambda *a, _m=mod.__name__: seen.setdefault(_m.rsplit(".", 1)[1], a))
+        mod.main(cfg)
+    assert seen["filter_to_stable"][:2] == ("VXGripper", "hull:2") and seen["gen_grasp_candidates"][:3] == ("VXGripper", "hull:2", 17)
+    assert seen["eval_grasps"][:3] == ("VXGripper", 3, "clutter_table")
