@@ -19,7 +19,7 @@ import numpy as np
 
 from ..env.selector import get_env_from_dict
 from ..util.geo.transforms import SE3Pose
-from ._common import parse_kv
+from ._common import cfg_get, gripper_name_from_cfg, parse_kv
 
 
 def _to_base_frame(env, contact_frame_poses: np.ndarray) -> np.ndarray:
@@ -59,9 +59,6 @@ def run(gripper_name: str, scene_index: int = 0, env_name: str = "clutter_table"
     print(f"Evaluation complete: {rate:.2%} success rate")
     print(f"Results saved to {target}")
     return report
-
-
-from ._common import cfg_get, gripper_name_from_cfg  # noqa: E402
 
 
 def main(cfg):

@@ -6,7 +6,7 @@ candidates.npz -> candidates_collision_free.npz {pose f64[N,4,4], joints[N,nj]} 
 """
 import os
 
-from ._common import candidate_dir, load_candidates, parse_kv, save_grasps, single_object_env
+from ._common import candidate_dir, cfg_get, gripper_name_from_cfg, load_candidates, object_id_from_cfg, parse_kv, save_grasps, single_object_env
 
 
 def run(gripper_name: str, object_id: str, file_dir: str | None = None):
@@ -17,9 +17,6 @@ def run(gripper_name: str, object_id: str, file_dir: str | None = None):
     print(sum(mask))
     save_grasps(os.path.join(d, "candidates_collision_free.npz"), poses[mask], joints[mask])
     return mask
-
-
-from ._common import cfg_get, gripper_name_from_cfg, object_id_from_cfg  # noqa: E402
 
 
 def main(cfg):

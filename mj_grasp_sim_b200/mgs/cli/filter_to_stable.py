@@ -9,7 +9,7 @@ the reference's two per-candidate Python loops.  Hydra is not required:
 """
 import os
 
-from ._common import candidate_dir, load_candidates, parse_kv, save_grasps, single_object_env
+from ._common import candidate_dir, cfg_get, gripper_name_from_cfg, load_candidates, object_id_from_cfg, parse_kv, save_grasps, single_object_env
 
 
 def run(gripper_name: str, object_id: str, file_dir: str | None = None, enough_stable: int = 1000):
@@ -24,9 +24,6 @@ def run(gripper_name: str, object_id: str, file_dir: str | None = None, enough_s
     save_grasps(os.path.join(where, "candidates_collision_free.npz"), *survivors)
     save_grasps(os.path.join(where, "stable_grasps.npz"), survivors[0][stable], survivors[1][stable])
     return free, stable
-
-
-from ._common import cfg_get, gripper_name_from_cfg, object_id_from_cfg  # noqa: E402
 
 
 def main(cfg):

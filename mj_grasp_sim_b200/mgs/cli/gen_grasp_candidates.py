@@ -14,7 +14,7 @@ import numpy as np
 from ..gripper.selector import get_gripper
 from ..obj.selector import get_object
 from ..sampler.antipodal import AntipodalGraspGenerator
-from ._common import parse_kv
+from ._common import cfg_get, gripper_name_from_cfg, object_id_from_cfg, parse_kv
 
 
 def run(gripper_name: str, object_id: str, num_grasps: int = 10000, output_dir: str | None = None, seed: int | None = None):
@@ -31,9 +31,6 @@ def run(gripper_name: str, object_id: str, num_grasps: int = 10000, output_dir: 
     np.savez(os.path.join(out, "candidates.npz"), pose=Hs, joints=joints)
     print("Done!")
     return Hs, joints
-
-
-from ._common import cfg_get, gripper_name_from_cfg, object_id_from_cfg  # noqa: E402
 
 
 def main(cfg):
