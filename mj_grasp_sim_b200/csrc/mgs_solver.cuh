@@ -831,8 +831,39 @@ MGS_DEVN void solve_noslip_w(Env &e) {
   const real scale = R_(1.0) / (MD.meaninertia * (nv > 1 ? nv : 1));
   real *AC = EF(efc_jar);  // 6 reals per contact: upper triangle of A_c (jar and jv are dead after Newton)
   real *T = EF(nsB);       // nv-vector scratch
+  // Starting point w of the Gauss-Seidel sweeps.  mj_solNoSlip works in force space (residual_i = sum_j AR_ij f_j + b_i) and
+  // ends with qacc = qacc_smooth + M^-1 J' f: the acceleration it reasons about is w = M^-1 J' f, what the current FORCES
+  // produce.  The primal iterate qacc - qacc_smooth equals it only when the Newton solve reached M (qacc - qacc_smooth) = J' f;
+  // on a cone-transition step of a VX300 grasp the two differed by 49 rad/s^2 on the 1e-5 kg m^2 object (found by the fp64
+  // host build vs the oracle, which restates the force-space form).
+  //   fp64 build: w = M^-1 J' f, exactly the oracle / MuJoCo formulation.
+  //   fp32 build: w = qacc - qacc_smooth.  In fp32 the Newton solve stops at a gradient floor of ~1e-6 |J' f|, and that residual
+  //   divided by such inertias is tens of rad/s^2 on EVERY step: with the force-space start 23 % of VX300 rollouts blew up
+  //   (1-lane fp32 host build vs oracle, 48 candidates), with the primal start the labels agree 48/48.  The primal iterate is
+  //   the better-conditioned value of the same quantity; the two coincide for a converged solve.
+#ifdef MGS_REAL_DOUBLE
+  #pragma unroll 1
+  PFOR(d, nv) {
+    real t = 0;
+    MGS_UNROLL_INNER
+    for (int i = 0; i < EH.nefc; i++) t += EF(J)[i * nv + d] * EF(efc_force)[i];
+    T[d] = t;
+  }
+  WSYNC();
+  #pragma unroll 1
+  PFOR(d, nv) {
+    const int lo = LDG(MD.dof_treeadr + d), hi = lo + LDG(MD.dof_treenum + d);
+    const real *Mrow = EF(Minv) + d * nv;
+    real t = 0;
+    MGS_UNROLL_INNER
+    for (int k = lo; k < hi; k++) t += Mrow[k] * T[k];
+    EF(wvec)[d] = t;
+  }
+#else
   #pragma unroll 1
   PFOR(d, nv) EF(wvec)[d] = EF(qacc)[d] - EF(qacc_smooth)[d];
+#endif
+  WSYNC();
   // B_c = M^-1 J_c' (3 x nv per contact) for the first `ncov` contacts, kept in H (nv*nv reals, free between the
   // Newton solve and the integrator): one (row, dof) per lane, M^-1 block diagonal per kinematic tree.  With B_c a
   // force change costs 3 FMAs per dof instead of a J' product plus an M^-1 product (ncu r1_i: the two were 3.6 k of

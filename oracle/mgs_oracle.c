@@ -1360,7 +1360,16 @@ static void solve_noslip(OrcSim *s) {
   double *B = (double *)malloc(sizeof(double) * (size_t)nefc * nv); /* rows: M^-1 J_i' for friction rows */
   double *w = s->w3;
   double scale = 1.0 / (m->meaninertia * (nv > 1 ? nv : 1));
-  for (int d = 0; d < nv; d++) w[d] = s->qacc[d] - s->qacc_smooth[d];
+  /* w = M^-1 J' f.  mj_solNoSlip works in force space (residual_i = sum_j AR_ij f_j + b_i with b = J qacc_smooth - aref)
+   * and ends with qacc = qacc_smooth + M^-1 J' f, so the acceleration it reasons about is the one the current FORCES
+   * produce - not the primal iterate qacc, which differs from it whenever the Newton solve stopped short of
+   * M (qacc - qacc_smooth) = J' f (on bodies with tiny inertia the gap can be tens of rad/s^2). */
+  for (int d = 0; d < nv; d++) {
+    double t = 0;
+    for (int i = 0; i < nefc; i++) t += s->J[i * nv + d] * s->efc_force[i];
+    w[d] = t;
+  }
+  chol_solve(s->L, w, nv);
   for (int i = 0; i < nefc; i++) {
     int fr = s->efc_type[i] == CT_FRICTION_DOF || (s->efc_type[i] == CT_CONTACT && i != s->con[s->efc_id[i]].efc);
     if (!fr) continue;
