@@ -19,7 +19,8 @@
  * pointers (e.g. torch tensor .data_ptr()) and a cudaStream_t passed as void*; the plain variants
  * take host pointers and perform the host<->device copies themselves (pinned staging).
  * Buffers are owned by the caller; the model handle owns only the model constants and scratch.
- * One host thread per model handle.  There is no CPU fallback: without a CUDA device every call
+ * One host thread per model handle at a time; different handles may be driven from different threads (launches are
+ * serialised internally).  There is no CPU fallback: without a CUDA device every call
  * fails with an error.
  */
 #ifndef MGS_B200_H
@@ -102,6 +103,21 @@ int mgs_step_device(MgsModel *model, int n, int nstep, const void *d_state_in, v
 /* environments of the most recent launch on this model that dropped contacts for lack of capacity
  * (synchronises the device); re-run with larger capacities if non-zero and exactness matters */
 int mgs_overflow_count(MgsModel *model);
+
+/* Per-candidate auxiliary results of the most recent launch on this model (synchronises the device): 4 floats per candidate -
+ * [0] flags: bit 0 = the environment dropped contacts / constraint rows for lack of capacity (its label was computed on a
+ *     truncated contact set: re-run it on a model created with larger capacities), bit 1 = the state blew up (label False);
+ * [1], [2] stability rollouts: displacement [m] and rotation [deg] of the grasped object over the close phase - what the
+ *     reference computes as positional / rotational drift (mgs/env/gravityless_object_grasping.py:175-200) - NaN when the
+ *     candidate lost contact before that point; [3] reserved (0). */
+int mgs_last_aux(MgsModel *model, int n, float *aux_out);
+
+/* mgs_step_*: clamp qvel to [-clip, clip] before every step (ClutterTableEnv.gen_clutter does that around each mj_step,
+ * mgs/env/clutter_table.py:215-221); 0 switches it off (default) */
+int mgs_set_qvel_clip(MgsModel *model, double clip);
+
+/* identifies the sources this library was built from (sha256 prefix of csrc/ + include/, set by lib.build()) */
+const char *mgs_build_stamp(void);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 long long mgs_launch_count(void);

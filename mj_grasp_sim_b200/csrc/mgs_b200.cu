@@ -4,8 +4,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/mgs_b200.h"
 #include "mgs_model_build.h"
@@ -17,7 +19,17 @@
 
 // ---------------------------------------------------------------------------------- host side
 static thread_local std::string g_err;
-static long long g_launches = 0;
+static std::atomic<long long> g_launches{0};
+// One lock for everything that touches per-kernel-variant global state: the variant's __constant__ block (rewritten per
+// launch), its dynamic-shared-memory attribute (per kernel function, so shared by all models on the variant) and the
+// per-device "previous launch finished" events.  Host threads may call into different model handles concurrently
+// (ctypes releases the GIL); launches are enqueued under the lock, they do not execute under it.
+static std::mutex g_launch_mu;
+static std::vector<cudaEvent_t> g_last_done;  // [device], created on first use, never destroyed
+static std::vector<char> g_have_last;
+#ifndef MGS_BUILD_STAMP
+#define MGS_BUILD_STAMP "unstamped"
+#endif
 
 static int fail(const std::string &msg) { g_err = msg; return -1; }
 #define CU(call)                                                                                  \
@@ -38,11 +50,15 @@ struct MgsModel {
   // staging for the host-pointer entry points (grown on demand)
   void *d_stage, *h_stage;
   size_t stage_bytes;
+  float *d_aux;  // [aux_cap][4] per-candidate auxiliary results of the most recent rollout launch (flags, drift)
+  int aux_cap, aux_n;
+  double qvel_clip;
   cudaStream_t stream;
 };
 
 extern "C" const char *mgs_last_error(void) { return g_err.c_str(); }
-extern "C" long long mgs_launch_count(void) { return g_launches; }
+extern "C" long long mgs_launch_count(void) { return g_launches.load(); }
+extern "C" const char *mgs_build_stamp(void) { return MGS_BUILD_STAMP; }
 
 extern "C" int mgs_model_create(const MgsModelDesc *desc, int device, MgsModel **out) {
   return mgs_model_create_ex(desc, device, 0, 0, out);
@@ -57,10 +73,14 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
   ModelBlob blob;
   std::string err;
   if (!build_model_blob(desc, blob, err)) return fail("model: " + err);
-  if (ncon_max > 0) blob.ncon_max = ncon_max;
+  if (ncon_max > 0) {
+    blob.ncon_max = (ncon_max + 3) & ~3;
+    blob.nefc_max = blob.rows_static + blob.ncon_max * blob.rows_per_contact;  // the default for this contact capacity
+  }
   if (nefc_max > 0) blob.nefc_max = nefc_max;
-  if (blob.ncon_max > 64 || blob.nefc_max < desc->nv || 6 * blob.ncon_max > 2 * blob.nefc_max)
-    return fail("bad contact capacities (need ncon_max <= 64 and nefc_max >= 3 * ncon_max)");
+  if (blob.ncon_max > 64 || blob.nefc_max < desc->nv || 6 * blob.ncon_max > 2 * blob.nefc_max ||
+      blob.nefc_max < blob.dm.ne_rows + blob.dm.nf_rows)
+    return fail("bad contact capacities (need ncon_max <= 64, nefc_max >= 3 * ncon_max and room for the equality / dof-friction rows)");
   MgsModel *M = new MgsModel();
   memset(M, 0, sizeof(*M));
   M->device = device;
@@ -84,6 +104,7 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
   // 12-warp variant (more registers per thread) takes over.
   const char *force_wpb = getenv("MGS_WARPS_PER_BLOCK");  // tuning knobs: force the CTA size / the variant
   const char *force_var = getenv("MGS_KERNEL_VARIANT");
+  std::lock_guard<std::mutex> lock(g_launch_mu);  // the occupancy sweep changes the variants' shared-memory attribute
   const MgsKernelOps *variants[2] = {mgs_kernel_ops_w16(), mgs_kernel_ops_w12()};
   int best_warps = 0;
   for (int v = 0; v < 2; v++) {
@@ -103,7 +124,7 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
   }
   if (best_warps == 0) { delete M; return fail("kernel does not fit on this device"); }
   M->smem_per_block = env_bytes * M->warps_per_block;
-  CU(M->ops->prepare(M->smem_per_block));
+  // (the attribute is set again before every launch: it belongs to the kernel function, not to this model)
   M->state_stride = desc->nq + 2 * desc->nv + desc->nu + 7 * desc->nmocap;
   M->diag_stride = mgs_diag_stride(desc->nv, desc->nbody, blob.ncon_max, blob.nefc_max);
   CU(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
@@ -116,6 +137,7 @@ extern "C" void mgs_model_destroy(MgsModel *M) {
   cudaSetDevice(M->device);
   cudaFree(M->d_blob);
   cudaFree(M->d_counter);
+  if (M->d_aux) cudaFree(M->d_aux);
   if (M->d_stage) cudaFree(M->d_stage);
   if (M->h_stage) cudaFreeHost(M->h_stage);
   if (M->stream) cudaStreamDestroy(M->stream);
@@ -129,6 +151,22 @@ extern "C" int mgs_overflow_count(MgsModel *M) {
       cudaMemcpy(v, M->d_counter, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess)
     return fail("mgs_overflow_count: CUDA error");
   return (int)v[1];
+}
+
+extern "C" int mgs_last_aux(MgsModel *M, int n, float *aux_out) {
+  if (!M || !aux_out) return fail("null argument");
+  if (n > M->aux_n) return fail("mgs_last_aux: the most recent launch had fewer candidates");
+  if (n <= 0) return 0;
+  if (cudaSetDevice(M->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpy(aux_out, M->d_aux, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail("mgs_last_aux: CUDA error");
+  return 0;
+}
+
+extern "C" int mgs_set_qvel_clip(MgsModel *M, double clip) {
+  if (!M) return fail("null model");
+  M->qvel_clip = clip > 0 ? clip : 0;
+  return 0;
 }
 
 extern "C" int mgs_model_info(const MgsModel *M, MgsModelInfo *info) {
@@ -146,7 +184,16 @@ static int launch(MgsModel *M, const RolloutParams &prm, const BatchIO &io_in, c
   if (prm.n <= 0) return 0;
   BatchIO io = io_in;
   io.work_counter = M->d_counter;
-  CU(cudaMemsetAsync(M->d_counter, 0, 2 * sizeof(unsigned int), st));
+  if (prm.n > M->aux_cap) {
+    CU(cudaDeviceSynchronize());
+    if (M->d_aux) cudaFree(M->d_aux);
+    M->d_aux = nullptr; M->aux_cap = 0;
+    const int cap = (prm.n + 1023) & ~1023;
+    CU(cudaMalloc(&M->d_aux, (size_t)cap * 4 * sizeof(float)));
+    M->aux_cap = cap;
+  }
+  io.aux = M->d_aux;
+  M->aux_n = prm.n;
   // Wave quantisation: every candidate of a batch costs about the same, so what matters is the number of
   // "waves" of resident environments.  If fewer warps per CTA give the same number of waves, use fewer: each
   // environment then shares its SM with fewer neighbours (4096 candidates: 2 waves of 14 warps/SM beat
@@ -161,18 +208,22 @@ static int launch(MgsModel *M, const RolloutParams &prm, const BatchIO &io_in, c
   int blocks_needed = (prm.n + wpb - 1) / wpb;
   int grid = M->num_sms * M->blocks_per_sm;
   if (grid > blocks_needed) grid = blocks_needed;
-  // the constants of this launch (model pointers, layout, parameters, I/O) go to __constant__ memory,
-  // stream-ordered; wait for the previous launch on this device before overwriting them
-  static cudaEvent_t last_done[64];  // one per device, created once, never destroyed
-  static bool have_last[64];
-  if (!have_last[M->device]) CU(cudaEventCreateWithFlags(&last_done[M->device], cudaEventDisableTiming));
-  else CU(cudaStreamWaitEvent(st, last_done[M->device], 0));
-  have_last[M->device] = true;
+  // The constants of this launch (model pointers, layout, parameters, I/O) go to the variant's __constant__ block,
+  // stream-ordered: the stream first waits for the previous launch on this device (any model, any stream), THEN resets this
+  // model's work queue / overflow counter, sets the variant's shared-memory attribute for this model and launches.
+  std::lock_guard<std::mutex> lock(g_launch_mu);
+  if ((size_t)M->device >= g_last_done.size()) { g_last_done.resize(M->device + 1); g_have_last.resize(M->device + 1, 0); }
+  if (!g_have_last[M->device]) {
+    CU(cudaEventCreateWithFlags(&g_last_done[M->device], cudaEventDisableTiming));
+    g_have_last[M->device] = 1;
+  } else CU(cudaStreamWaitEvent(st, g_last_done[M->device], 0));
+  CU(cudaMemsetAsync(M->d_counter, 0, 2 * sizeof(unsigned int), st));
+  CU(M->ops->prepare(M->smem_per_block));
   KernelConsts kc;
   kc.m = M->dm; kc.L = M->L; kc.prm = prm; kc.io = io;
   CU(M->ops->launch(&kc, grid, wpb * 32, (size_t)(M->smem_per_block / M->warps_per_block) * wpb, st));
   g_launches++;
-  CU(cudaEventRecord(last_done[M->device], st));
+  CU(cudaEventRecord(g_last_done[M->device], st));
   return 0;
 }
 
@@ -297,7 +348,7 @@ extern "C" int mgs_step_device(MgsModel *M, int n, int nstep, const void *d_stat
   CU(cudaSetDevice(M->device));
   RolloutParams prm;
   memset(&prm, 0, sizeof(prm));
-  prm.mode = MGS_MODE_STEP; prm.n = n; prm.nstep = nstep;
+  prm.mode = MGS_MODE_STEP; prm.n = n; prm.nstep = nstep; prm.qvel_clip = (real)M->qvel_clip;
   BatchIO io;
   memset(&io, 0, sizeof(io));
   io.state_in = (const real *)d_state_in; io.state_out = (real *)d_state_out; io.diag_out = (real *)d_diag_out;

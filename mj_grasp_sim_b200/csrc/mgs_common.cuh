@@ -47,8 +47,8 @@ typedef float real;
 // (ncu r1_a / r1_c: "no instruction" = 12-17 of the 18-24 stall cycles per issue).  One CTA per SM whose
 // warps enter every stage together share the fetches.  The barriers carry no data dependency (warps
 // never touch each other's environment); they only align code position, and every warp executes the
-// same number of them per step, whatever its contact count or solver path.  -DMGS_NO_STAGE_BARRIER
-// turns them off for A/B measurements.
+// same number of them per step, whatever its contact count or solver path.  -DMGS_BAR_MASK=0 turns
+// them off for A/B measurements.
 // MGS_BAR_MASK selects which of the six per-step barriers are compiled in (bit k = barrier k):
 // 0 step start, 1 before collision, 2 after collision, 3 after constraint assembly, 4 after Newton,
 // 5 before integration.
@@ -171,6 +171,7 @@ static inline void layout_compute(Layout *L, int nq, int nv, int nu, int nbody, 
 struct RolloutParams {
   int mode, n, nj, base_qposadr, nstep, nstep_close, nstep_lift, shake_steps, repose_on_close;
   real lift_dist, shake_dist;
+  real qvel_clip;  // MGS_MODE_STEP only: clamp qvel to +-qvel_clip before every step (0 = off); clutter_table.py:215-221
   int joint_qposadr[MGS_MAX_NJ];
   real close_ctrl[MGS_MAX_NU];
 };
@@ -187,6 +188,8 @@ struct BatchIO {
   const real *state_in;
   real *state_out;
   real *diag_out;  // optional [n][diag_stride]: ncon, nefc, niter, then contacts/qacc (tests)
+  float *aux;      // optional [n][4]: flags (bit 0 capacity overflow, bit 1 state blew up), object drift over the close phase
+                   // (position [m], rotation [deg]; gravityless_object_grasping.py:175-200), reserved
   int state_stride, diag_stride;
   unsigned int *work_counter;
 };

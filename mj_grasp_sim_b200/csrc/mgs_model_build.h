@@ -12,6 +12,7 @@ struct ModelBlob {
   std::vector<char> bytes;
   DevModel dm;  // pointers hold byte OFFSETS until rebase()
   int ncon_max, nefc_max;
+  int rows_static, rows_per_contact;  // nefc_max default = rows_static + ncon_max * rows_per_contact
 };
 
 namespace mgs_detail {
@@ -164,7 +165,9 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
   if (nv > 24 && nfreeobj <= 1) nc = 32;
   nc = (nc + 3) & ~3;
   out.ncon_max = nc;
-  out.nefc_max = ne + nfr + nlim + nc * (maxdim < 3 ? 3 : maxdim);  // every contact slot can hold the largest cone
+  out.rows_static = ne + nfr + nlim;
+  out.rows_per_contact = maxdim < 3 ? 3 : maxdim;
+  out.nefc_max = out.rows_static + nc * out.rows_per_contact;  // every contact slot can hold the largest cone
   return true;
 }
 

@@ -34,7 +34,16 @@ MGS_DEVN void reset_w(Env &e) {
 
 // set_qpos(joints) + set_pose(base): simualtion.py:45-49, gripper/base.py:48-59
 MGS_DEVN void place_w(Env &e, const float *pose7, const float *joints) {
-  if (joints) PFOR(k, PRM.nj) EF(qpos)[PRM.joint_qposadr[k]] = (real)LDG(joints + k);
+  // `data.qpos[idxs] = qpos` is a sequential scatter: when two entries of idxs name the same address (Robotiq's two misnamed
+  // joints both resolve to the object's x, robotiq2f85.py:275,279) the LAST one wins.  One lane writes them in order.
+  if (joints) {
+    #pragma unroll 1
+    PFOR(one, 1) {
+      #pragma unroll 1
+      for (int k = 0; k < PRM.nj; k++) EF(qpos)[PRM.joint_qposadr[k]] = (real)LDG(joints + k);
+    }
+    WSYNC();
+  }
   #pragma unroll 1
   PFOR(k, 7) {
     real v = (real)LDG(pose7 + k);
@@ -60,11 +69,35 @@ MGS_DEVN int ramp_w(Env &e, const real *start, const real *target, int n, int ch
   return 0;
 }
 
-MGS_DEVN int stability_program_w(Env &e, const float *pose7, const float *joints, int *steps) {
+// qpos address of the grasped object's free joint: the object fragment comes last in the scene template, so it is the last joint
+MGS_DEV int object_qposadr() {
+  const int j = MD.njnt - 1;
+  return (j >= 0 && LDG(MD.jnt_type + j) == JNT_FREE) ? LDG(MD.jnt_qposadr + j) : -1;
+}
+
+// object drift over the close phase (gravityless_object_grasping.py:175-200; get_object_transform casts to float32):
+// |dp| and the rotation angle acos(2 <q0,q1>^2 - 1) in degrees
+MGS_DEV void drift_w(const Env &e, const real *before, float *out) {
+  const int a = object_qposadr();
+  if (a < 0 || !out) return;
+  float dp = 0, dot = 0;
+  for (int k = 0; k < 3; k++) { const float d = (float)before[k] - (float)EF(qpos)[a + k]; dp += d * d; }
+  for (int k = 3; k < 7; k++) dot += (float)before[k] * (float)EF(qpos)[a + k];
+  dot = fminf(1.0f, fmaxf(-1.0f, dot));
+  const float ang = acosf(fminf(1.0f, fmaxf(-1.0f, 2.0f * dot * dot - 1.0f)));
+  if (MGS_LANE == 0) { out[0] = sqrtf(dp); out[1] = ang * 57.29577951308232f; }
+}
+
+MGS_DEVN int stability_program_w(Env &e, const float *pose7, const float *joints, int *steps, float *drift) {
   reset_w(e);
   place_w(e, pose7, joints);
   forward_w(e);
   MGS_STAGE_BARRIER(5);  // the integrate slot of a step (keeps the CTA stage-aligned)
+  real obj0[7] = {0, 0, 0, 1, 0, 0, 0};
+  {
+    const int a = object_qposadr();
+    if (a >= 0) for (int k = 0; k < 7; k++) obj0[k] = EF(qpos)[a + k];
+  }
   // close_gripper_at (panda.py:225-241 and the five siblings): mocap <- pose, ctrl <- close signal
   if (PRM.repose_on_close) place_w(e, pose7, (const float *)0);
   #pragma unroll 1
@@ -74,6 +107,7 @@ MGS_DEVN int stability_program_w(Env &e, const float *pose7, const float *joints
   WSYNC();
   if (step_w(e, PRM.nstep_close, steps)) return 0;
   if (!contact_with_object_w(e, 0)) return 0;
+  drift_w(e, obj0, drift);
   // lift (:205-226)
   real start[3], target[3];
   copy3(start, EF(mocap));
@@ -204,11 +238,20 @@ MGS_DEVN void run_env_w(Env &e, int env) {
     PFOR(i, 7 * MD.nmocap) out[MD.nq + 2 * MD.nv + MD.nu + i] = EF(mocap)[i];
     if (IO.diag_out) write_diag_w(e, IO.diag_out + (size_t)env * IO.diag_stride);
     #pragma unroll 1
-    PFOR(k, 1) { if (IO.labels) IO.labels[env] = (uint8_t)(EH.bad ? 0 : 1); if (IO.steps) IO.steps[env] = steps; }
+    PFOR(k, 1) {
+      if (IO.labels) IO.labels[env] = (uint8_t)(EH.bad ? 0 : 1);
+      if (IO.steps) IO.steps[env] = steps;
+      if (IO.aux) { float *a = IO.aux + 4 * (size_t)env; a[0] = (float)((EH.overflow ? 1 : 0) | (EH.bad ? 2 : 0)); a[1] = a[2] = a[3] = 0; }
+#ifndef MGS_HOST
+      if (EH.overflow) atomicAdd(IO.work_counter + 1, 1u);
+#endif
+    }
     WSYNC();
     return;
   }
   const float *pose7 = IO.pose7 + (size_t)env * 7, *joints = IO.joints + (size_t)env * PRM.nj;
+  float *aux = IO.aux ? IO.aux + 4 * (size_t)env : (float *)0;
+  if (aux && MGS_LANE == 0) { aux[1] = nanf(""); aux[2] = nanf(""); aux[3] = 0; }
   int label;
   if (PRM.mode == MGS_MODE_COLLISION) {
     reset_w(e);
@@ -226,12 +269,13 @@ MGS_DEVN void run_env_w(Env &e, int env) {
   } else if (PRM.mode == MGS_MODE_CLUTTER_STABLE) {
     label = clutter_stable_program_w(e, pose7, joints, &steps);
   } else {
-    label = stability_program_w(e, pose7, joints, &steps);
+    label = stability_program_w(e, pose7, joints, &steps, aux ? aux + 1 : (float *)0);
   }
   #pragma unroll 1
   PFOR(k, 1) {
     IO.labels[env] = (uint8_t)label;
     if (IO.steps) IO.steps[env] = steps;
+    if (aux) aux[0] = (float)((EH.overflow ? 1 : 0) | (EH.bad ? 2 : 0));
 #ifndef MGS_HOST
     if (EH.overflow) atomicAdd(IO.work_counter + 1, 1u);
 #endif

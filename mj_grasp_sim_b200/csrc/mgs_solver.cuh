@@ -165,6 +165,10 @@ MGS_DEVN void make_constraint_w(Env &e) {
       cnt_base += total;
     }
     nl = cnt_base;
+    if (ne + nf + nl > LY.nefc_max) {  // limit rows that did not fit were dropped above: flag it and keep the row count in range
+      if (MGS_LANE == 0) EH.overflow += 1;
+      nl = LY.nefc_max - ne - nf;
+    }
   }
   const int row_con0 = ne + nf + nl;
   // contact rows: prefix sum of condim over contacts (capacity-limited)
@@ -1075,6 +1079,11 @@ MGS_DEVN void integrate_w(Env &e) {
 MGS_DEVN int step_w(Env &e, int nstep, int *steps_done) {
   #pragma unroll 1
   for (int k = 0; k < nstep; k++) {
+    if (PRM.qvel_clip > 0) {  // scene generation clamps qvel before every step (clutter_table.py:215-221); MGS_MODE_STEP only
+      #pragma unroll 1
+      PFOR(i, MD.nv) EF(qvel)[i] = fmax(-PRM.qvel_clip, fmin(PRM.qvel_clip, EF(qvel)[i]));
+      WSYNC();
+    }
     if (EH.bad || bad_state_w(e, 0)) { EH.bad = 1; return 1; }
     forward_w(e);
     MGS_STAGE_BARRIER(5);

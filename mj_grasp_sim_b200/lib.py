@@ -36,19 +36,40 @@ class MgsError(RuntimeError):
 
 
 def _sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + [
         os.path.join(os.path.dirname(_PKG), "include", f) for f in ("mgs_b200.h", "mgs_model_desc.h")]
+
+
+def source_stamp() -> str:
+    """sha256 prefix over the library's sources (csrc/ + include/): compiled into the .so as mgs_build_stamp() so that a test
+    can tell a stale prebuilt library from one built from the checked-out tree."""
+    import hashlib
+    h = hashlib.sha256()
+    for s in _sources():
+        h.update(os.path.basename(s).encode())
+        h.update(open(s, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def _built_stamp(so: str) -> str:
+    try:
+        return open(so + ".stamp").read().strip()
+    except OSError:
+        return ""
 
 
 def build(force: bool = False, f64: bool = False) -> str:
     """Compile csrc/mgs_b200.cu -> libmgs_b200.so (sm_100a).  Cross-compiles without a GPU."""
     so = SO_PATH_F64 if f64 else SO_PATH
-    if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in _sources()):
+    stamp = source_stamp()
+    if not force and os.path.exists(so) and _built_stamp(so) == stamp:
         return so
     # two translation units = two variants of the rollout kernel (16 / 12 warps per CTA, see csrc/mgs_kernel_ops.h)
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-DMGS_REAL_DOUBLE"] if f64 else []) + ["-o", so, os.path.join(CSRC, "mgs_b200.cu"),
-                                                                             os.path.join(CSRC, "mgs_kernel_w12.cu")]
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-DMGS_REAL_DOUBLE"] if f64 else []) + [f'-DMGS_BUILD_STAMP="{stamp}"', "-o", so,
+                                                                             os.path.join(CSRC, "mgs_b200.cu"), os.path.join(CSRC, "mgs_kernel_w12.cu")]
     subprocess.check_call(cmd)
+    with open(so + ".stamp", "w") as f:
+        f.write(stamp)
     return so
 
 
@@ -61,6 +82,8 @@ def bind(L, prefix="mgs_"):
     g("model_destroy").restype = None
     g("model_info").argtypes = [vp, C.POINTER(MgsModelInfo)]
     g("step_host").argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    g("last_aux").argtypes = [vp, C.c_int, fp]
+    g("set_qvel_clip").argtypes = [vp, C.c_double]
     if prefix == "mgs_":
         L.mgs_model_create.argtypes = [C.POINTER(MgsModelDesc), C.c_int, C.POINTER(vp)]
         L.mgs_model_create_ex.argtypes = [C.POINTER(MgsModelDesc), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
@@ -72,6 +95,7 @@ def bind(L, prefix="mgs_"):
         L.mgs_clutter_stable_mask.argtypes = [vp, C.c_int, dp, fp, fp, C.c_int, ip, C.c_int, dp, C.POINTER(MgsRolloutCfg), u8p, ip]
         L.mgs_launch_count.restype = C.c_longlong
         L.mgs_overflow_count.argtypes = [vp]
+        L.mgs_build_stamp.restype = C.c_char_p
     else:
         L.l1_model_create.argtypes = [C.POINTER(MgsModelDesc), C.POINTER(vp)]
         L.l1_rollout_host.argtypes = [vp, C.c_int, C.c_int, fp, fp, C.c_int, ip, C.c_int, dp, C.POINTER(MgsRolloutCfg), u8p, ip]
@@ -108,6 +132,7 @@ class BatchSim:
     def __init__(self, model, device: int = 0, f64: bool = False, lib=None, prefix: str = "mgs_", ncon_max: int = 0, nefc_max: int = 0,
                  ground_name: str = "geom:ground"):
         self.model = model
+        self.device = device
         self.L = lib if lib is not None else load(f64)
         self.p = prefix
         self.desc, self._keep = make_desc(model, ground_name)
@@ -259,6 +284,19 @@ class BatchSim:
                                         C.byref(cfg), _u8(out), _ip(steps))
         self._check(rc)
         return out.astype(bool), steps
+
+    def last_aux(self, n: int):
+        """Per-candidate auxiliary results of the most recent launch: dict(overflow bool[n], bad bool[n], pos_drift f32[n],
+        rot_drift_deg f32[n]) - see mgs_last_aux in include/mgs_b200.h."""
+        a = np.zeros((n, 4), dtype=np.float32)
+        if n:
+            self._check(self._f("last_aux")(self.h, n, _fp(a)))
+        fl = a[:, 0].astype(np.int32)
+        return dict(overflow=(fl & 1).astype(bool), bad=(fl & 2).astype(bool), pos_drift=a[:, 1].copy(), rot_drift_deg=a[:, 2].copy())
+
+    def set_qvel_clip(self, clip: float):
+        """step(): clamp qvel to +-clip before every step (scene generation); 0 = off."""
+        self._check(self._f("set_qvel_clip")(self.h, float(clip)))
 
     def overflow_count(self) -> int:
         """Environments of the last launch that dropped contacts (capacity too small)."""

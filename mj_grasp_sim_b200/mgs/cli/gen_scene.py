@@ -41,45 +41,78 @@ def gen_stable_scene(gripper_name, object_ids, env_name="clutter_table", seed=No
     return scene_dict
 
 
+class GraspTable:
+    """Column store of world-frame grasp candidates of one scene: pose[N,4,4], joints[N,nj] and, per row, the index of the
+    object the grasp was generated for (`owner`, into `objects` = [(name, id), ...])."""
+
+    def __init__(self, pose, joints, owner, objects):
+        self.pose, self.joints, self.owner, self.objects = pose, joints, owner, objects
+
+    @classmethod
+    def from_scene(cls, env, source):
+        """`source(object_id) -> (pose[N,4,4] in the object frame, joints[N,nj])`; rows are moved to the world frame with the
+        object's settled pose (gen_scene.py:58-60).  Objects without candidates do not get an owner slot."""
+        cols, objects = ([], [], []), []
+        for name, oid in zip(env.object_names, env.object_ids):
+            pose, joints = source(oid)
+            if len(pose) == 0:
+                continue
+            cols[0].append((env.get_obj_pose(name) @ SE3Pose.from_mat(np.array(pose, copy=True))).to_mat())
+            cols[1].append(np.asarray(joints))
+            cols[2].append(np.full(len(pose), len(objects), dtype=np.int32))
+            objects.append((name, oid))
+        if not objects:
+            raise ValueError("No collision free grasps")
+        return cls(*(np.concatenate(c) for c in cols), objects)
+
+    def __len__(self):
+        return len(self.pose)
+
+    def take(self, sel, move_owner=True):
+        """rows `sel` (mask or index array).  move_owner=False leaves the owner column in its old order - only meaningful for
+        a permutation, see `filter_grasps(reference_index_quirk=True)`."""
+        return GraspTable(self.pose[sel], self.joints[sel], self.owner[sel] if move_owner else self.owner, self.objects)
+
+    def se3(self):
+        return SE3Pose.from_mat(np.array(self.pose, copy=True), type="wxyz")
+
+    def per_object(self):
+        for k in np.unique(self.owner):
+            rows = self.owner == k
+            name, oid = self.objects[k]
+            yield k, {"object_id": oid, "object_name": name, "pose": self.pose[rows], "joints": self.joints[rows]}
+
+
 def filter_grasps(gripper_name, scene_def, env_name="clutter_table", grasps=None, only_collision_free=False, save_collision_grasps=False,
-                  enough_collision_free=128, rng=None):
+                  enough_collision_free=128, rng=None, reference_index_quirk=False):
+    """Per-scene filtering (gen_scene.py:48-172): collision mask over every object's candidates, then (unless
+    `only_collision_free`) the close+lift rollout on a random permutation of the survivors with
+    enough_stable = min(128, 32 * num_objects).  Returns (per-object survivors, per-object colliding candidates).
+
+    Known reference defect, NOT reproduced by default: the reference permutes poses and joints but its statement for the
+    object-index column is a comparison, not an assignment (gen_scene.py:113), so stable grasps are filed under the object
+    whose row they landed on after the shuffle.  `reference_index_quirk=True` reproduces that attribution bit for bit."""
     env = get_env_from_dict(env_name, deepcopy(scene_def))
-    num_objects = len(env.object_names)
-    all_poses, all_joints, obj_indices, obj_map = [], [], [], []
-    for obj_name, obj_id in zip(env.object_names, env.object_ids):
-        poses, joints = grasps[obj_id] if grasps is not None else get_grasps(gripper_name, obj_id)
-        if len(poses) == 0:
-            continue
-        world = (env.get_obj_pose(obj_name) @ SE3Pose.from_mat(deepcopy(poses))).to_mat()
-        all_poses.append(world); all_joints.append(joints)
-        obj_indices.append(np.full(len(world), len(obj_map), dtype=np.int32))
-        obj_map.append((obj_name, obj_id))
-    if len(all_poses) == 0:
-        raise ValueError("No collision free grasps")
-    all_poses, all_joints, obj_indices = np.concatenate(all_poses), np.concatenate(all_joints), np.concatenate(obj_indices)
-    free = env.grasp_collision_mask(SE3Pose.from_mat(deepcopy(all_poses), type="wxyz"), deepcopy(all_joints))
-    if sum(free) < enough_collision_free:
+    table = GraspTable.from_scene(env, (lambda oid: grasps[oid]) if grasps is not None else (lambda oid: get_grasps(gripper_name, oid)))
+    free = np.asarray(env.grasp_collision_mask(table.se3(), np.array(table.joints, copy=True)), dtype=bool)
+    if int(free.sum()) < enough_collision_free:
         raise ValueError("Not enough collision free grasps!")
-    res_p, res_j, res_i = all_poses[free], all_joints[free], obj_indices[free]
+    keep, colliding = table.take(free), table.take(~free)
     if not only_collision_free:
-        perm = (rng or np.random.default_rng()).permutation(len(res_p))
-        res_p, res_j, res_i = res_p[perm], res_j[perm], res_i[perm]
-        enough_stable = min(128, num_objects * 32)
-        stable = env.grasp_stable_mask(SE3Pose.from_mat(deepcopy(res_p), type="wxyz"), deepcopy(res_j),
-                                       deepcopy(scene_def["env_state"]["state"]), enough_stable=enough_stable)
-        if sum(stable) < enough_stable:
+        keep = keep.take((rng or np.random.default_rng()).permutation(len(keep)), move_owner=not reference_index_quirk)
+        want = min(128, 32 * len(env.object_names))
+        stable = np.asarray(env.grasp_stable_mask(keep.se3(), np.array(keep.joints, copy=True), deepcopy(scene_def["env_state"]["state"]),
+                                                  enough_stable=want), dtype=bool)
+        if int(stable.sum()) < want:
             raise ValueError("Not enough stable grasps!")
-        res_p, res_j, res_i = res_p[stable], res_j[stable], res_i[stable]
-    result, neg_result = [], []
-    for k in np.unique(res_i):
-        m = res_i == k
-        name, oid = obj_map[k]
-        result.append({"object_id": oid, "object_name": name, "pose": res_p[m], "joints": res_j[m]})
-        if save_collision_grasps:
-            cm = obj_indices[~free] == k
-            if sum(cm) > 0:
-                neg_result.append({"object_id": oid, "object_name": name, "pose": all_poses[~free][cm], "joints": all_joints[~free][cm]})
-    return result, neg_result
+        keep = keep.take(stable)
+    valid, invalid = [], []
+    rejected = dict(colliding.per_object()) if save_collision_grasps else {}
+    for k, entry in keep.per_object():
+        valid.append(entry)
+        if k in rejected:  # only objects that kept at least one grasp get a "_collision" file (:150-160)
+            invalid.append(rejected[k])
+    return valid, invalid
 
 
 def run(gripper_name, object_ids, env_name="clutter_table", seed=None, grasps=None, output_dir=None, **kw):

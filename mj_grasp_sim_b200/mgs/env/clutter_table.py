@@ -16,8 +16,9 @@ import numpy as np
 from ... import scenes
 from ...compiler.mjcf import compile_mjcf
 from ...lib import BatchSim, MgsRolloutCfg
-from ...shard import apply_enough_stable
+from ...shard import evaluate_sharded
 from ..core.simualtion import MjSimulation
+from .gravityless_object_grasping import EscalatingSim
 from ..util.geo.transforms import SE3Pose
 
 XML = scenes.CLUTTER_XML  # same options / body order as the reference template (:41-79), lights and camera element dropped
@@ -38,63 +39,25 @@ class ClutterTableEnv(MjSimulation):
         self.env_defintion = {"model_xml": self.model_xml, "assets": {**self.gripper_assets, **self.objs_assets}}
         self.model = compile_mjcf(self.model_xml, self.env_defintion["assets"])
         self._device, self._caps, self._sim = device, (ncon_max, nefc_max), None
-        self._record = scenes.record_from_model(self.model)
-        self._time = 0.0
+        self._esc = EscalatingSim(self._make_sim)
+        self._init_state()
+
+    GROUND_GEOM = "geom:table"
+
+    def _make_sim(self, caps):
+        if caps is None:
+            return self.sim
+        return BatchSim(self.model, device=self.sim.device, ncon_max=caps[0], nefc_max=caps[1], ground_name=self.GROUND_GEOM)
 
     @property
-    def sim(self) -> BatchSim:
-        if self._sim is None:
-            dev = self._device
-            if dev is None:
-                import torch
-                dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
-            self._sim = BatchSim(self.model, device=dev, ncon_max=self._caps[0], nefc_max=self._caps[1], ground_name="geom:table")
-        return self._sim
-
-    # ---- state in MuJoCo's mjSTATE_INTEGRATION layout ---------------------------------------
-    def _layout(self):
-        m = self.model
-        nq, nv, nu, nb, neq = m.nq, m.nv, m.nu, m.nbody, int(m.arr["neq"])
-        o_qpos, o_qvel = 1, 1 + nq
-        o_ws = o_qvel + nv  # act is empty
-        o_ctrl = o_ws + nv
-        o_applied = o_ctrl + nu
-        o_xfrc = o_applied + nv
-        o_eq = o_xfrc + 6 * nb
-        o_mpos = o_eq + neq
-        return dict(qpos=o_qpos, qvel=o_qvel, ws=o_ws, ctrl=o_ctrl, eq=o_eq, mpos=o_mpos, size=o_mpos + 7)
-
-    def get_state(self) -> np.ndarray:
-        m, L = self.model, self._layout()
-        nq, nv, nu = m.nq, m.nv, m.nu
-        st = np.zeros(L["size"])
-        st[0] = self._time
-        r = self._record
-        st[L["qpos"]:L["qpos"] + nq] = r[:nq]
-        st[L["qvel"]:L["qvel"] + nv] = r[nq:nq + nv]
-        st[L["ws"]:L["ws"] + nv] = r[nq + nv:nq + 2 * nv]
-        st[L["ctrl"]:L["ctrl"] + nu] = r[nq + 2 * nv:nq + 2 * nv + nu]
-        st[L["eq"]:L["eq"] + int(m.arr["neq"])] = 1.0
-        st[L["mpos"]:L["mpos"] + 7] = r[nq + 2 * nv + nu:]
-        return st
-
-    def _record_from_state(self, state) -> np.ndarray:
-        m, L = self.model, self._layout()
-        nq, nv, nu = m.nq, m.nv, m.nu
-        state = np.asarray(state, dtype=np.float64)
-        if state.shape != (L["size"],):
-            raise ValueError(f"state has {state.shape} entries, mjSTATE_INTEGRATION of this model has {L['size']}")
-        return np.concatenate([state[L["qpos"]:L["qpos"] + nq], state[L["qvel"]:L["qvel"] + nv], state[L["ws"]:L["ws"] + nv],
-                               state[L["ctrl"]:L["ctrl"] + nu], state[L["mpos"]:L["mpos"] + 7]])
-
-    def set_state(self, state):
-        self._record = self._record_from_state(state)
-        self._time = float(np.asarray(state)[0])
+    def last_overflow(self):
+        return self._esc.last_overflow
 
     # ---- scene generation (single-environment launches) -------------------------------------
     def _step(self, rec, nstep):
         out = self.sim.step(rec[None].astype(self.sim.real), nstep)
         self._time += nstep * float(self.model.opt["timestep"])
+        self._diag = None
         return out[0].astype(np.float64)
 
     def set_gripper_pose(self, pos):
@@ -109,7 +72,11 @@ class ClutterTableEnv(MjSimulation):
         info = dict(base_qposadr=self.gripper.get_freejoint_idxs(self)[0],
                     object_qposadr=[int(self.model.jnt_qposadr[self.model.names["joint"][f"{n}:joint"]]) for n in self.object_names])
         sd = int(np.random.randint(1 << 30)) if seed is None else seed
-        self._record = scenes.gen_clutter(self.model, info, self._step, sd)
+        self.sim.set_qvel_clip(50.0)  # the reference clamps qvel before EVERY step of the drop / settle phases (:215-221)
+        try:
+            self._record = scenes.gen_clutter(self.model, info, self._step, sd)
+        finally:
+            self.sim.set_qvel_clip(0.0)
 
     def gen_clutter_batch(self, seeds, require_stable: bool = True):
         """Beyond the reference (which generates one scene per process, gen_scene.py:28-45): generate len(seeds) scenes
@@ -118,7 +85,11 @@ class ClutterTableEnv(MjSimulation):
         info = dict(base_qposadr=self.gripper.get_freejoint_idxs(self)[0],
                     object_qposadr=[int(self.model.jnt_qposadr[self.model.names["joint"][f"{n}:joint"]]) for n in self.object_names])
         step = lambda r, k: self.sim.step(r.astype(self.sim.real), k).astype(np.float64)
-        recs = scenes.gen_clutter_batch(self.model, info, step, seeds)
+        self.sim.set_qvel_clip(50.0)
+        try:
+            recs = scenes.gen_clutter_batch(self.model, info, step, seeds)
+        finally:
+            self.sim.set_qvel_clip(0.0)
         ok, after = scenes.scenes_stable(self.model, info, step, recs.copy())
         out, keep_rec, keep_time = [], self._record, self._time
         for k in range(len(recs)):
@@ -166,6 +137,7 @@ class ClutterTableEnv(MjSimulation):
             ar["geom_conaffinity"][g] = 0
         for b in body_ids:
             ar["body_gravcomp"][b] = 1.0
+        self._esc.close()
         if self._sim is not None:
             self._sim.close()
             self._sim = None
@@ -196,7 +168,13 @@ class ClutterTableEnv(MjSimulation):
         out = np.zeros(len(pose7), dtype=bool)
         idx = np.nonzero(in_bound)[0]
         base = self.gripper.get_freejoint_idxs(self)[0]
-        out[idx] = self.sim.clutter_collision_mask(self._record, pose7[idx], j32[idx], jadr, base)
+        if len(idx):
+            p7, jj, rec = pose7[idx], j32[idx], self._record
+
+            def run_range(lo, hi):
+                sel = lambda k: (p7[lo:hi], jj[lo:hi]) if k is None else (p7[lo:hi][k], jj[lo:hi][k])
+                return self._esc.run(lambda sim, k: sim.clutter_collision_mask(rec, *sel(k), jadr, base), hi - lo)[0]
+            out[idx] = evaluate_sharded(len(idx), run_range)
         return out
 
     def grasp_stable_mask(self, poses: SE3Pose, joints: np.ndarray, env_state, nstep_lift: int = 3000, lift_dist: float = 0.3, enough_stable=None):
@@ -204,8 +182,14 @@ class ClutterTableEnv(MjSimulation):
         scene = self._record_from_state(env_state)
         base = self.gripper.get_freejoint_idxs(self)[0]
         cfg = MgsRolloutCfg(self.gripper.NSTEP_CLOSE, nstep_lift, 0, self.gripper.REPOSE_ON_CLOSE, lift_dist, 0.0)
-        labels, _ = self.sim.clutter_stable_mask(scene, pose7, j32, jadr, base, self.gripper.close_ctrl(), cfg)
-        return apply_enough_stable(labels, enough_stable)
+        ctrl = self.gripper.close_ctrl()
+
+        def run_range(lo, hi):
+            sel = lambda k: (pose7[lo:hi], j32[lo:hi]) if k is None else (pose7[lo:hi][k], j32[lo:hi][k])
+            return self._esc.run(lambda sim, k: sim.clutter_stable_mask(scene, *sel(k), jadr, base, ctrl, cfg), hi - lo)[0][0]
+        # enough_stable as the reference's early stop (:293-296), in rounds of one GPU-filling chunk per rank
+        info = self.sim.info
+        return evaluate_sharded(len(pose7), run_range, enough_stable, chunk=info.warps_per_block * info.blocks_per_sm * info.num_sms)
 
     # ---- persistence (scene.npz payload) --------------------------------------------------------
     def to_dict(self):

@@ -1,20 +1,28 @@
 """GravitylessObjectGrasping - drop-in for /root/reference/mgs/env/gravityless_object_grasping.py.
 
-Same constructor and the same two public methods with the same argument meaning:
+Same constructor and the same public methods with the same argument meaning:
   grasp_collision_mask(poses, joints) -> bool[N]                       (reference :90-125)
   grasp_stability_evaluation_from_joints(poses, joints, nstep_lift, lift_dist, shake_steps,
                                          shake_dist, enough_stable) -> bool[N]      (reference :127-295)
+  get_object_transform / check_contact / check_contact_with_object       (reference :297-321)
 but every candidate is evaluated in ONE batched launch of the sm_100a rollout kernel through the C ABI
 (libmgs_b200.so) instead of a Python loop over mujoco.mj_step.  With torch.distributed initialised the
-candidates are sharded contiguously over the ranks and only the labels are gathered.
+candidates are sharded over the ranks and only the labels are gathered.
+
+Capacity: the kernel keeps a bounded number of contacts / constraint rows per environment in shared memory.  A
+candidate that needed more is flagged by the library; this class re-evaluates exactly those candidates on a second
+model instance with the largest capacities and warns if any still does not fit - labels computed on truncated
+contact sets are never returned silently (`last_overflow` holds the counts of the most recent call).
 """
 from __future__ import annotations
+
+import warnings
 
 import numpy as np
 
 from ...compiler.mjcf import compile_mjcf
 from ...lib import BatchSim, MgsRolloutCfg
-from ...shard import apply_enough_stable, gather_labels, shard_range
+from ...shard import evaluate_sharded
 from ..core.simualtion import MjSimulation
 from ..util.geo.transforms import SE3Pose
 
@@ -36,6 +44,58 @@ XML = r"""
 </mujoco>
 """
 
+MAX_CAPS = (64, 0)  # escalation capacities: the library's largest contact count, rows to match
+
+
+class EscalatingSim:
+    """Two instances of one model: the default capacities (most environments resident per SM) and, created on first
+    need, the largest ones.  `run(call, n)` evaluates n candidates with `call(sim, index_array_or_None) -> arrays`, then
+    re-runs the candidates whose environment overflowed on the big instance."""
+
+    def __init__(self, make_sim):
+        self._make, self._small, self._big = make_sim, None, None
+        self.last_overflow = dict(first_pass=0, after_escalation=0)
+
+    @property
+    def small(self) -> BatchSim:
+        if self._small is None:
+            self._small = self._make(None)
+        return self._small
+
+    @property
+    def big(self) -> BatchSim:
+        if self._big is None:
+            self._big = self._make(MAX_CAPS)
+        return self._big
+
+    def close(self):
+        for s in (self._small, self._big):
+            if s is not None:
+                s.close()
+        self._small = self._big = None
+
+    def run(self, call, n):
+        out = call(self.small, None)
+        out = [np.array(o) for o in (out if isinstance(out, tuple) else (out,))]
+        aux = self.small.last_aux(n)
+        over = np.nonzero(aux["overflow"])[0]
+        self.last_overflow = dict(first_pass=int(len(over)), after_escalation=0)
+        if len(over) and self.small.info.ncon_max < MAX_CAPS[0]:
+            again = call(self.big, over)
+            again = again if isinstance(again, tuple) else (again,)
+            for o, a in zip(out, again):
+                o[over] = a
+            aux2 = self.big.last_aux(len(over))
+            for k in ("bad", "pos_drift", "rot_drift_deg"):
+                aux[k][over] = aux2[k]
+            aux["overflow"][over] = aux2["overflow"]
+            over = over[aux2["overflow"]]
+            self.last_overflow["after_escalation"] = int(len(over))
+        if len(over):
+            warnings.warn(f"{len(over)} of {n} environments needed more than {MAX_CAPS[0]} contacts: their labels were computed on a "
+                          "truncated contact set", RuntimeWarning, stacklevel=3)
+        return (out[0] if len(out) == 1 else tuple(out)), aux
+
 
 class GravitylessObjectGrasping(MjSimulation):
     def __init__(self, gripper, obj, device: int | None = None, ncon_max: int = 0, nefc_max: int = 0):
@@ -45,17 +105,18 @@ class GravitylessObjectGrasping(MjSimulation):
         self.model_xml = XML.format(gripper=self.gripper_xml, object=self.object_xml)
         self.model = compile_mjcf(self.model_xml, {**self.gripper_assets, **self.object_assets})
         self._device, self._caps, self._sim = device, (ncon_max, nefc_max), None
+        self._esc = EscalatingSim(self._make_sim)
+        self._init_state()
 
-    # -- the batched simulator is created on first use (needs a CUDA device; there is no CPU fallback)
+    def _make_sim(self, caps):
+        if caps is None:
+            return self.sim
+        dev = self.sim.device
+        return BatchSim(self.model, device=dev, ncon_max=caps[0], nefc_max=caps[1], ground_name=self.GROUND_GEOM)
+
     @property
-    def sim(self) -> BatchSim:
-        if self._sim is None:
-            dev = self._device
-            if dev is None:
-                import torch
-                dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
-            self._sim = BatchSim(self.model, device=dev, ncon_max=self._caps[0], nefc_max=self._caps[1])
-        return self._sim
+    def last_overflow(self):
+        return self._esc.last_overflow
 
     def _process(self, poses: SE3Pose, joints: np.ndarray):
         if len(poses) != len(joints):
@@ -69,32 +130,53 @@ class GravitylessObjectGrasping(MjSimulation):
         pose7 = processed.to_vec(layout="pq", type="wxyz").astype(np.float32).reshape(-1, 7)
         return pose7, joints.astype(np.float32).reshape(len(pose7), len(names)), np.array(self.get_joint_idxs(names), dtype=np.int32)
 
-    def _sharded(self, n, fn):
-        """Run fn(lo, hi) on this rank's contiguous block and gather the labels from all ranks."""
-        try:
-            import torch.distributed as dist
-            on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        except Exception:
-            on = False
-        if not on:
-            return fn(0, n)
-        import torch
-        lo, hi = shard_range(n, dist.get_rank(), dist.get_world_size())
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else None
-        return gather_labels(fn(lo, hi), n, device=dev)
-
     def grasp_collision_mask(self, poses: SE3Pose, joints: np.ndarray) -> np.ndarray:
         pose7, joints32, jadr = self._process(poses, joints)
         base = self.gripper.get_freejoint_idxs(self)[0]
-        return self._sharded(len(pose7), lambda lo, hi: self.sim.collision_mask(pose7[lo:hi], joints32[lo:hi], jadr, base))
+
+        def run_range(lo, hi):
+            sel = lambda idx: (pose7[lo:hi], joints32[lo:hi]) if idx is None else (pose7[lo:hi][idx], joints32[lo:hi][idx])
+            return self._esc.run(lambda sim, idx: sim.collision_mask(*sel(idx), jadr, base), hi - lo)[0]
+        return evaluate_sharded(len(pose7), run_range)
 
     def grasp_stability_evaluation_from_joints(self, poses: SE3Pose, joints: np.ndarray, nstep_lift: int = 3000, lift_dist: float = 0.1,
-                                               shake_steps: int = 500, shake_dist: float = 0.02, enough_stable=None) -> np.ndarray:
+                                               shake_steps: int = 500, shake_dist: float = 0.02, enough_stable=None, return_drift: bool = False):
+        """bool[N] like the reference (:295).  `return_drift=True` additionally returns the two arrays the reference computes and
+        leaves commented out of its return statement (:175-200, :283-295): positional drift [m] and rotational drift [deg] of the
+        object over the close phase, NaN for candidates that were skipped or lost contact while closing."""
         pose7, joints32, jadr = self._process(poses, joints)
+        n = len(pose7)
         base = self.gripper.get_freejoint_idxs(self)[0]
         cfg = MgsRolloutCfg(self.gripper.NSTEP_CLOSE, nstep_lift, shake_steps, self.gripper.REPOSE_ON_CLOSE, lift_dist, shake_dist)
         ctrl = self.gripper.close_ctrl()
-        labels = self._sharded(len(pose7), lambda lo, hi: self.sim.stability(pose7[lo:hi], joints32[lo:hi], jadr, base, ctrl, cfg)[0])
-        # `enough_stable`: the reference stops evaluating after that many successes and labels the rest
-        # False (:151-156); evaluating everything and masking the tail gives the same array
-        return apply_enough_stable(labels, enough_stable)
+        pos_drift, rot_drift = np.full(n, np.nan), np.full(n, np.nan)
+
+        def run_range(lo, hi):
+            sel = lambda idx: (pose7[lo:hi], joints32[lo:hi]) if idx is None else (pose7[lo:hi][idx], joints32[lo:hi][idx])
+            (lab, _), aux = self._esc.run(lambda sim, idx: sim.stability(*sel(idx), jadr, base, ctrl, cfg), hi - lo)
+            pos_drift[lo:hi], rot_drift[lo:hi] = aux["pos_drift"], aux["rot_drift_deg"]
+            return lab
+        # `enough_stable`: the reference stops simulating after that many successes and labels the rest False (:151-156).
+        # Kept as an early stop in rounds of one GPU-filling chunk per rank (shard.evaluate_sharded).
+        info = self.sim.info
+        labels = evaluate_sharded(n, run_range, enough_stable, chunk=info.warps_per_block * info.blocks_per_sm * info.num_sms)
+        if return_drift:  # (drifts are per rank: each rank holds those of the candidates it evaluated itself)
+            return labels, pos_drift, rot_drift
+        return labels
+
+    # ---- single-environment queries of the reference class (operate on the handle's state record) -----------------
+    def get_object_transform(self, object_name: str) -> SE3Pose:  # :297-304
+        a = int(self.model.jnt_qposadr[self.model.names["joint"][f"{object_name}:joint"]])
+        q = self.data.qpos
+        return SE3Pose(np.copy(q[a:a + 3]).astype(np.float32), np.copy(q[a + 3:a + 7]).astype(np.float32), "wxyz")
+
+    def check_contact(self) -> bool:  # :306-307
+        return self.data.ncon != 0
+
+    def check_contact_with_object(self) -> bool:  # :309-321: a contact whose two geom ids straddle the ground geom's id
+        g = int(self.model.names["geom"][self.GROUND_GEOM])
+        geoms = self.data.contact.geom
+        return bool((((geoms[:, 0] < g) & (geoms[:, 1] > g)) | ((geoms[:, 0] > g) & (geoms[:, 1] < g))).any())
+
+    def idle_grasp(self, pose: SE3Pose, joints: np.ndarray):
+        raise NotImplementedError("idle_grasp opens the interactive MuJoCo viewer (:73-88); there is no viewer on the batched path")

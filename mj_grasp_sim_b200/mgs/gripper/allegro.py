@@ -26,5 +26,9 @@ class GripperAllegro(MjGripper):
     def get_actuator_joint_names(self) -> List[str]:  # allegro.py:380-398
         return [f"{f}j{k}" for f in ("ff", "mf", "rf", "th") for k in range(4)]
 
+    def open_gripper(self, sim):  # allegro.py:349-352
+        sim.set_qpos(np.copy(self.open_pose), sim.get_joint_idxs(self.get_actuator_joint_names()))
+        sim.data.ctrl[:] = np.copy(self.open_pose)
+
     def close_ctrl(self) -> np.ndarray:
         return np.copy(self.close_pose)

@@ -48,6 +48,65 @@ class MjGripper:
         start = sim.get_joint_idxs([self.FREEJOINT])[0]
         return list(range(start, start + 7))
 
+    # --- imperative protocol on ONE environment (the sim handle's state record; see mgs/core/simualtion.py) -----------
+    # The batched entry points of the environments do not go through these: they read close_ctrl() / REPOSE_ON_CLOSE
+    # and run the same sequence for every candidate inside the kernel (csrc/mgs_rollout.cuh).  The methods exist so
+    # that reference callers that drive a gripper by hand keep working, one environment at a time.
+    def set_pose(self, sim, pose: SE3Pose):
+        """base.py:48-59: teleport the base (free-joint qpos and the mocap target it is welded to), then mj_forward."""
+        idxs = self.get_freejoint_idxs(sim)
+        vec = np.asarray(pose.to_vec(layout="pq", type="wxyz"), dtype=np.float64).reshape(-1)
+        sim.data.qpos[idxs[0]:idxs[0] + 7] = vec
+        sim.data.mocap_pos[0, :] = vec[:3]
+        sim.data.mocap_quat[0, :] = vec[3:]
+        sim.mj_forward()
+
+    def open_gripper(self, sim):
+        """default (robotiq2f85.py:237-238): zero control"""
+        sim.data.ctrl[:] = 0.0
+
+    def close_gripper(self, sim):
+        sim.data.ctrl[:] = self.close_ctrl()
+
+    def close_gripper_at(self, sim, pose: SE3Pose):
+        """panda.py:225-241 and the five siblings: mocap target <- pose (Allegro / LEAP: set_pose again), ctrl <- the close
+        signal, then NSTEP_CLOSE steps."""
+        if self.REPOSE_ON_CLOSE:
+            self.set_pose(sim, pose)
+        else:
+            vec = np.asarray(pose.to_vec(layout="pq", type="wxyz"), dtype=np.float64).reshape(-1)
+            sim.data.mocap_pos[0, :] = vec[:3]
+            sim.data.mocap_quat[0, :] = vec[3:]
+        sim.data.ctrl[:] = self.close_ctrl()
+        sim.mj_step(self.NSTEP_CLOSE)
+
+    def lift_up(self, sim, viewer=None):
+        """base.py:61-66"""
+        for _ in range(10000):
+            sim.data.mocap_pos[0, 2] += 0.00003
+            sim.mj_step(1)
+
+    # Shakable (base.py:111-143): the mocap target moves in small increments along the pose's axes
+    def _move(self, sim, pose: SE3Pose, axis, step, n):
+        d = np.asarray(pose.to_mat(), dtype=np.float64).reshape(4, 4)[:3, :3] @ np.asarray(axis, dtype=np.float64)
+        for _ in range(n):
+            sim.data.mocap_pos[0, :] += step * d
+            sim.mj_step(1)
+
+    def move_back(self, sim, pose: SE3Pose, viewer=None):
+        self._move(sim, pose, [0, 0, -1.0], 0.0002, 1000)
+
+    def move_right(self, sim, pose: SE3Pose, viewer=None):
+        self._move(sim, pose, [0, 1.0, 0], 0.0005, 500)
+
+    def move_left(self, sim, pose: SE3Pose, viewer=None):
+        self._move(sim, pose, [0, -1.0, 0], 0.0005, 500)
+
+    def shake_grasp_at(self, sim, pose: SE3Pose):
+        self.move_back(sim, pose)
+        self.move_right(sim, pose)
+        self.move_left(sim, pose)
+
     # --- per-gripper data -------------------------------------------------------------------
     def base_to_contact_transform(self) -> SE3Pose:
         raise NotImplementedError

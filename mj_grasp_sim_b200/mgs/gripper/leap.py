@@ -23,5 +23,8 @@ class GripperLeap(MjGripper):
         return [f"{f}_{j}" for f, js in (("if", ("mcp", "rot", "pip", "dip")), ("mf", ("mcp", "rot", "pip", "dip")),
                                          ("rf", ("mcp", "rot", "pip", "dip")), ("th", ("cmc", "axl", "mcp", "ipl"))) for j in js]
 
+    def open_gripper(self, sim):  # leap.py:400-401: a no-op in the reference
+        return
+
     def close_ctrl(self) -> np.ndarray:
         return np.copy(self.close_pose)

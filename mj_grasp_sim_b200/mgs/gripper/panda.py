@@ -24,6 +24,12 @@ class GripperPanda(MjGripper):
     def close_ctrl(self) -> np.ndarray:  # panda.py:236
         return np.array([0.0, -0.04])
 
+    def open_gripper(self, sim):  # panda.py:195-207
+        q = sim.get_joint_idxs(self.get_actuator_joint_names())
+        sim.data.qpos[q[0]], sim.data.qpos[q[1]] = self.Q1_RANGE[1], self.Q2_RANGE[1]
+        sim.data.ctrl[0], sim.data.ctrl[1] = self.Q1_RANGE[1], self.Q2_RANGE[1]
+        sim.mj_forward()
+
     def width_to_joints(self, width):  # panda.py:217-223
         w = np.clip(width, self.MIN_WIDTH_CLAMP, self.MAX_WIDTH)
         return np.clip(w / 2.0, *self.Q1_RANGE), np.clip(-0.04 + w / 2.0, *self.Q2_RANGE)

@@ -39,5 +39,9 @@ class GripperShadowRight(MjGripper):
         return ["rh_FFJ4", "rh_FFJ3", "rh_FFJ2", "rh_FFJ1", "rh_MFJ4", "rh_MFJ3", "rh_MFJ2", "rh_MFJ1", "rh_RFJ4", "rh_RFJ3", "rh_RFJ2",
                 "rh_RFJ1", "rh_LFJ5", "rh_LFJ4", "rh_LFJ3", "rh_LFJ2", "rh_LFJ1", "rh_THJ5", "rh_THJ4", "rh_THJ3", "rh_THJ2", "rh_THJ1"]
 
+    def open_gripper(self, sim):  # shadow.py:373-377
+        sim.set_qpos(np.zeros(22), sim.get_joint_idxs(self.get_actuator_joint_names()))
+        sim.data.ctrl[:] = qpos_to_ctrl(np.zeros(22))
+
     def close_ctrl(self) -> np.ndarray:
         return qpos_to_ctrl(CLOSE_QPOS)

@@ -28,6 +28,12 @@ class GripperVX300(MjGripper):
     def close_ctrl(self) -> np.ndarray:  # vx300.py:306-309
         return np.array([self.Q1_RANGE[0], self.Q2_RANGE[1]])
 
+    def open_gripper(self, sim):  # vx300.py:259-272
+        q = sim.get_joint_idxs(self.get_actuator_joint_names())
+        sim.data.qpos[q[0]], sim.data.qpos[q[1]] = self.Q1_RANGE[1], self.Q2_RANGE[0]
+        sim.data.ctrl[0], sim.data.ctrl[1] = self.Q1_RANGE[1], self.Q2_RANGE[0]
+        sim.mj_forward()
+
     def width_to_joints(self, width):  # vx300.py:284-294
         w = np.clip(width, self.MIN_WIDTH, self.MAX_WIDTH)
         return np.clip(0.5 * w, *self.Q1_RANGE), np.clip(-0.5 * w, *self.Q2_RANGE)

@@ -96,10 +96,11 @@ def random_hull_points(seed: int, n_v: int = 32):
     return p * ax, mass
 
 
-def hull_object_fragment(seed: int, n_v: int = 32, name="obj"):
+def hull_object_fragment(seed: int, n_v: int = 32, name="obj", mass_scale: float = 1.0):
     """Convex-hull object with the reference's object recipe: condim 4, friction 1/.3/.1,
     solimp .998 .998 .001, solref .001 1, free joint damping 1e-4 (ycb.py:138-157)."""
     pts, mass = random_hull_points(seed, n_v)
+    mass *= mass_scale
     h = meshlib.build_hull(pts)
     fn = f"{name}_hull_{seed}.obj"
     xml = f"""<asset><mesh name="{name}_coll_0" file="{fn}"/></asset>
@@ -202,15 +203,28 @@ def box_mesh(size):
     return h.verts, h.tri
 
 
-def workload(gripper: str, kind: str, seed: int, n: int, n_v: int = 32):
+# "marginal" candidate sets (label-agreement measurements need an informative label distribution: on the plain antipodal
+# sets 93-98 % of the parallel-jaw candidates are stable, so a constant predictor scores 95 %).  Per gripper: how far (m) the
+# grasp frame is pulled back along its approach axis (uniform in [0.5, 1] x retreat: the fingertips barely reach the
+# object), lateral noise sigma = retreat / 4, object 10 x heavier.  Tuned so that the oracle's stable fraction is 0.3-0.6.
+MARGINAL = {"panda": 0.03, "vx300": 0.03, "robotiq2f85": 0.025, "allegro": 0.0, "leap": 0.0, "shadow": 0.06}
+
+
+def workload(gripper: str, kind: str, seed: int, n: int, n_v: int = 32, marginal: bool = False):
     """(model, info, pose7 float32 [n,7], joints float32 [n,nj]) for one synthetic object."""
     if kind == "cube":
         ox, oa = cube_fragment()
         verts, tri = box_mesh(0.02)
     else:
-        ox, oa, (verts, tri) = hull_object_fragment(seed, n_v)
+        ox, oa, (verts, tri) = hull_object_fragment(seed, n_v, mass_scale=10.0 if marginal else 1.0)
     model, info = build_scene(gripper, ox, oa)
     H, width = antipodal_candidates(verts, tri, n, seed)
+    if marginal and MARGINAL[gripper] > 0:
+        rng = np.random.default_rng(6000 + seed)
+        r = MARGINAL[gripper]
+        H = H.copy()
+        H[:, :3, 3] += rng.normal(scale=0.25 * r, size=(n, 3))
+        H[:, :3, 3] -= H[:, :3, 2] * (r * rng.uniform(0.5, 1.0, size=(n, 1)))
     if gripper == "leap":
         # The reference's LEAP candidates come from its contact sampler (palm poses, identity b2c); that
         # sampler is out of scope, so the harness turns the antipodal frame into a palm pose: fingers point

@@ -46,3 +46,45 @@ def apply_enough_stable(labels: np.ndarray, enough_stable) -> np.ndarray:
         return labels
     before = np.concatenate([[0], np.cumsum(labels)[:-1]])
     return labels & (before < enough_stable)
+
+
+def dist_state():
+    """(world, rank, device for collectives) of the initialised default process group, else (1, 0, None)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            import torch
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else None
+            return dist.get_world_size(), dist.get_rank(), dev
+    except Exception:
+        pass
+    return 1, 0, None
+
+
+def evaluate_sharded(n: int, run_range, enough_stable=None, chunk: int = 0) -> np.ndarray:
+    """Labels bool[n] of candidates 0..n-1, evaluated by `run_range(lo, hi) -> bool[hi-lo]` on this rank's share.
+
+    Without `enough_stable`: one contiguous block per rank, one label gather.  With it, the reference's early stop
+    (gravityless_object_grasping.py:151-156: once `enough_stable` successes were seen the remaining candidates are
+    labelled False WITHOUT being simulated) is kept: candidates are evaluated in sequential rounds of world x `chunk`
+    (one chunk = what keeps one GPU full, so a smaller round would not finish sooner), the round's labels are gathered,
+    and the loop stops as soon as the running success count reaches `enough_stable`.  The returned array equals the
+    reference's sequential result."""
+    world, rank, dev = dist_state()
+    if enough_stable is None:
+        if world == 1:
+            return np.asarray(run_range(0, n), dtype=bool)
+        lo, hi = shard_range(n, rank, world)
+        return gather_labels(run_range(lo, hi), n, device=dev)
+    chunk = max(1, int(chunk) if chunk else n)
+    labels = np.zeros(n, dtype=bool)
+    done, count = 0, 0
+    while done < n and count < enough_stable:
+        rn = min(n - done, world * chunk)
+        lo, hi = shard_range(rn, rank, world)
+        local = np.asarray(run_range(done + lo, done + hi), dtype=bool) if hi > lo else np.zeros(0, dtype=bool)
+        got = gather_labels(local, rn, device=dev) if world > 1 else local
+        labels[done:done + rn] = got
+        count += int(got.sum())
+        done += rn
+    return apply_enough_stable(labels, enough_stable)

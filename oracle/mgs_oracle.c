@@ -67,6 +67,7 @@ typedef struct OrcSim {
   int efc_type[NEFC_MAX], efc_id[NEFC_MAX], efc_state[NEFC_MAX];
   /* diagnostics */
   int solver_niter, bad, nstep_done, ncon_overflow, ncon_peak, nefc_peak;
+  double qvel_clip; /* > 0: clamp qvel to +-qvel_clip before every step (ClutterTableEnv.gen_clutter, clutter_table.py:215-221) */
   /* scratch */
   double *w1, *w2, *w3, *w4, *w5, *w6, *jtmp;
 } OrcSim;
@@ -1516,8 +1517,12 @@ static void integrate(OrcSim *s) {
   s->time += h;
 }
 
+void orc_set_qvel_clip(OrcSim *s, double clip) { s->qvel_clip = clip > 0 ? clip : 0; }
+
 int orc_step(OrcSim *s, int nstep) {
   for (int k = 0; k < nstep; k++) {
+    if (s->qvel_clip > 0)
+      for (int i = 0; i < s->m.nv; i++) s->qvel[i] = s->qvel[i] > s->qvel_clip ? s->qvel_clip : (s->qvel[i] < -s->qvel_clip ? -s->qvel_clip : s->qvel[i]);
     if (s->bad || bad_vec(s->qpos, s->m.nq) || bad_vec(s->qvel, s->m.nv)) { s->bad = 1; return -1; }
     orc_forward(s);
     if (bad_vec(s->qacc, s->m.nv)) { s->bad = 1; return -1; }

@@ -50,6 +50,8 @@ def lib():
         for name in ("ncon", "nefc", "niter", "bad", "contact_with_object", "ncon_peak", "nefc_peak"):
             getattr(L, "orc_" + name).argtypes = [C.c_void_p]
             getattr(L, "orc_" + name).restype = C.c_int
+        L.orc_set_qvel_clip.argtypes = [C.c_void_p, C.c_double]
+        L.orc_set_qvel_clip.restype = None
         L.orc_step.argtypes = [C.c_void_p, C.c_int]
         L.orc_step.restype = C.c_int
         L.orc_contact.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
@@ -141,6 +143,7 @@ class OracleSim:
     def reset(self): self.L.orc_reset(self.h)
     def forward(self): self.L.orc_forward(self.h)
     def step(self, n=1): return self.L.orc_step(self.h, n)
+    def set_qvel_clip(self, clip): self.L.orc_set_qvel_clip(self.h, float(clip))
     def kinematics(self): self.L.orc_kinematics_only(self.h)
     def contact_with_object(self): return bool(self.L.orc_contact_with_object(self.h))
 

@@ -18,6 +18,8 @@ struct L1Model {
   Layout L;
   int state_stride, diag_stride;
   std::vector<real> scratch;
+  std::vector<float> aux;
+  double qvel_clip = 0;
 };
 static std::string g_err;
 
@@ -47,8 +49,11 @@ extern "C" int l1_model_info(const L1Model *M, MgsModelInfo *info) {
   return 0;
 }
 
-static void run_all(L1Model *M, const RolloutParams &prm, const BatchIO &io) {
+static void run_all(L1Model *M, const RolloutParams &prm, const BatchIO &io_in) {
   Env e;
+  BatchIO io = io_in;
+  M->aux.assign((size_t)4 * (prm.n > 0 ? prm.n : 1), 0.0f);
+  io.aux = M->aux.data();
   g_k.m = M->dm; g_k.L = M->L; g_k.prm = prm; g_k.io = io;
   for (int env = 0; env < prm.n; env++) {
     env_bind(e, M->scratch.data());
@@ -56,10 +61,17 @@ static void run_all(L1Model *M, const RolloutParams &prm, const BatchIO &io) {
   }
 }
 
+extern "C" int l1_last_aux(L1Model *M, int n, float *out) {
+  if ((size_t)4 * n > M->aux.size()) { g_err = "l1_last_aux: the most recent call had fewer candidates"; return -1; }
+  memcpy(out, M->aux.data(), sizeof(float) * 4 * n);
+  return 0;
+}
+extern "C" int l1_set_qvel_clip(L1Model *M, double clip) { M->qvel_clip = clip > 0 ? clip : 0; return 0; }
+
 extern "C" int l1_step_host(L1Model *M, int n, int nstep, const void *state_in, void *state_out, void *diag_out) {
   RolloutParams prm;
   memset(&prm, 0, sizeof(prm));
-  prm.mode = MGS_MODE_STEP; prm.n = n; prm.nstep = nstep;
+  prm.mode = MGS_MODE_STEP; prm.n = n; prm.nstep = nstep; prm.qvel_clip = (real)M->qvel_clip;
   BatchIO io;
   memset(&io, 0, sizeof(io));
   io.state_in = (const real *)state_in; io.state_out = (real *)state_out; io.diag_out = (real *)diag_out;

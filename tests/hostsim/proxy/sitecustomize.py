@@ -22,6 +22,7 @@ if os.environ.get("MGS_PROXY", "1") == "1":
     from mj_grasp_sim_b200 import lib as mlib
     import mj_grasp_sim_b200.mgs.env.clutter_table as _ct
     import mj_grasp_sim_b200.mgs.env.gravityless_object_grasping as _gog
+    import mj_grasp_sim_b200.mgs.core.simualtion as _simmod
 
     _orig = mlib.BatchSim
     _libs = {f: mlib.bind(C.CDLL(lane1.build(f)), prefix="l1_") for f in (False, True)}
@@ -33,5 +34,5 @@ if os.environ.get("MGS_PROXY", "1") == "1":
         def overflow_count(self):
             return 0
 
-    mlib.BatchSim = _gog.BatchSim = _ct.BatchSim = ProxySim
+    mlib.BatchSim = _gog.BatchSim = _ct.BatchSim = _simmod.BatchSim = ProxySim
     mlib.load = lambda f64=False: None

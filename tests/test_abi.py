@@ -22,10 +22,23 @@ def test_exports_match_header(so):
     hdr = open(os.path.join(ROOT, "include", "mgs_b200.h")).read()
     names = set(re.findall(r"\b(mgs_[a-z_]+)\s*\(", hdr))
     assert {"mgs_model_create", "mgs_grasp_stability", "mgs_grasp_collision_mask", "mgs_rollout_device", "mgs_step_device",
-            "mgs_step_host", "mgs_last_error", "mgs_model_destroy", "mgs_model_info", "mgs_launch_count"} <= names
+            "mgs_step_host", "mgs_last_error", "mgs_model_destroy", "mgs_model_info", "mgs_launch_count", "mgs_last_aux",
+            "mgs_set_qvel_clip", "mgs_build_stamp", "mgs_overflow_count"} <= names
     L = C.CDLL(so)
     for n in names:
         assert hasattr(L, n), n
+
+
+def test_build_stamp_matches_the_checked_out_sources(so):
+    """The prebuilt .so files are git-ignored artefacts: the stamp compiled into the library must be the hash of the sources
+    in this tree, so a stale library cannot pass for HEAD."""
+    L = C.CDLL(so)
+    L.mgs_build_stamp.restype = C.c_char_p
+    assert L.mgs_build_stamp().decode() == mlib.source_stamp()
+    so64 = mlib.build(f64=True)
+    L64 = C.CDLL(so64)
+    L64.mgs_build_stamp.restype = C.c_char_p
+    assert L64.mgs_build_stamp().decode() == mlib.source_stamp()
 
 
 def test_model_desc_header_in_sync():

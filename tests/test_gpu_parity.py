@@ -338,3 +338,196 @@ def test_first_50_steps_every_gripper(libs, gripper, qtol):
         # warm start, whose answers differ from a cold start within mpr_tolerance (visible on LEAP's very stiff contacts)
         r64 = first50(gripper, 8, True, chunk=1)
         assert r64["n_same_contacts"] >= 6 and r64["qpos_rel_same_contacts"] <= 1e-7, r64
+
+
+def test_loaded_library_is_head_and_not_the_host_proxy(libs):
+    """The prebuilt .so is a git-ignored artefact: its compiled-in stamp must equal the hash of the sources of this tree, and
+    BatchSim must be the CUDA binding (the CPU proxy harness tests/hostsim/proxy must not be active in the GPU tier)."""
+    import sys
+    mlib, _ = libs
+    L = mlib.load()
+    assert L.mgs_build_stamp().decode() == mlib.source_stamp()
+    if os.path.exists(mlib.SO_PATH_F64):
+        assert mlib.load(f64=True).mgs_build_stamp().decode() == mlib.source_stamp()
+    assert mlib.BatchSim.__module__ == "mj_grasp_sim_b200.lib" and mlib.BatchSim.__name__ == "BatchSim"
+    assert "hostsim.lane1" not in sys.modules or os.environ.get("MGS_PROXY") is None
+    maps = open("/proc/self/maps").read()
+    assert "libmgs_b200.so" in maps and "liblane1" not in maps
+
+
+def test_two_models_alive_on_one_device(libs, panda_cube, robotiq_hull):
+    """the dynamic-shared-memory attribute belongs to the kernel function, not to a model.  Create A (large shared
+    memory per CTA), then B (smaller, same kernel variant or not), then run A, B, A: every launch must succeed and repeat its
+    own results."""
+    mlib, _ = libs
+    mA, iA, pA, jA = robotiq_hull
+    mB, iB, pB, jB = panda_cube
+    sched = mlib.MgsRolloutCfg(200, 60, 10, 0, 0.02, 0.02)
+    A = mlib.BatchSim(mA)
+    a0 = A.stability(pA, jA, iA["joint_qposadr"], iA["base_qposadr"], iA["close_ctrl"], sched)
+    B = mlib.BatchSim(mB, ncon_max=8, nefc_max=40)  # a deliberately small CTA
+    C2 = mlib.BatchSim(mB)
+    b0 = B.stability(pB, jB, iB["joint_qposadr"], iB["base_qposadr"], iB["close_ctrl"], sched)
+    a1 = A.stability(pA, jA, iA["joint_qposadr"], iA["base_qposadr"], iA["close_ctrl"], sched)
+    c0 = C2.stability(pB, jB, iB["joint_qposadr"], iB["base_qposadr"], iB["close_ctrl"], sched)
+    b1 = B.stability(pB, jB, iB["joint_qposadr"], iB["base_qposadr"], iB["close_ctrl"], sched)
+    a2 = A.stability(pA, jA, iA["joint_qposadr"], iA["base_qposadr"], iA["close_ctrl"], sched)
+    for x, y in ((a0, a1), (a0, a2), (b0, b1)):
+        assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1])
+    assert len(c0[0]) == len(pB)
+
+
+def test_concurrent_host_threads_on_two_models(libs, panda_cube, vx300_hull):
+    """launch() serialises the per-variant constant block under a lock: two host threads driving two model handles at once
+    (ctypes releases the GIL) must each get the results of a solo run."""
+    import threading
+    mlib, _ = libs
+    sched = mlib.MgsRolloutCfg(200, 60, 10, 0, 0.02, 0.02)
+    sims, solo, got = [], [], [None, None]
+    for m, info, p, j in (panda_cube, vx300_hull):
+        G = mlib.BatchSim(m)
+        sims.append((G, info, p, j))
+        solo.append(G.stability(p, j, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], sched))
+
+    def work(k):
+        G, info, p, j = sims[k]
+        for _ in range(4):
+            got[k] = G.stability(p, j, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], sched)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for k in range(2):
+        assert np.array_equal(got[k][0], solo[k][0]) and np.array_equal(got[k][1], solo[k][1])
+
+
+def test_duplicate_joint_addresses_last_value_wins_on_gpu(libs, robotiq_hull):
+    """Robotiq's two misnamed joints resolve to one qpos address; the scatter must be last-wins like the reference's
+    `data.qpos[idxs] = qpos`, deterministically, and equal to the oracle."""
+    mlib, orc = libs
+    m, info, pose7, joints = robotiq_hull
+    j = joints[:16].copy()
+    j[:, 2], j[:, 6] = 0.3, 0.002
+    sched = (300, 100, 0, 0, 0.02, 0.02)
+    G = mlib.BatchSim(m)
+    lab, steps = G.stability(pose7[:16], j, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], mlib.MgsRolloutCfg(*sched))
+    olab, osteps = _oracle_batch(orc, m, info, 1, pose7[:16], j, sched)
+    assert np.array_equal(lab, olab) and np.array_equal(steps, osteps)
+
+
+def test_overflow_is_reported_per_candidate_and_escalated(libs):
+    """Environments that exceed the contact / row capacities are flagged per candidate (mgs_last_aux) and the env mirror re-runs
+    exactly those on the largest capacities: no label from a truncated contact set is returned silently."""
+    from mj_grasp_sim_b200 import scenes
+    from mj_grasp_sim_b200.mgs.env.gravityless_object_grasping import GravitylessObjectGrasping
+    from mj_grasp_sim_b200.mgs.gripper.selector import get_gripper
+    from mj_grasp_sim_b200.mgs.obj.selector import get_object
+    from mj_grasp_sim_b200.mgs.util.geo.transforms import SE3Pose
+    mlib, orc = libs
+    m, info, pose7, joints = scenes.workload("panda", "cube", 0, 64)
+    small = mlib.BatchSim(m, ncon_max=4, nefc_max=40)
+    sched = mlib.MgsRolloutCfg(600, 200, 20, 0, 0.03, 0.02)
+    small.stability(pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], sched)
+    aux = small.last_aux(len(pose7))
+    assert aux["overflow"].sum() == small.overflow_count() > 0  # pad-on-cube needs up to 8 contacts
+    # the env mirror with the same tiny first-pass capacities ends up with the labels of a roomy model
+    env = GravitylessObjectGrasping(get_gripper("PandaGripper"), get_object("cube"), ncon_max=4, nefc_max=40)
+    env.gripper.NSTEP_CLOSE = 600
+    v, t = env.obj.mesh()
+    H, w = scenes.antipodal_candidates(v, t, 64, 0)
+    poses, jj = SE3Pose.from_mat(H), scenes.panda_width_to_joints(w)
+    lab = env.grasp_stability_evaluation_from_joints(poses, jj, nstep_lift=200, lift_dist=0.03, shake_steps=20)
+    assert env.last_overflow["first_pass"] > 0 and env.last_overflow["after_escalation"] == 0
+    roomy = GravitylessObjectGrasping(get_gripper("PandaGripper"), get_object("cube"))
+    roomy.gripper.NSTEP_CLOSE = 600
+    lab2, pd, rd = roomy.grasp_stability_evaluation_from_joints(poses, jj, nstep_lift=200, lift_dist=0.03, shake_steps=20, return_drift=True)
+    assert roomy.last_overflow["first_pass"] == 0
+    over = small.last_aux(64)["overflow"]
+    assert np.array_equal(lab[~over], lab2[~over])  # untouched candidates are bit-identical; escalated ones ran on 64 contacts
+    assert (lab == lab2).mean() >= 0.98
+    assert np.isfinite(pd[lab2]).all() and (pd[lab2] < 0.05).all() and np.isfinite(rd[lab2]).all()
+
+
+def test_enough_stable_stops_early_on_gpu(libs):
+    from mj_grasp_sim_b200 import scenes
+    from mj_grasp_sim_b200.mgs.env.gravityless_object_grasping import GravitylessObjectGrasping
+    from mj_grasp_sim_b200.mgs.gripper.selector import get_gripper
+    from mj_grasp_sim_b200.mgs.obj.selector import get_object
+    from mj_grasp_sim_b200.mgs.util.geo.transforms import SE3Pose
+    from mj_grasp_sim_b200 import shard
+    mlib, _ = libs
+    env = GravitylessObjectGrasping(get_gripper("PandaGripper"), get_object("hull:0"))
+    env.gripper.NSTEP_CLOSE = 400
+    v, t = env.obj.mesh()
+    n = 6000  # more than one GPU-filling chunk (148 SMs x <=16 environments)
+    H, w = scenes.antipodal_candidates(v, t, n, 0)
+    poses, jj = SE3Pose.from_mat(H), scenes.panda_width_to_joints(w)
+    kw = dict(nstep_lift=100, lift_dist=0.02, shake_steps=10)
+    l0 = mlib.load().mgs_launch_count()
+    full = env.grasp_stability_evaluation_from_joints(poses, jj, **kw)
+    l1 = mlib.load().mgs_launch_count()
+    early = env.grasp_stability_evaluation_from_joints(poses, jj, enough_stable=50, **kw)
+    l2 = mlib.load().mgs_launch_count()
+    assert np.array_equal(early, shard.apply_enough_stable(full, 50)) and early.sum() == 50
+    assert l1 - l0 == 1 and l2 - l1 == 1  # the target is reached inside the first chunk: one launch, the other candidates never run
+
+
+def test_imperative_protocol_on_gpu(libs):
+    """set_qpos / gripper.set_pose / close_gripper_at / check_contact_with_object / get_state / set_state on ONE environment
+    through the CUDA library, against the oracle driven the same way."""
+    from mj_grasp_sim_b200 import scenes
+    from mj_grasp_sim_b200.mgs.env.gravityless_object_grasping import GravitylessObjectGrasping
+    from mj_grasp_sim_b200.mgs.gripper.selector import get_gripper
+    from mj_grasp_sim_b200.mgs.obj.selector import get_object
+    from mj_grasp_sim_b200.mgs.util.geo.transforms import SE3Pose
+    mlib, orc = libs
+    env = GravitylessObjectGrasping(get_gripper("PandaGripper"), get_object("hull:0"))
+    m, info, pose7, joints = scenes.workload("panda", "hull", 0, 4)
+    g = env.gripper
+    pose = SE3Pose(pose7[2, :3].astype(np.float64), pose7[2, 3:].astype(np.float64), "wxyz")
+    env.mj_resetData()
+    env.set_qpos(joints[2].astype(np.float64), env.get_joint_idxs(g.get_actuator_joint_names()))
+    g.set_pose(env, pose)
+    env.mj_forward()
+    s = orc.OracleSim(env.model)
+    s.reset()
+    s.place(pose7[2].astype(np.float64), info["base_qposadr"], joints[2].astype(np.float64), info["joint_qposadr"])
+    s.forward()
+    assert env.check_contact() == (s.ncon != 0)
+    g.NSTEP_CLOSE = 50
+    g.close_gripper_at(env, pose)
+    s.ctrl[:] = g.close_ctrl()
+    s.step(50)
+    assert np.abs(env.data.qpos - s.qpos).max() < 1e-4 and env.check_contact_with_object() == s.contact_with_object()
+    st = env.get_state()
+    env.mj_step(10)
+    q10 = env.data.qpos.copy()
+    env.set_state(st)
+    env.mj_step(10)
+    assert np.array_equal(env.data.qpos, q10)
+
+
+def test_robotiq_golden_closed_state_through_cuda(libs):
+    """The MuJoCo-recorded Robotiq closed state (robotiq_2f_85.yaml:11) reproduced by the CUDA builds, not only by the oracle."""
+    import json
+    from mj_grasp_sim_b200 import scenes
+    from mj_grasp_sim_b200.compiler.mjcf import compile_mjcf
+    from test_golden_robotiq import SCAN_XML
+    mlib, _ = libs
+    gold = np.array(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "robotiq_2f85_state_close.json")))["state"])
+    gx, ga = scenes.gripper_fragment("robotiq2f85")
+    m = compile_mjcf(SCAN_XML.format(gripper=gx), ga)
+    q_gold = gold[1:1 + m.nq]
+    for f64 in (False, True):
+        if f64 and not os.path.exists(mlib.SO_PATH_F64):
+            continue
+        G = mlib.BatchSim(m, f64=f64, ground_name="geom:center")
+        q0 = m.qpos0.copy()
+        q0[0:3] = [0, 0, -0.15]
+        st = G.pack_state(q0, np.zeros(m.nv), ctrl=np.array([255.0]), mocap_pos=np.array([0, 0, -0.15]), mocap_quat=np.array([1.0, 0, 0, 0]))
+        out = G.unpack_state(G.step(st, 2500))
+        jn = m.names["joint"]
+        for name in ("right_driver_joint", "right_coupler_joint", "right_spring_link_joint", "right_follower_joint",
+                     "left_driver_joint", "left_coupler_joint", "left_spring_link_joint", "left_follower_joint"):
+            a = m.jnt_qposadr[jn[name]]
+            assert abs(out["qpos"][0, a] - q_gold[a]) < 5e-4, (f64, name, out["qpos"][0, a], q_gold[a])
+        assert np.abs(out["qpos"][0, :3] - q_gold[:3]).max() < 1e-5 and np.abs(out["qvel"][0]).max() < 1e-3

@@ -20,9 +20,20 @@ L = lane1.sim(m)
 sched = MgsRolloutCfg(150, 60, 10, 0, 0.01, 0.01)
 lab, _ = L.stability(pose7[lo:hi], joints[lo:hi], info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], sched)
 full = shard.gather_labels(lab, len(pose7))
+ref, _ = L.stability(pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], sched)
+assert full.shape == ref.shape and (full == ref).all(), (full, ref)
+# the env-level path: rounds of world x chunk with the enough_stable early stop (shard.evaluate_sharded)
+evaluated = []
+def run_range(lo, hi):
+    evaluated.append(hi - lo)
+    return L.stability(pose7[lo:hi], joints[lo:hi], info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], sched)[0]
+for enough in (None, 1, 2, 100):
+    del evaluated[:]
+    got = shard.evaluate_sharded(len(pose7), run_range, enough, chunk=2)
+    assert (got == shard.apply_enough_stable(ref, enough)).all(), (enough, got, ref)
+    if enough == 1 and ref[:4].any():
+        assert sum(evaluated) <= 2  # first round (2 ranks x 2 candidates) already reached the target: no second round
 if rank == 0:
-    ref, _ = L.stability(pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], sched)
-    assert full.shape == ref.shape and (full == ref).all(), (full, ref)
     print("GLOO_OK", full.astype(int))
 dist.destroy_process_group()
 """

@@ -1,42 +1,101 @@
-"""Label agreement of the CUDA path (fp32 product build and the fp64 ablation) with the fp64 oracle, full
-8000-step schedule, per gripper.  Run on the GPU box: python tools/label_agreement.py [n_per_gripper]"""
-import json, os, sys, time
+"""Label agreement of the CUDA path (fp32 product build and the fp64 ablation) with the fp64 oracle over the full 8000-step
+schedule, per gripper, on MARGINAL candidate sets (scenes.workload(..., marginal=True): oracle stable fraction 0.2-0.6, so that a
+constant predictor cannot score well).
+
+  python tools/label_agreement.py --make-oracle [n]   (CPU, anywhere)  oracle labels -> tests/golden/labels_r2/*.npz
+  python tools/label_agreement.py [n] [grippers]      (GPU box)        CUDA labels vs the cached oracle labels
+                                                                       -> gpurun_out/label_agreement_r2.json (copy to profiles/)
+The cache keys on a checksum of the candidate arrays: if a workload generator changes, the cache is refused, not silently reused.
+"""
+import hashlib, json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from mj_grasp_sim_b200 import scenes
-from mj_grasp_sim_b200.lib import BatchSim, MgsRolloutCfg, SO_PATH_F64
-from oracle.oracle import RolloutCfg, batch
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-only = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None  # e.g. "shadow,leap"
-rows = []
-for gripper, kind, seeds in (("panda", "cube", [0]), ("panda", "hull", [0, 1]), ("vx300", "hull", [0, 1]), ("robotiq2f85", "hull", [0, 1]),
-                             ("allegro", "hull", [0]), ("leap", "hull", [0]), ("shadow", "hull", [0])):
-    if only is not None and gripper not in only:
-        continue
-    for seed in seeds:
-        m, info, pose7, joints = scenes.workload(gripper, kind, seed, n)
-        rep = scenes.GRIPPERS[gripper]["repose"]
-        sched = (3000, 3000, 500, rep, 0.1, 0.02)
-        t = time.time()
-        ofree, _ = batch(m, 0, pose7.astype(np.float64), info["base_qposadr"], joints.astype(np.float64), info["joint_qposadr"], info["close_ctrl"], RolloutCfg(*sched), os.cpu_count())
-        olab, osteps = batch(m, 1, pose7.astype(np.float64), info["base_qposadr"], joints.astype(np.float64), info["joint_qposadr"], info["close_ctrl"], RolloutCfg(*sched), os.cpu_count())
-        t_or = time.time() - t
-        row = dict(gripper=gripper, object=f"{kind}:{seed}", n=n, oracle_stable=float(olab.mean()), oracle_free=float(ofree.mean()), oracle_s=round(t_or, 1))
-        for tag, f64 in (("f32", False), ("f64", True)):
-            if f64 and not os.path.exists(SO_PATH_F64):
-                continue
-            G = BatchSim(m, f64=f64)
+GOLD = os.path.join(ROOT, "tests", "golden", "labels_r2")
+# (gripper, object kind, object seeds): n candidates per object
+SETS = (("panda", "hull", (0, 1)), ("vx300", "hull", (0, 1)), ("robotiq2f85", "hull", (0, 1)), ("allegro", "hull", (0, 1)),
+        ("leap", "hull", (0, 1)), ("shadow", "hull", (0, 1)))
+SCHED = lambda g: (3000, 3000, 500, scenes.GRIPPERS[g]["repose"], 0.1, 0.02)
+
+
+def checksum(pose7, joints):
+    return hashlib.sha256(np.ascontiguousarray(pose7).tobytes() + np.ascontiguousarray(joints).tobytes()).hexdigest()[:16]
+
+
+def cache_path(gripper, kind, seed, n):
+    return os.path.join(GOLD, f"{gripper}_{kind}{seed}_{n}.npz")
+
+
+def load_oracle(gripper, kind, seed, n, pose7, joints):
+    d = np.load(cache_path(gripper, kind, seed, n))
+    if str(d["checksum"]) != checksum(pose7, joints):
+        raise RuntimeError(f"oracle label cache {cache_path(gripper, kind, seed, n)} was made for different candidates: rerun --make-oracle")
+    return d["free"].astype(bool), d["stable"].astype(bool), d["steps"]
+
+
+def make_oracle(n, only):
+    from oracle.oracle import RolloutCfg, batch
+    os.makedirs(GOLD, exist_ok=True)
+    for gripper, kind, seeds in SETS:
+        if only and gripper not in only:
+            continue
+        for seed in seeds:
+            m, info, pose7, joints = scenes.workload(gripper, kind, seed, n, marginal=True)
+            a = (pose7.astype(np.float64), info["base_qposadr"], joints.astype(np.float64), info["joint_qposadr"], info["close_ctrl"],
+                 RolloutCfg(*SCHED(gripper)), os.cpu_count() or 1)
             t = time.time()
-            free = G.collision_mask(pose7, joints, info["joint_qposadr"], info["base_qposadr"])
-            lab, steps = G.stability(pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], MgsRolloutCfg(*sched))
-            row[f"{tag}_free_agree"] = float((free == ofree).mean())
-            row[f"{tag}_stable_agree"] = float((lab == olab).mean())
-            row[f"{tag}_overflow"] = G.overflow_count()
-            row[f"{tag}_s"] = round(time.time() - t, 1)
-            row[f"{tag}_env_steps"] = int(steps.sum())
-            G.close()
-        rows.append(row)
-        print(json.dumps(row), flush=True)
-json.dump(rows, open(os.path.join(ROOT, "gpurun_out", os.environ.get("MGS_LABELS_OUT", "label_agreement.json")), "w"), indent=1)
+            free, _ = batch(m, 0, *a)
+            lab, steps = batch(m, 1, *a)
+            np.savez_compressed(cache_path(gripper, kind, seed, n), free=free, stable=lab, steps=steps.astype(np.int32),
+                                checksum=checksum(pose7, joints))
+            print(json.dumps(dict(gripper=gripper, object=f"{kind}:{seed}", n=n, oracle_free=float(free.mean()), oracle_stable=float(lab.mean()),
+                                  seconds=round(time.time() - t, 1))), flush=True)
+
+
+def measure(n, only):
+    from mj_grasp_sim_b200.lib import BatchSim, MgsRolloutCfg, SO_PATH_F64
+    rows = []
+    for gripper, kind, seeds in SETS:
+        if only and gripper not in only:
+            continue
+        for seed in seeds:
+            m, info, pose7, joints = scenes.workload(gripper, kind, seed, n, marginal=True)
+            ofree, olab, osteps = load_oracle(gripper, kind, seed, n, pose7, joints)
+            row = dict(gripper=gripper, object=f"{kind}:{seed}", n=n, marginal=scenes.MARGINAL[gripper], oracle_stable=float(olab.mean()),
+                       oracle_free=float(ofree.mean()))
+            for tag, f64 in (("f32", False), ("f64", True)):
+                if f64 and not os.path.exists(SO_PATH_F64):
+                    continue
+                G = BatchSim(m, f64=f64)
+                t = time.time()
+                free = G.collision_mask(pose7, joints, info["joint_qposadr"], info["base_qposadr"])
+                lab, steps = G.stability(pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], MgsRolloutCfg(*SCHED(gripper)))
+                row[f"{tag}_free_agree"] = float((free == ofree).mean())
+                row[f"{tag}_stable_agree"] = float((lab == olab).mean())
+                row[f"{tag}_stable_fraction"] = float(lab.mean())
+                row[f"{tag}_false_pos"] = int((lab & ~olab).sum())
+                row[f"{tag}_false_neg"] = int((~lab & olab).sum())
+                row[f"{tag}_overflow"] = G.overflow_count()
+                row[f"{tag}_s"] = round(time.time() - t, 1)
+                row[f"{tag}_env_steps"] = int(steps.sum())
+                G.close()
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+    # per-gripper totals
+    tot = {}
+    for r in rows:
+        t = tot.setdefault(r["gripper"], dict(n=0, f32=0.0, f64=0.0, stable=0.0))
+        t["n"] += r["n"]; t["f32"] += r["f32_stable_agree"] * r["n"]; t["f64"] += r.get("f64_stable_agree", 0.0) * r["n"]; t["stable"] += r["oracle_stable"] * r["n"]
+    summary = {g: dict(n=t["n"], oracle_stable=t["stable"] / t["n"], f32_stable_agree=t["f32"] / t["n"], f64_stable_agree=t["f64"] / t["n"]) for g, t in tot.items()}
+    print(json.dumps(summary), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(dict(rows=rows, per_gripper=summary), open(os.path.join(ROOT, "gpurun_out", os.environ.get("MGS_LABELS_OUT", "label_agreement_r2.json")), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    n = int(args[0]) if args else 512
+    only = set(args[1].split(",")) if len(args) > 1 else None
+    (make_oracle if "--make-oracle" in sys.argv else measure)(n, only)
