@@ -8,6 +8,28 @@
 #pragma once
 #include "mgs_collide.cuh"
 
+// accumulator types of the precision-critical reductions of the Newton solve (ablation switches)
+#ifdef MGS_ACC64_JAR
+typedef double acc_jar_t;
+#else
+typedef real acc_jar_t;
+#endif
+#ifdef MGS_ACC64_GRAD
+typedef double acc_grad_t;
+#else
+typedef real acc_grad_t;
+#endif
+#ifdef MGS_ACC64_LS
+typedef double acc_ls_t;
+#else
+typedef real acc_ls_t;
+#endif
+#ifdef MGS_ACC64_HESS
+typedef double acc_hess_t;
+#else
+typedef real acc_hess_t;
+#endif
+
 // constraint row tag: type (2 bits) | state (3 bits) | id
 #define EFC_TAG(i) (IARR(EF(efc_tsi))[i])
 #define EFC_TYPE(i) (EFC_TAG(i) & 3)
@@ -452,12 +474,19 @@ MGS_DEVN void eval_point_w(Env &e, const real *qacc) {
   const int nv = MD.nv;
   #pragma unroll 1
   PFOR(i, EH.nefc) {
-    real t = -EF(efc_aref)[i];
+    acc_jar_t t = -(acc_jar_t)EF(efc_aref)[i];
     MGS_UNROLL_INNER
-    for (int d = 0; d < nv; d++) t += EF(J)[i * nv + d] * qacc[d];
-    EF(efc_jar)[i] = t;
+    for (int d = 0; d < nv; d++) t += (acc_jar_t)EF(J)[i * nv + d] * (acc_jar_t)qacc[d];
+    EF(efc_jar)[i] = (real)t;
   }
-  matvec_w(EF(Ma), EF(M), qacc, nv);  // ends with WSYNC
+  #pragma unroll 1
+  PFOR(i, nv) {
+    acc_jar_t t = 0;
+    MGS_UNROLL_INNER
+    for (int j = 0; j < nv; j++) t += (acc_jar_t)EF(M)[i * nv + j] * (acc_jar_t)qacc[j];
+    EF(Ma)[i] = (real)t;
+  }
+  WSYNC();
 }
 MGS_DEV real gauss_cost_w(const Env &e, const real *qacc) {
   real g = 0;
@@ -502,11 +531,11 @@ MGS_DEVN void newton_hessian_w(Env &e) {
   #pragma unroll 1
   PFOR(idx, npairs) {
     const int ab = LDG(MD.tri_ab + idx), a = ab >> 8, b = ab & 255;  // lower-triangle index table
-    real s = EF(M)[a * nv + b];
+    acc_hess_t s = EF(M)[a * nv + b];
     const real *Ja = EF(J) + a, *Jb = EF(J) + b;
     MGS_UNROLL_INNER
-    for (int i = 0; i < nefc; i++) s += W[i] * Ja[i * nv] * Jb[i * nv];
-    EF(H)[a * nv + b] = s;
+    for (int i = 0; i < nefc; i++) s += (acc_hess_t)W[i] * (acc_hess_t)Ja[i * nv] * (acc_hess_t)Jb[i * nv];
+    EF(H)[a * nv + b] = (real)s;
   }
   // contacts on the cone surface (usually few): every lane rebuilds the small block, lanes split (a,b)
   #pragma unroll 1
@@ -561,9 +590,10 @@ MGS_DEVN void solve_newton_w(Env &e) {
     real gn = 0;
     #pragma unroll 1
     PFOR(d, nv) {
-      real t = EF(Ma)[d] - EF(qfrc_smooth)[d];
+      acc_grad_t tt = (acc_grad_t)EF(Ma)[d] - (acc_grad_t)EF(qfrc_smooth)[d];
       MGS_UNROLL_INNER
-      for (int i = 0; i < EH.nefc; i++) t -= EF(J)[i * nv + d] * EF(efc_force)[i];
+      for (int i = 0; i < EH.nefc; i++) tt -= (acc_grad_t)EF(J)[i * nv + d] * (acc_grad_t)EF(efc_force)[i];
+      const real t = (real)tt;
       EF(grad)[d] = t;
       EF(search)[d] = t;
       gn += t * t;
@@ -572,7 +602,10 @@ MGS_DEVN void solve_newton_w(Env &e) {
     // fp32: the gradient cannot be resolved below ~eps * |force terms|; floor the tolerance accordingly.  (A per-step
     // rounding-noise estimate of the gradient, K * eps * |terms| with K = 2..8, was tried as a further floor: it never
     // binds - the warm starts that iterate are far above the noise - so it is not kept.)
-    real tol_eff = fmax(MD.tolerance, R_(20.0) * (real)REAL_EPS * scale * fabs(cost));
+#ifndef MGS_TOL_FLOOR_K
+#define MGS_TOL_FLOOR_K 20.0
+#endif
+    real tol_eff = fmax(MD.tolerance, (real)MGS_TOL_FLOOR_K * (real)REAL_EPS * scale * fabs(cost));
     // (MuJoCo tests the gradient only after an iteration; a warm start that already meets the tolerance skips
     // the Hessian here - the two answers differ by less than the solver tolerance.)
 #ifdef MGS_NO_EARLY_GRAD_EXIT
@@ -595,10 +628,10 @@ MGS_DEVN void solve_newton_w(Env &e) {
     }
     #pragma unroll 1
     PFOR(i, EH.nefc) {
-      real t = 0;
+      acc_ls_t t = 0;
       MGS_UNROLL_INNER
-      for (int d = 0; d < nv; d++) t += EF(J)[i * nv + d] * EF(search)[d];
-      EF(efc_jv)[i] = t;
+      for (int d = 0; d < nv; d++) t += (acc_ls_t)EF(J)[i * nv + d] * (acc_ls_t)EF(search)[d];
+      EF(efc_jv)[i] = (real)t;
     }
     g1 = wsum(g1); g2 = wsum(g2); sn = wsum(sn);
     WSYNC();
@@ -665,8 +698,10 @@ MGS_DEVN void solve_newton_w(Env &e) {
       break;
     }
     EH.niter = iter + 1;
-    tol_eff = fmax(MD.tolerance, R_(20.0) * (real)REAL_EPS * scale * fabs(cost));
+    tol_eff = fmax(MD.tolerance, (real)MGS_TOL_FLOOR_K * (real)REAL_EPS * scale * fabs(cost));
+#ifndef MGS_NO_IMPROVEMENT_EXIT
     if (scale * (oldcost - cost) < tol_eff) break;
+#endif
   }
   WSYNC();
 }
@@ -845,7 +880,7 @@ MGS_DEVN void solve_noslip_w(Env &e) {
   //   divided by such inertias is tens of rad/s^2 on EVERY step: with the force-space start 23 % of VX300 rollouts blew up
   //   (1-lane fp32 host build vs oracle, 48 candidates), with the primal start the labels agree 48/48.  The primal iterate is
   //   the better-conditioned value of the same quantity; the two coincide for a converged solve.
-#ifdef MGS_REAL_DOUBLE
+#if defined(MGS_REAL_DOUBLE) || defined(MGS_NOSLIP_FORCE_START)
   #pragma unroll 1
   PFOR(d, nv) {
     real t = 0;

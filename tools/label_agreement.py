@@ -66,7 +66,7 @@ def measure(n, only):
             row = dict(gripper=gripper, object=f"{kind}:{seed}", n=n, marginal=scenes.MARGINAL[gripper], oracle_stable=float(olab.mean()),
                        oracle_free=float(ofree.mean()))
             for tag, f64 in (("f32", False), ("f64", True)):
-                if f64 and not os.path.exists(SO_PATH_F64):
+                if f64 and (not os.path.exists(SO_PATH_F64) or os.environ.get("MGS_LABELS_SKIP_F64")):
                     continue
                 G = BatchSim(m, f64=f64)
                 t = time.time()
