@@ -25,6 +25,15 @@ typedef float real;
 #define REAL_EPS 1.2e-7f
 #endif
 #define MGS_MINVAL R_(1e-15)
+// fp32 build: qpos carries a low-order companion word (qpos = hi + lo, integrated in double): with h = 1 ms a slow creep
+// (|qvel| < ~1e-4) moves a coordinate by less than one fp32 ulp per step, so plain fp32 accumulation either stalls or rounds
+// the creep to whole ulps - which is what decides marginal grasps over thousands of steps.
+#if !defined(MGS_REAL_DOUBLE) && !defined(MGS_NO_QPOS_COMP)
+#define MGS_QPOS_COMP 1
+#define MGS_NQ_LO(nq) (nq)
+#else
+#define MGS_NQ_LO(nq) 0
+#endif
 
 #ifdef MGS_HOST
 #define MGS_DEV static inline
@@ -113,7 +122,7 @@ struct DevModel {
 // temporaries) and SOLVER (constraint rows) are never live at the same time, so they OVERLAY each
 // other - shared memory per environment is what bounds the number of resident warps per SM.
 #define MGS_LAYOUT_PERSIST(X)                                                                                      \
-  X(hdr, 8) X(qpos, nq) X(qvel, nv) X(qacc_ws, nv) X(ctrl, nu) X(mocap, 7 * nmocap)                                          \
+  X(hdr, 8) X(qpos, nq) X(qpos_lo, MGS_NQ_LO(nq)) X(qvel, nv) X(qacc_ws, nv) X(ctrl, nu) X(mocap, 7 * nmocap)                                          \
   X(xpos, 3 * nbody) X(xquat, 4 * nbody) X(xmat, 9 * nbody) X(rootcom, 3 * nbody) X(cdof, 6 * nv)                  \
   X(M, nv * nv) X(Minv, nv * nv) X(H, nv * nv)                                                                     \
   X(ten_length, ntendon) X(ten_J, ntendon * nv) X(act_moment, nu * nv) X(act_force, nu) X(act_length, nu)          \

@@ -16,7 +16,7 @@ static inline int mgs_diag_stride(int nv, int nbody, int ncon_max, int nefc_max)
 
 MGS_DEVN void reset_w(Env &e) {
   #pragma unroll 1
-  PFOR(i, MD.nq) EF(qpos)[i] = LDG(MD.qpos0 + i);
+  PFOR(i, MD.nq) { EF(qpos)[i] = LDG(MD.qpos0 + i); QPOS_LO_CLEAR(i); }
   #pragma unroll 1
   PFOR(i, MD.nv) { EF(qvel)[i] = 0; EF(qacc_ws)[i] = 0; }
   #pragma unroll 1
@@ -40,7 +40,7 @@ MGS_DEVN void place_w(Env &e, const float *pose7, const float *joints) {
     #pragma unroll 1
     PFOR(one, 1) {
       #pragma unroll 1
-      for (int k = 0; k < PRM.nj; k++) EF(qpos)[PRM.joint_qposadr[k]] = (real)LDG(joints + k);
+      for (int k = 0; k < PRM.nj; k++) { EF(qpos)[PRM.joint_qposadr[k]] = (real)LDG(joints + k); QPOS_LO_CLEAR(PRM.joint_qposadr[k]); }
     }
     WSYNC();
   }
@@ -48,6 +48,7 @@ MGS_DEVN void place_w(Env &e, const float *pose7, const float *joints) {
   PFOR(k, 7) {
     real v = (real)LDG(pose7 + k);
     EF(qpos)[PRM.base_qposadr + k] = v;
+    QPOS_LO_CLEAR(PRM.base_qposadr + k);
     EF(mocap)[k] = v;
   }
   WSYNC();
@@ -146,7 +147,7 @@ MGS_DEVN void load_record_w(Env &e, const real *in) {
   #pragma unroll 1
   PFOR(i, 4 * LY.ncache) IARR(EF(mpr_cache))[i] = (i & 3) == 3 ? 0 : -1;
   #pragma unroll 1
-  PFOR(i, MD.nq) EF(qpos)[i] = in[i];
+  PFOR(i, MD.nq) { EF(qpos)[i] = in[i]; QPOS_LO_CLEAR(i); }
   #pragma unroll 1
   PFOR(i, MD.nv) { EF(qvel)[i] = in[MD.nq + i]; EF(qacc_ws)[i] = in[MD.nq + MD.nv + i]; }
   #pragma unroll 1

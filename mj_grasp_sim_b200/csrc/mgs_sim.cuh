@@ -154,6 +154,11 @@ MGS_DEV void env_bind(Env &e, real *base) {
   WSYNC();
 }
 #define IARR(p) ((int *)(p))
+#ifdef MGS_QPOS_COMP
+#define QPOS_LO_CLEAR(i) (EF(qpos_lo)[i] = 0)
+#else
+#define QPOS_LO_CLEAR(i) ((void)0)
+#endif
 
 // ---------------------------------------------------------------------------------- dense linear algebra (warp)
 // `blocked` != 0: the matrix is block diagonal with one block per kinematic tree (the mass matrix M and
@@ -388,8 +393,17 @@ MGS_DEVN void kinematics_w(Env &e) {
         real *anchor = EF(xanchor) + 3 * j, *axis = EF(xaxis) + 3 * j;
         if (jt == JNT_FREE) {
           copy3(xp, EF(qpos) + qa);
+#ifdef MGS_QPOS_COMP
+          // the integrator keeps hi + lo normalised (in double); only an externally written quaternion is renormalised in place
+          xq[0] = EF(qpos)[qa + 3]; xq[1] = EF(qpos)[qa + 4]; xq[2] = EF(qpos)[qa + 5]; xq[3] = EF(qpos)[qa + 6];
+          if (fabs(xq[0] * xq[0] + xq[1] * xq[1] + xq[2] * xq[2] + xq[3] * xq[3] - R_(1.0)) > R_(1e-5)) {
+            normquat(EF(qpos) + qa + 3);
+            for (int k = 3; k < 7; k++) { xq[k - 3] = EF(qpos)[qa + k]; QPOS_LO_CLEAR(qa + k); }
+          } else normquat(xq);
+#else
           normquat(EF(qpos) + qa + 3);
           xq[0] = EF(qpos)[qa + 3]; xq[1] = EF(qpos)[qa + 4]; xq[2] = EF(qpos)[qa + 5]; xq[3] = EF(qpos)[qa + 6];
+#endif
           copy3(anchor, xp);
           axis[0] = 0; axis[1] = 0; axis[2] = 1;
           continue;

@@ -1091,6 +1091,46 @@ MGS_DEVN void integrate_w(Env &e) {
   #pragma unroll 1
   PFOR(d, nv) EF(qvel)[d] += h * EF(search)[d];
   WSYNC();
+#ifdef MGS_QPOS_COMP
+  // position update on qpos = hi + lo in double (a handful of fp64 operations per joint and step)
+  #pragma unroll 1
+  PFOR(j, MD.njnt) {
+    const int qa = LDG(MD.jnt_qposadr + j), da = LDG(MD.jnt_dofadr + j);
+    const double hd = (double)h;
+    if (LDG(MD.jnt_type + j) == JNT_FREE) {
+      for (int k = 0; k < 3; k++) {
+        const double Q = (double)EF(qpos)[qa + k] + (double)EF(qpos_lo)[qa + k] + hd * (double)EF(qvel)[da + k];
+        const float hi = (float)Q;
+        EF(qpos)[qa + k] = hi; EF(qpos_lo)[qa + k] = (float)(Q - (double)hi);
+      }
+      const double w0 = EF(qvel)[da + 3], w1 = EF(qvel)[da + 4], w2 = EF(qvel)[da + 5];
+      const double wn = sqrt(w0 * w0 + w1 * w1 + w2 * w2), ang = wn * hd;
+      if (ang > 0) {
+        // half-angle sine / cosine: series below 1e-2 rad (error < 1e-17), library calls above
+        const double ha = 0.5 * ang, ha2 = ha * ha;
+        const double sn = (ha < 1e-2 ? ha * (1.0 - ha2 * (1.0 / 6.0) * (1.0 - ha2 * (1.0 / 20.0) * (1.0 - ha2 * (1.0 / 42.0)))) : sin(ha)) / wn;
+        const double cs = ha < 1e-2 ? 1.0 - ha2 * 0.5 * (1.0 - ha2 * (1.0 / 12.0) * (1.0 - ha2 * (1.0 / 30.0))) : cos(ha);
+        const double b0 = cs, b1 = sn * w0, b2 = sn * w1, b3 = sn * w2;
+        const double a0 = (double)EF(qpos)[qa + 3] + (double)EF(qpos_lo)[qa + 3], a1 = (double)EF(qpos)[qa + 4] + (double)EF(qpos_lo)[qa + 4],
+                     a2 = (double)EF(qpos)[qa + 5] + (double)EF(qpos_lo)[qa + 5], a3 = (double)EF(qpos)[qa + 6] + (double)EF(qpos_lo)[qa + 6];
+        double r[4] = {a0 * b0 - a1 * b1 - a2 * b2 - a3 * b3, a0 * b1 + a1 * b0 + a2 * b3 - a3 * b2,
+                       a0 * b2 - a1 * b3 + a2 * b0 + a3 * b1, a0 * b3 + a1 * b2 - a2 * b1 + a3 * b0};
+        const double inv = 1.0 / sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
+        for (int k = 0; k < 4; k++) {
+          const double Q = r[k] * inv;
+          const float hi = (float)Q;
+          EF(qpos)[qa + 3 + k] = hi; EF(qpos_lo)[qa + 3 + k] = (float)(Q - (double)hi);
+        }
+      }
+    } else {
+      const double Q = (double)EF(qpos)[qa] + (double)EF(qpos_lo)[qa] + hd * (double)EF(qvel)[da];
+      const float hi = (float)Q;
+      EF(qpos)[qa] = hi; EF(qpos_lo)[qa] = (float)(Q - (double)hi);
+    }
+  }
+  WSYNC();
+}
+#else
   #pragma unroll 1
   PFOR(j, MD.njnt) {
     int qa = LDG(MD.jnt_qposadr + j), da = LDG(MD.jnt_dofadr + j);
@@ -1109,6 +1149,7 @@ MGS_DEVN void integrate_w(Env &e) {
   }
   WSYNC();
 }
+#endif
 
 // mj_step x nstep; returns nonzero if the state blew up (the env is then labelled failed)
 MGS_DEVN int step_w(Env &e, int nstep, int *steps_done) {
