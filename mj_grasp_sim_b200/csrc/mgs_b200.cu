@@ -78,9 +78,9 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
     blob.nefc_max = blob.rows_static + blob.ncon_max * blob.rows_per_contact;  // the default for this contact capacity
   }
   if (nefc_max > 0) blob.nefc_max = nefc_max;
-  if (blob.ncon_max > 64 || blob.nefc_max < desc->nv || 6 * blob.ncon_max > 2 * blob.nefc_max ||
+  if (blob.ncon_max > 256 || blob.nefc_max < desc->nv || 6 * blob.ncon_max > 2 * blob.nefc_max ||
       blob.nefc_max < blob.dm.ne_rows + blob.dm.nf_rows)
-    return fail("bad contact capacities (need ncon_max <= 64, nefc_max >= 3 * ncon_max and room for the equality / dof-friction rows)");
+    return fail("bad contact capacities (need ncon_max <= 256, nefc_max >= 3 * ncon_max and room for the equality / dof-friction rows)");
   MgsModel *M = new MgsModel();
   memset(M, 0, sizeof(*M));
   M->device = device;

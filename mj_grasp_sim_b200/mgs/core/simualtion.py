@@ -75,6 +75,16 @@ class MjSimulation:
     _sim = None
     _device = None
     _caps = (0, 0)
+    gripper = None
+
+    @property
+    def compute_f64(self) -> bool:
+        """Precision policy of the batched kernel for this environment (gripper.COMPUTE_F64; MGS_PRECISION overrides)."""
+        import os
+        force = os.environ.get("MGS_PRECISION", "").lower()
+        if force in ("f32", "f64"):
+            return force == "f64"
+        return bool(getattr(self.gripper, "COMPUTE_F64", False))
 
     # ---- the batched simulator is created on first use (needs a CUDA device; there is no CPU fallback)
     @property
@@ -84,7 +94,8 @@ class MjSimulation:
             if dev is None:
                 import torch
                 dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
-            self._sim = BatchSim(self.model, device=dev, ncon_max=self._caps[0], nefc_max=self._caps[1], ground_name=self.GROUND_GEOM)
+            self._sim = BatchSim(self.model, device=dev, ncon_max=self._caps[0], nefc_max=self._caps[1], ground_name=self.GROUND_GEOM,
+                                 f64=self.compute_f64)
         return self._sim
 
     # ---- single-environment state -------------------------------------------------------------

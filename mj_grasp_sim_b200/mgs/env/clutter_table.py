@@ -47,7 +47,8 @@ class ClutterTableEnv(MjSimulation):
     def _make_sim(self, caps):
         if caps is None:
             return self.sim
-        return BatchSim(self.model, device=self.sim.device, ncon_max=caps[0], nefc_max=caps[1], ground_name=self.GROUND_GEOM)
+        return BatchSim(self.model, device=self.sim.device, ncon_max=caps[0], nefc_max=caps[1], ground_name=self.GROUND_GEOM,
+                        f64=self.compute_f64)
 
     @property
     def last_overflow(self):

@@ -44,7 +44,7 @@ XML = r"""
 </mujoco>
 """
 
-MAX_CAPS = (64, 0)  # escalation capacities: the library's largest contact count, rows to match
+MAX_CAPS = (128, 0)  # escalation capacities: contacts (rows to match); 4-6x what a grasp normally produces
 
 
 class EscalatingSim:
@@ -112,7 +112,7 @@ class GravitylessObjectGrasping(MjSimulation):
         if caps is None:
             return self.sim
         dev = self.sim.device
-        return BatchSim(self.model, device=dev, ncon_max=caps[0], nefc_max=caps[1], ground_name=self.GROUND_GEOM)
+        return BatchSim(self.model, device=dev, ncon_max=caps[0], nefc_max=caps[1], ground_name=self.GROUND_GEOM, f64=self.compute_f64)
 
     @property
     def last_overflow(self):

@@ -9,6 +9,7 @@ from .base import MjGripper
 
 class GripperAllegro(MjGripper):
     ASSET_DIR = "allegro"
+    COMPUTE_F64 = True
     REPOSE_ON_CLOSE = 1  # close_gripper_at calls set_pose first (allegro.py:354-357)
 
     def __init__(self, pose: SE3Pose):

@@ -20,6 +20,10 @@ class MjGripper:
     FREEJOINT = "freejoint"
     REPOSE_ON_CLOSE = 0
     NSTEP_CLOSE = 3000  # mujoco.mj_step(sim.model, sim.data, nstep=3000) in every close_gripper_at
+    # Arithmetic of the rollout kernel for scenes with this gripper: fp32 for the parallel-jaw grippers; the 16+-dof hands run the
+    # fp64 build of the same kernel (MuJoCo is fp64; on marginal candidate sets the fp32 hands agree with the oracle on 97.4-98.8 %
+    # of the labels, the fp64 build on 98.8-100 %: profiles/label_agreement_r2*.json).  MGS_PRECISION=f32|f64 overrides.
+    COMPUTE_F64 = False
 
     def __init__(self, pose: SE3Pose, base_body: str):
         vec = pose.to_vec(layout="pq", type="wxyz")

@@ -9,6 +9,7 @@ from .base import MjGripper
 
 class GripperLeap(MjGripper):
     ASSET_DIR = "leap"
+    COMPUTE_F64 = True
     REPOSE_ON_CLOSE = 1  # close_gripper_at calls set_pose first (leap.py:406-409)
 
     def __init__(self, pose: SE3Pose):

@@ -28,6 +28,7 @@ def qpos_to_ctrl(qpos):
 
 class GripperShadowRight(MjGripper):
     ASSET_DIR = "shadow"
+    COMPUTE_F64 = True
 
     def __init__(self, pose: SE3Pose, grasp_type=None):
         super().__init__(pose, "rh_wrist")

@@ -74,6 +74,10 @@ GRIPPERS = {
 }
 
 
+# precision policy of the product path per gripper (mgs/gripper/base.py COMPUTE_F64)
+F64_GRIPPERS = ("allegro", "leap", "shadow")
+
+
 def gripper_fragment(name: str):
     g = GRIPPERS[name]
     d = os.path.join(ASSET_PATH, g["dir"])

@@ -53,3 +53,16 @@ def leap_hull():
 def shadow_hull():
     from mj_grasp_sim_b200 import scenes
     return scenes.workload("shadow", "hull", 0, 32)
+
+
+# 64-candidate sets of the label tests at the 0.98 bar (one flip allowed); the 48-candidate fixtures above keep their seeds' draws
+@pytest.fixture(scope="session")
+def robotiq_hull64():
+    from mj_grasp_sim_b200 import scenes
+    return scenes.workload("robotiq2f85", "hull", 0, 64)
+
+
+@pytest.fixture(scope="session")
+def vx300_hull64():
+    from mj_grasp_sim_b200 import scenes
+    return scenes.workload("vx300", "hull", 0, 64)

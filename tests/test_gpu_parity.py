@@ -46,7 +46,7 @@ def test_first_50_steps_fp32(libs, panda_cube):
         assert d["bad"].max() == 0 and d["overflow"].max() == 0
         assert (d["ncon"] == s.ncon).all()
         assert np.abs(u["qpos"] - s.qpos).max() <= 1e-4 * max(1.0, np.abs(s.qpos).max())
-        assert np.abs(u["qvel"] - s.qvel).max() <= 1e-3 * max(1.0, np.abs(s.qvel).max())
+        assert np.abs(u["qvel"] - s.qvel).max() <= 1e-4 * max(1.0, np.abs(s.qvel).max())
         assert np.abs(st - st[0]).max() == 0  # identical inputs -> bitwise identical outputs on every warp
     assert s.ncon > 0
 
@@ -68,7 +68,7 @@ def test_fp64_ablation_matches_oracle_tightly(libs, panda_cube):
     assert np.abs(u["qpos"][0] - s.qpos).max() < 1e-8 and np.abs(u["qvel"][0] - s.qvel).max() < 1e-6
 
 
-@pytest.mark.parametrize("fixture", ["panda_cube", "panda_hull", "robotiq_hull", "vx300_hull"])
+@pytest.mark.parametrize("fixture", ["panda_cube", "panda_hull", "robotiq_hull64", "vx300_hull64"])
 def test_labels_agree_with_oracle(libs, request, fixture):
     mlib, orc = libs
     m, info, pose7, joints = request.getfixturevalue(fixture)
@@ -78,11 +78,37 @@ def test_labels_agree_with_oracle(libs, request, fixture):
     ofree, _ = _oracle_batch(orc, m, info, 0, pose7, joints, FULL)
     olab, osteps = _oracle_batch(orc, m, info, 1, pose7, joints, FULL)
     assert G.overflow_count() == 0
-    assert (free == ofree).mean() >= 0.97
-    assert (lab == olab).mean() >= 0.97  # >= 98 % is the north-star bar over large batches; 48-64 candidates here
+    assert (free == ofree).all()
+    assert (lab == olab).mean() >= 0.98  # 64 candidates: at most one marginal flip (the bar at scale: test_label_agreement_at_the_north_star_bar)
     same = lab == olab
     assert np.array_equal(steps[same & lab], osteps[same & lab])  # survivors run exactly 8000 steps
     assert steps[lab].min() == 8000 if lab.any() else True
+
+
+@pytest.mark.parametrize("gripper", ["panda", "vx300", "robotiq2f85", "allegro", "leap", "shadow"])
+def test_label_agreement_at_the_north_star_bar(libs, gripper):
+    """>= 98 % success-label agreement with the oracle over FULL 8000-step rollouts, 1024 candidates per gripper (two objects x
+    512), on MARGINAL candidate sets (oracle stable fraction 0.06-0.55: a constant predictor scores <= 0.8), with the build the
+    precision policy selects (fp32 parallel-jaw, fp64 hands) and no truncated contact set (overflowed candidates are re-run on
+    the largest capacities and none may remain).  The oracle labels are the committed cache tests/golden/labels_r2 (made by
+    tools/label_agreement.py --make-oracle; refused if the candidate arrays changed)."""
+    import sys
+    from mj_grasp_sim_b200 import scenes
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import label_agreement as la
+    mlib, _ = libs
+    f64 = gripper in scenes.F64_GRIPPERS
+    if f64 and not os.path.exists(mlib.SO_PATH_F64):
+        pytest.fail("the fp64 build (product path of the dexterous hands) is missing")
+    agree = n = 0
+    for seed in (0, 1):
+        r = la.measure_one(gripper, "hull", seed, 512, f64)
+        assert r["overflow"] == 0, r
+        assert r["free_agree"] >= 0.998, r
+        assert 0.05 <= r["oracle_stable"] <= 0.6, r
+        agree += r["stable_agree"] * 512
+        n += 512
+    assert agree / n >= 0.98, (gripper, agree / n)
 
 
 def test_edge_sizes_and_determinism(libs, panda_cube):
@@ -115,12 +141,11 @@ def test_full_size_properties(libs):
     total = 600 + 200 + 40 + 40 + 80
     assert set(np.unique(steps[lab])) <= {total}
     assert steps.max() <= total and steps.min() >= 0
-    assert (steps[~lab] < total).all() or (steps[~lab] <= total).all()
     # a strided sample agrees with the oracle on the same schedule
     idx = np.arange(0, 4096, 64)
     olab, osteps = orc.batch(m, 1, pose7[idx].astype(np.float64), info["base_qposadr"], joints[idx].astype(np.float64),
                              info["joint_qposadr"], info["close_ctrl"], orc.RolloutCfg(600, 200, 40, 0, 0.03, 0.02), os.cpu_count() or 1)
-    assert (lab[idx] == olab).mean() >= 0.95
+    assert (lab[idx] == olab).mean() >= 0.98
     # duplicated candidates get identical labels wherever they sit in the batch
     dup = np.concatenate([pose7[:100], pose7[:100]]), np.concatenate([joints[:100], joints[:100]])
     l2, s2 = G.stability(dup[0], dup[1], info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], sched)
@@ -169,14 +194,14 @@ def test_mgs_env_api_and_cli_files(libs, tmp_path):
     assert (stable == olab).mean() >= 0.97
 
 
-@pytest.mark.parametrize("fixture,bar", [("allegro_hull", 0.9), ("leap_hull", 0.85), ("shadow_hull", 0.85)])
+@pytest.mark.parametrize("fixture,bar", [("allegro_hull", 0.97), ("leap_hull", 0.96), ("shadow_hull", 0.96)])
 def test_dexterous_hands_labels(libs, request, fixture, bar):
-    """16-DoF hands (config 4): hand-object contact is far more chaotic than a parallel-jaw pinch, so the
-    fp32 bar on a small batch is lower; tools/label_agreement.py reports the measured rates at scale."""
+    """16-DoF hands (config 4) on the plain (non-marginal) candidate sets, product precision (fp64 build): 32-48 candidates, at
+    most one flip.  The bar at scale is test_label_agreement_at_the_north_star_bar."""
     mlib, orc = libs
     m, info, pose7, joints = request.getfixturevalue(fixture)
     sched = (3000, 3000, 500, 0 if fixture == "shadow_hull" else 1, 0.1, 0.02)
-    G = mlib.BatchSim(m)
+    G = mlib.BatchSim(m, f64=True)
     lab, steps = G.stability(pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], mlib.MgsRolloutCfg(*sched))
     olab, osteps = _oracle_batch(orc, m, info, 1, pose7, joints, sched)
     assert G.overflow_count() == 0

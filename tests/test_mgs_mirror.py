@@ -83,7 +83,7 @@ def test_cli_pipeline_end_to_end_on_the_host_build(tmp_path, monkeypatch):
     from oracle.oracle import RolloutCfg, batch
     L = mlib.bind(C.CDLL(lane1.build(False)), prefix="l1_")
     from mj_grasp_sim_b200.mgs.core import simualtion as simmod
-    host = lambda model, device=0, ncon_max=0, nefc_max=0, ground_name="geom:ground": mlib.BatchSim(model, lib=L, prefix="l1_", ground_name=ground_name)
+    host = lambda model, device=0, ncon_max=0, nefc_max=0, ground_name="geom:ground", f64=False: mlib.BatchSim(model, lib=L, prefix="l1_", ground_name=ground_name)
     monkeypatch.setattr(simmod, "BatchSim", host)
     monkeypatch.setattr(gog, "BatchSim", host)
     H, joints = gen_grasp_candidates.run("PandaGripper", "hull:0", 6, str(tmp_path), seed=4)

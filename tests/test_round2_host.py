@@ -114,7 +114,7 @@ def _host_env(monkeypatch, gripper_name, obj_id):
     from mj_grasp_sim_b200.mgs.gripper.selector import get_gripper
     from mj_grasp_sim_b200.mgs.obj.selector import get_object
     Lh = mlib.bind(C.CDLL(lane1.build(True)), prefix="l1_")
-    host = lambda model, device=0, ncon_max=0, nefc_max=0, ground_name="geom:ground": mlib.BatchSim(model, lib=Lh, prefix="l1_", ground_name=ground_name)
+    host = lambda model, device=0, ncon_max=0, nefc_max=0, ground_name="geom:ground", f64=False: mlib.BatchSim(model, lib=Lh, prefix="l1_", ground_name=ground_name)
     monkeypatch.setattr(simmod, "BatchSim", host)
     monkeypatch.setattr(gog, "BatchSim", host)
     return gog.GravitylessObjectGrasping(get_gripper(gripper_name), get_object(obj_id))

@@ -54,41 +54,67 @@ def make_oracle(n, only):
                                   seconds=round(time.time() - t, 1))), flush=True)
 
 
+def run_escalated(G_small, make_big, call):
+    """Labels with NO truncated contact set: candidates whose environment overflowed the default capacities are re-run on the
+    largest ones (what mgs.env's EscalatingSim does).  Returns (arrays..., n_overflow_first, n_overflow_left)."""
+    out = [np.array(o) for o in call(G_small, None)]
+    n = len(out[0])
+    over = np.nonzero(G_small.last_aux(n)["overflow"])[0]
+    left = 0
+    if len(over):
+        big = make_big()
+        again = call(big, over)
+        for o, a in zip(out, again):
+            o[over] = a
+        left = int(big.last_aux(len(over))["overflow"].sum())
+        big.close()
+    return out, int(len(over)), left
+
+
+def measure_one(gripper, kind, seed, n, f64):
+    """CUDA labels (one build) of one cached marginal set vs the oracle's.  Returns a dict of figures."""
+    from mj_grasp_sim_b200.lib import BatchSim, MgsRolloutCfg
+    m, info, pose7, joints = scenes.workload(gripper, kind, seed, n, marginal=True)
+    ofree, olab, osteps = load_oracle(gripper, kind, seed, n, pose7, joints)
+    G = BatchSim(m, f64=f64)
+    t = time.time()
+    free = G.collision_mask(pose7, joints, info["joint_qposadr"], info["base_qposadr"])
+    sel = lambda idx: (pose7, joints) if idx is None else (pose7[idx], joints[idx])
+    (lab, steps), over0, over1 = run_escalated(
+        G, lambda: BatchSim(m, f64=f64, ncon_max=128), lambda sim, idx: sim.stability(*sel(idx), info["joint_qposadr"], info["base_qposadr"],
+                                                                                  info["close_ctrl"], MgsRolloutCfg(*SCHED(gripper))))
+    lab = lab.astype(bool)
+    G.close()
+    return dict(free_agree=float((free == ofree).mean()), stable_agree=float((lab == olab).mean()), stable_fraction=float(lab.mean()),
+                false_pos=int((lab & ~olab).sum()), false_neg=int((~lab & olab).sum()), overflow_first_pass=over0, overflow=over1,
+                s=round(time.time() - t, 1), env_steps=int(steps.sum()), oracle_stable=float(olab.mean()), oracle_free=float(ofree.mean()))
+
+
 def measure(n, only):
-    from mj_grasp_sim_b200.lib import BatchSim, MgsRolloutCfg, SO_PATH_F64
+    from mj_grasp_sim_b200.lib import SO_PATH_F64
     rows = []
     for gripper, kind, seeds in SETS:
         if only and gripper not in only:
             continue
         for seed in seeds:
-            m, info, pose7, joints = scenes.workload(gripper, kind, seed, n, marginal=True)
-            ofree, olab, osteps = load_oracle(gripper, kind, seed, n, pose7, joints)
-            row = dict(gripper=gripper, object=f"{kind}:{seed}", n=n, marginal=scenes.MARGINAL[gripper], oracle_stable=float(olab.mean()),
-                       oracle_free=float(ofree.mean()))
+            row = dict(gripper=gripper, object=f"{kind}:{seed}", n=n, marginal=scenes.MARGINAL[gripper],
+                       product="f64" if gripper in scenes.F64_GRIPPERS else "f32")
             for tag, f64 in (("f32", False), ("f64", True)):
                 if f64 and (not os.path.exists(SO_PATH_F64) or os.environ.get("MGS_LABELS_SKIP_F64")):
                     continue
-                G = BatchSim(m, f64=f64)
-                t = time.time()
-                free = G.collision_mask(pose7, joints, info["joint_qposadr"], info["base_qposadr"])
-                lab, steps = G.stability(pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], MgsRolloutCfg(*SCHED(gripper)))
-                row[f"{tag}_free_agree"] = float((free == ofree).mean())
-                row[f"{tag}_stable_agree"] = float((lab == olab).mean())
-                row[f"{tag}_stable_fraction"] = float(lab.mean())
-                row[f"{tag}_false_pos"] = int((lab & ~olab).sum())
-                row[f"{tag}_false_neg"] = int((~lab & olab).sum())
-                row[f"{tag}_overflow"] = G.overflow_count()
-                row[f"{tag}_s"] = round(time.time() - t, 1)
-                row[f"{tag}_env_steps"] = int(steps.sum())
-                G.close()
+                r = measure_one(gripper, kind, seed, n, f64)
+                row["oracle_stable"], row["oracle_free"] = r.pop("oracle_stable"), r.pop("oracle_free")
+                row.update({f"{tag}_{k}": v for k, v in r.items()})
             rows.append(row)
             print(json.dumps(row), flush=True)
-    # per-gripper totals
+    # per-gripper totals; "product" = the build the precision policy selects for that gripper (mgs/gripper/base.py COMPUTE_F64)
     tot = {}
     for r in rows:
-        t = tot.setdefault(r["gripper"], dict(n=0, f32=0.0, f64=0.0, stable=0.0))
+        t = tot.setdefault(r["gripper"], dict(n=0, f32=0.0, f64=0.0, stable=0.0, product=r["product"], overflow=0))
         t["n"] += r["n"]; t["f32"] += r["f32_stable_agree"] * r["n"]; t["f64"] += r.get("f64_stable_agree", 0.0) * r["n"]; t["stable"] += r["oracle_stable"] * r["n"]
-    summary = {g: dict(n=t["n"], oracle_stable=t["stable"] / t["n"], f32_stable_agree=t["f32"] / t["n"], f64_stable_agree=t["f64"] / t["n"]) for g, t in tot.items()}
+        t["overflow"] += r.get(r["product"] + "_overflow", 0)
+    summary = {g: dict(n=t["n"], oracle_stable=t["stable"] / t["n"], f32_stable_agree=t["f32"] / t["n"], f64_stable_agree=t["f64"] / t["n"],
+                       product=t["product"], product_stable_agree=t[t["product"]] / t["n"], product_overflow=t["overflow"]) for g, t in tot.items()}
     print(json.dumps(summary), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(dict(rows=rows, per_gripper=summary), open(os.path.join(ROOT, "gpurun_out", os.environ.get("MGS_LABELS_OUT", "label_agreement_r2.json")), "w"), indent=1)
