@@ -44,8 +44,10 @@ typedef struct MgsRolloutCfg {
 } MgsRolloutCfg;
 
 typedef struct MgsModelInfo {
-  int nq, nv, nu, nmocap, state_stride, diag_stride, ncon_max, nefc_max, smem_bytes_per_env, warps_per_block,
-      blocks_per_sm, num_sms, real_bytes;
+  int nq, nv, nu, nmocap, state_stride, diag_stride, ncon_max, nefc_max, smem_bytes_per_env,
+      warps_per_block, /* environments per CTA */
+      blocks_per_sm, num_sms, real_bytes,
+      lanes_per_env; /* threads that share one environment: 32 (warp per environment) or 256 (environment per CTA) */
 } MgsModelInfo;
 
 int mgs_model_create(const MgsModelDesc *desc, int device, MgsModel **out);

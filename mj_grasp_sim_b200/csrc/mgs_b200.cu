@@ -89,25 +89,26 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
   M->dm = blob.dm;
   rebase_model(M->dm, M->d_blob);
   CU(cudaMalloc(&M->d_counter, 2 * sizeof(unsigned int)));  // [0] work queue head, [1] environments that overflowed a capacity
-  layout_compute(&M->L, desc->nq, desc->nv, desc->nu, desc->nbody, desc->njnt, desc->nmocap, desc->ntendon, desc->ncgeom, blob.ncon_max,
-                 blob.nefc_max, desc->npair);
+  auto make_layout = [&](int lanes) {
+    layout_compute(&M->L, desc->nq, desc->nv, desc->nu, desc->nbody, desc->njnt, desc->nmocap, desc->ntendon, desc->ncgeom, blob.ncon_max,
+                   blob.nefc_max, desc->npair, blob.dm.nM, lanes);
+    return (int)(M->L.total * sizeof(real));
+  };
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   M->num_sms = prop.multiProcessorCount;
-  const int env_bytes = (int)(M->L.total * sizeof(real));
-  if ((size_t)env_bytes > prop.sharedMemPerBlockOptin) {
-    delete M;
-    return fail("model needs more shared memory per environment than one CTA can have (env-per-block variant not built yet)");
-  }
-  // CTA size = the warps-per-block that gives the most resident warps per SM (shared memory per environment and the
-  // per-CTA reservation decide).  First with the 16-warp variant; if at most 12 environments fit per SM anyway, the
-  // 12-warp variant (more registers per thread) takes over.
+  int env_bytes = make_layout(32);
+  // Warp-per-environment variants: CTA size = the warps-per-block that gives the most resident warps per SM (shared memory per
+  // environment and the per-CTA reservation decide).  First with the 16-warp variant; if at most 12 environments fit per SM
+  // anyway, the 12-warp variant (more registers per thread) takes over.  Scenes that leave room for fewer than
+  // MGS_WIDE_BELOW_ENVS environments per SM (or for none) run the environment-per-CTA variant instead.
   const char *force_wpb = getenv("MGS_WARPS_PER_BLOCK");  // tuning knobs: force the CTA size / the variant
   const char *force_var = getenv("MGS_KERNEL_VARIANT");
+  const bool force_wide = force_var && std::string(force_var) == "wide";
   std::lock_guard<std::mutex> lock(g_launch_mu);  // the occupancy sweep changes the variants' shared-memory attribute
   const MgsKernelOps *variants[2] = {mgs_kernel_ops_w16(), mgs_kernel_ops_w12()};
   int best_warps = 0;
-  for (int v = 0; v < 2; v++) {
+  for (int v = 0; v < 2 && !force_wide && (size_t)env_bytes <= prop.sharedMemPerBlockOptin; v++) {
     const MgsKernelOps *ops = variants[v];
     if (force_var && std::string(force_var) != (v == 0 ? "w16" : "w12")) continue;
     if (v == 1 && !force_var && (best_warps == 0 || best_warps > ops->max_warps || M->blocks_per_sm != 1)) break;
@@ -121,6 +122,19 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
       if (occ * w >= vb && occ > 0) { vb = occ * w; vw = w; vo = occ; }  // ties go to the LARGER CTA: one CTA per SM keeps all resident warps stage-aligned
     }
     if (vb >= best_warps && vb > 0) { best_warps = vb; M->warps_per_block = vw; M->blocks_per_sm = vo; M->ops = ops; }
+  }
+  if (force_wide || (!force_var && best_warps < MGS_WIDE_BELOW_ENVS)) {
+    const MgsKernelOps *ops = mgs_kernel_ops_wide();
+    env_bytes = make_layout(ops->lanes_per_env);
+    if ((size_t)env_bytes > prop.sharedMemPerBlockOptin) {
+      delete M;
+      return fail("model needs more shared memory per environment than one CTA can have: lower ncon_max / nefc_max");
+    }
+    CU(ops->prepare(env_bytes));
+    int occ = 0;
+    CU(ops->occupancy(&occ, ops->lanes_per_env, (size_t)env_bytes));
+    best_warps = occ;
+    M->warps_per_block = 1; M->blocks_per_sm = occ; M->ops = ops;
   }
   if (best_warps == 0) { delete M; return fail("kernel does not fit on this device"); }
   M->smem_per_block = env_bytes * M->warps_per_block;
@@ -177,6 +191,7 @@ extern "C" int mgs_model_info(const MgsModel *M, MgsModelInfo *info) {
   info->smem_bytes_per_env = (int)(M->L.total * sizeof(real));
   info->warps_per_block = M->warps_per_block; info->blocks_per_sm = M->blocks_per_sm; info->num_sms = M->num_sms;
   info->real_bytes = (int)sizeof(real);
+  info->lanes_per_env = M->ops->lanes_per_env;
   return 0;
 }
 
@@ -221,7 +236,7 @@ static int launch(MgsModel *M, const RolloutParams &prm, const BatchIO &io_in, c
   CU(M->ops->prepare(M->smem_per_block));
   KernelConsts kc;
   kc.m = M->dm; kc.L = M->L; kc.prm = prm; kc.io = io;
-  CU(M->ops->launch(&kc, grid, wpb * 32, (size_t)(M->smem_per_block / M->warps_per_block) * wpb, st));
+  CU(M->ops->launch(&kc, grid, wpb * M->ops->lanes_per_env, (size_t)(M->smem_per_block / M->warps_per_block) * wpb, st));
   g_launches++;
   CU(cudaEventRecord(g_last_done[M->device], st));
   return 0;

@@ -349,18 +349,14 @@ MGS_DEVN int best_face_w(int hull, real nx, real ny, real nz, real *align) {
 MGS_DEV void best_face_lanes(int want, const GeomRef &g, const real *n, int *face, real *align) {
   real nl[3] = {0, 0, 0};
   if (want) mulmatTvec3(nl, g.R, n);
-  unsigned m = wballot(want);
+  int pending = want;
   #pragma unroll 1
-  while (m) {
-#ifdef MGS_HOST
-    const int src = 0;
-#else
-    const int src = __ffs(m) - 1;
-#endif
-    m &= m - 1;
+  for (;;) {
+    const int src = wfirst(pending);  // lanes with a request are served in lane order
+    if (src < 0) break;
     real al;
     const int f = best_face_w(wbcasti(g.hull, src), wbcast(nl[0], src), wbcast(nl[1], src), wbcast(nl[2], src), &al);
-    if (MGS_LANE == src) { *face = f; *align = al; }
+    if (MGS_LANE == src) { *face = f; *align = al; pending = 0; }
   }
 }
 MGS_DEVN int face_polygon(const GeomRef &g, int f, real (*poly)[3], real *nw) {

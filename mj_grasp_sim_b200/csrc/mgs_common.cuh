@@ -43,6 +43,20 @@ typedef float real;
 #define WSYNC() ((void)0)
 #define LDG(p) (*(p))
 #define MGS_STAGE_BARRIER(k) ((void)0)
+#elif defined(MGS_WIDE)
+// ENVIRONMENT PER CTA ("wide" variant, -DMGS_WIDE=<threads>): the same device source with the lane abstraction widened to a
+// whole thread block - every PFOR loop is strided over MGS_WIDE threads, WSYNC is a CTA barrier and the "warp" collectives
+// (wsum, wany, wrank, ...) are block-level.  For scenes whose per-environment state fills most of an SM's shared memory
+// (BASELINE configs[4]: Shadow hand + 10 objects, nv = 94, ~220 KB): with one warp per environment a single warp would run on
+// the SM; here 8 warps share the environment's rows / pairs / matrix entries.  No stage barriers: there is nothing to align.
+#include <cuda_runtime.h>
+#define MGS_DEV __device__ __forceinline__
+#define MGS_DEVN static __device__ __noinline__
+#define LANES MGS_WIDE
+#define MGS_LANE ((int)threadIdx.x)
+#define WSYNC() __syncthreads()
+#define LDG(p) __ldg(p)
+#define MGS_STAGE_BARRIER(k) ((void)0)
 #else
 #include <cuda_runtime.h>
 #define MGS_DEV __device__ __forceinline__
@@ -91,7 +105,7 @@ enum { MGS_MODE_STEP = 0, MGS_MODE_COLLISION = 1, MGS_MODE_STABILITY = 2, MGS_MO
 // Model constants on the device (all pointers into one read-only blob).
 struct DevModel {
   int nq, nv, nu, nbody, njnt, neq, nmocap, ntendon, nwrap, ncgeom, npair, nhull;
-  int maxdepth, max_tree_dofs, ne_rows, nf_rows, ngravcomp, dofmask_words, cone_elliptic, iterations, ls_iterations, noslip_iterations, mpr_iterations, ground_geomid;
+  int maxdepth, max_tree_dofs, nM, ne_rows, nf_rows, ngravcomp, dofmask_words, cone_elliptic, iterations, ls_iterations, noslip_iterations, mpr_iterations, ground_geomid;
   real timestep, impratio, tolerance, ls_tolerance, noslip_tolerance, mpr_tolerance, meaninertia, gravity[3];
   const int *body_parentid, *body_rootid, *body_mocapid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_depth;
   const real *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0, *body_subtreemass, *body_gravcomp;
@@ -112,6 +126,12 @@ struct DevModel {
   const real *actuator_gainprm, *actuator_biasprm, *actuator_ctrlrange, *actuator_forcerange, *actuator_gear;
   const int *eq_type, *eq_obj1id, *eq_obj2id, *eq_active, *eq_rowadr, *tri_ab;
   const int *dof_frictionrank;       // [nv]: rank of dof d among the dofs with frictionloss > 0 (its row is ne_rows + rank), -1 if none
+  // Block storage of the per-tree matrices (M, M^-1, the blocked uses of the H scratch): the block of a kinematic tree with t dofs
+  // is a dense t x t row-major tile, tiles back to back (nM = sum t^2 words instead of nv^2).  Entry (i, j) of one tree lives at
+  // dof_rowoff[i] + j; rows of one tree are dof_treenum apart.
+  const int *dof_rowoff;             // [nv]
+  const int *blk_ij;                 // [nM]: (i << 8) | j of every stored entry
+  const int *tri_madr;               // [nv (nv + 1) / 2], parallel to tri_ab: address of M(a, b), -1 when a and b are in different trees
   const unsigned int *body_dofmask;  // [nbody][dofmask_words]: bit d set = dof d is on the path from the body to its root
   const real *eq_data, *eq_solref, *eq_solimp;
   const real *mocap_pos0, *mocap_quat0;
@@ -124,11 +144,11 @@ struct DevModel {
 #define MGS_LAYOUT_PERSIST(X)                                                                                      \
   X(hdr, 8) X(qpos, nq) X(qpos_lo, MGS_NQ_LO(nq)) X(qvel, nv) X(qacc_ws, nv) X(ctrl, nu) X(mocap, 7 * nmocap)                                          \
   X(xpos, 3 * nbody) X(xquat, 4 * nbody) X(xmat, 9 * nbody) X(rootcom, 3 * nbody) X(cdof, 6 * nv)                  \
-  X(M, nv * nv) X(Minv, nv * nv) X(H, nv * nv)                                                                     \
+  X(M, nM) X(Minv, nM) X(H, nv * nv)                                                                     \
   X(ten_length, ntendon) X(ten_J, ntendon * nv) X(act_moment, nu * nv) X(act_force, nu) X(act_length, nu)          \
   X(qfrc_smooth, nv) X(qacc_smooth, nv) X(qacc, nv) X(qfrc_constraint, nv) X(Ma, nv) X(grad, nv) X(search, nv)     \
   X(Mv, nv) X(wvec, nv) X(con_pos, 3 * ncon_max) X(con_normal, 3 * ncon_max) X(con_dist, ncon_max)                 \
-  X(con_mu, ncon_max) X(con_pair, ncon_max) X(con_efc, ncon_max) X(nsB, 3 * nv) X(nsS, 32) X(mpr_cache, 4 * ncache)
+  X(con_mu, ncon_max) X(con_pair, ncon_max) X(con_efc, ncon_max) X(nsB, 3 * nv) X(nsS, lanes) X(mpr_cache, 4 * ncache)
 #define MGS_LAYOUT_TRANSIENT(X)                                                                                    \
   X(xipos, 3 * nbody) X(ximat, 9 * nbody) X(xanchor, 3 * njnt) X(xaxis, 3 * njnt) X(gxpos, 3 * ncgeom)             \
   X(gxmat, 9 * ncgeom) X(cinert, 10 * nbody) X(crb, 10 * nbody) X(cdof_dot, 6 * nv) X(cvel, 6 * nbody)             \
@@ -151,8 +171,9 @@ struct Layout {
 #define MGS_CLIP_STRIDE 109
 #define MGS_MPR_CACHE_MAX 128  // geom pairs (the first ones of the list: the object pairs) whose last MPR result is remembered:
                                // 4 words per pair - portal vertex pairs or separating axis (words 0-2), hill-climb start vertices (3)
+// `lanes`: threads that share one environment (32 for the warp-per-environment variants, MGS_WIDE for the env-per-CTA one)
 static inline void layout_compute(Layout *L, int nq, int nv, int nu, int nbody, int njnt, int nmocap, int ntendon, int ncgeom,
-                                  int ncon_max, int nefc_max, int npair) {
+                                  int ncon_max, int nefc_max, int npair, int nM, int lanes = 32) {
   int off = 0;
   const int ncache = npair < MGS_MPR_CACHE_MAX ? npair : MGS_MPR_CACHE_MAX;
   L->ncache = ncache;

@@ -13,6 +13,24 @@
 #define MGS_STR(x) MGS_STR_(x)
 #define MGS_KERNEL MGS_CAT(mgs_rollout_kernel_, MGS_KERNEL_TAG)
 
+#ifdef MGS_WIDE
+// environment per CTA: the whole block works on one candidate at a time, pulled from the same global queue
+__global__ void __launch_bounds__(MGS_WIDE, 1)
+MGS_KERNEL() {
+  __shared__ unsigned int s_env;
+  real *base = reinterpret_cast<real *>(mgs_smem_raw);
+  Env e;
+  for (;;) {
+    if (threadIdx.x == 0) s_env = atomicAdd(IO.work_counter, 1u);
+    __syncthreads();
+    const unsigned int env = s_env;
+    __syncthreads();
+    if (env >= (unsigned int)PRM.n) break;
+    env_bind(e, base);
+    run_env_w(e, (int)env);
+  }
+}
+#else
 __global__ void __launch_bounds__(MGS_MAX_WARPS_PER_BLOCK * 32, 1)
 MGS_KERNEL() {
   real *base = reinterpret_cast<real *>(mgs_smem_raw) + (size_t)(threadIdx.x >> 5) * LY.total;
@@ -28,6 +46,8 @@ MGS_KERNEL() {
   }
   // a warp that runs out of work leaves; exited warps no longer count towards the CTA barrier
 }
+
+#endif
 
 namespace {
 cudaError_t ops_prepare(int smem_bytes) {
@@ -45,7 +65,11 @@ cudaError_t ops_launch(const KernelConsts *kc, int grid, int threads, size_t sme
   MGS_KERNEL<<<grid, threads, smem_bytes, st>>>();
   return cudaGetLastError();
 }
-const MgsKernelOps g_ops = {MGS_MAX_WARPS_PER_BLOCK, "mgs_rollout_kernel_" MGS_STR(MGS_KERNEL_TAG), ops_prepare, ops_occupancy, ops_launch};
+#ifdef MGS_WIDE
+const MgsKernelOps g_ops = {1, MGS_WIDE, "mgs_rollout_kernel_" MGS_STR(MGS_KERNEL_TAG), ops_prepare, ops_occupancy, ops_launch};
+#else
+const MgsKernelOps g_ops = {MGS_MAX_WARPS_PER_BLOCK, 32, "mgs_rollout_kernel_" MGS_STR(MGS_KERNEL_TAG), ops_prepare, ops_occupancy, ops_launch};
+#endif
 }  // namespace
 
 const MgsKernelOps *MGS_CAT(mgs_kernel_ops_, MGS_KERNEL_TAG)() { return &g_ops; }

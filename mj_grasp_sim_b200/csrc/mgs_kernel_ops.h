@@ -10,7 +10,8 @@
 struct KernelConsts;
 
 struct MgsKernelOps {
-  int max_warps;
+  int max_warps;      // environments per CTA at most (warp variants: one warp each; wide variant: 1)
+  int lanes_per_env;  // threads that share one environment: 32, or MGS_WIDE for the environment-per-CTA variant
   const char *name;
   cudaError_t (*prepare)(int smem_bytes);                                   // carve-out + max dynamic shared memory
   cudaError_t (*occupancy)(int *blocks_per_sm, int threads, size_t smem_bytes);
@@ -19,3 +20,7 @@ struct MgsKernelOps {
 
 const MgsKernelOps *mgs_kernel_ops_w16();
 const MgsKernelOps *mgs_kernel_ops_w12();
+// environment per CTA (csrc/mgs_kernel_wide.cu): scenes whose state leaves room for fewer than MGS_WIDE_BELOW_ENVS
+// warp-environments per SM (Shadow hand in 10-object clutter: one)
+const MgsKernelOps *mgs_kernel_ops_wide();
+#define MGS_WIDE_BELOW_ENVS 4

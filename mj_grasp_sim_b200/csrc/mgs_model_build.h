@@ -91,6 +91,25 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
     m.dof_treeadr = put<int>(b, tadr.data(), nv);
     m.dof_treenum = put<int>(b, tnum.data(), nv);
     m.max_tree_dofs = maxt;
+    // block storage of the per-tree matrices
+    std::vector<int> rowoff(nv > 0 ? nv : 1, 0), ij;
+    int nM = 0;
+    for (int i = 0; i < nv;) {
+      const int t = tnum[i];
+      for (int r = 0; r < t; r++) {
+        rowoff[i + r] = nM + r * t - i;
+        for (int c = 0; c < t; c++) ij.push_back(((i + r) << 8) | (i + c));
+      }
+      nM += t * t;
+      i += t;
+    }
+    m.nM = nM;
+    m.dof_rowoff = put<int>(b, rowoff.data(), nv);
+    m.blk_ij = put<int>(b, ij.data(), ij.size());
+    std::vector<int> tm;
+    for (int a = 0; a < nv; a++)
+      for (int c = 0; c <= a; c++) tm.push_back(tadr[a] == tadr[c] ? rowoff[a] + c : -1);
+    m.tri_madr = put<int>(b, tm.data(), tm.size());
   }
   PR_(dof_armature, nv); PR_(dof_damping, nv); PR_(dof_frictionloss, nv); PR_(dof_solref, 2 * nv); PR_(dof_solimp, 5 * nv); PR_(dof_invweight0, nv);
   PI_(cgeom_geomid, ng); PI_(cgeom_type, ng); PI_(cgeom_bodyid, ng); PI_(cgeom_hullid, ng);

@@ -197,7 +197,10 @@ MGS_DEVN void write_diag_w(const Env &e, real *o) {
   PFOR(d, nv) { p[d] = EF(qacc)[d]; p[nv + d] = EF(qacc_smooth)[d]; p[2 * nv + d] = EF(qfrc_smooth)[d]; }
   p += 3 * nv;
   #pragma unroll 1
-  PFOR(i, nv * nv) p[i] = EF(M)[i];
+  PFOR(i, nv * nv) {  // the diagnostics carry M dense
+    const int r = i / nv, c = i - r * nv;
+    p[i] = (LDG(MD.dof_treeadr + r) == LDG(MD.dof_treeadr + c)) ? EF(M)[LDG(MD.dof_rowoff + r) + c] : R_(0.0);
+  }
   p += nv * nv;
   #pragma unroll 1
   PFOR(i, 3 * MD.nbody) p[i] = EF(xpos)[i];

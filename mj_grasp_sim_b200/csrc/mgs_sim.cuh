@@ -18,11 +18,114 @@ MGS_DEV real wsum(real x) { return x; }
 MGS_DEV int wsumi(int x) { return x; }
 MGS_DEV int wany(int p) { return p; }
 MGS_DEV int wscan_excl(int x, int *total) { *total = x; return 0; }
-MGS_DEV unsigned wballot(int p) { return p ? 1u : 0u; }
 MGS_DEV real wbcast(real x, int src) { (void)src; return x; }
 MGS_DEV int wbcasti(int x, int src) { (void)src; return x; }
 MGS_DEV void wargmax(real &v, int &idx) { (void)v; (void)idx; }
 MGS_DEV int wrank(int p, int *total) { *total = p ? 1 : 0; return 0; }
+MGS_DEV int wfirst(int p) { return p ? 0 : -1; }
+#elif defined(MGS_WIDE)
+// block-level versions (environment per CTA).  Every collective is called by ALL threads of the CTA from converged code, like
+// the full-mask warp intrinsics of the warp variant; results are identical on every thread and do not depend on timing
+// (partial results are combined in warp order).  The trailing barrier of each lets the scratch be reused by the next call.
+#define MGS_NWARP (MGS_WIDE / 32)
+static __shared__ real mgs_cta_r[MGS_NWARP];
+static __shared__ int mgs_cta_i[MGS_NWARP];
+MGS_DEV real wsum(real x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if ((threadIdx.x & 31) == 0) mgs_cta_r[threadIdx.x >> 5] = x;
+  __syncthreads();
+  real s = mgs_cta_r[0];
+#pragma unroll
+  for (int w = 1; w < MGS_NWARP; w++) s += mgs_cta_r[w];
+  __syncthreads();
+  return s;
+}
+MGS_DEV int wsumi(int x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if ((threadIdx.x & 31) == 0) mgs_cta_i[threadIdx.x >> 5] = x;
+  __syncthreads();
+  int s = mgs_cta_i[0];
+#pragma unroll
+  for (int w = 1; w < MGS_NWARP; w++) s += mgs_cta_i[w];
+  __syncthreads();
+  return s;
+}
+MGS_DEV int wany(int p) { return __syncthreads_or(p); }
+MGS_DEV real wbcast(real x, int src) {
+  if ((int)threadIdx.x == src) mgs_cta_r[0] = x;
+  __syncthreads();
+  const real r = mgs_cta_r[0];
+  __syncthreads();
+  return r;
+}
+MGS_DEV int wbcasti(int x, int src) {
+  if ((int)threadIdx.x == src) mgs_cta_i[0] = x;
+  __syncthreads();
+  const int r = mgs_cta_i[0];
+  __syncthreads();
+  return r;
+}
+// number of threads below this one with `p` set (and the CTA total)
+MGS_DEV int wrank(int p, int *total) {
+  const unsigned m = __ballot_sync(0xffffffffu, p);
+  if ((threadIdx.x & 31) == 0) mgs_cta_i[threadIdx.x >> 5] = __popc(m);
+  __syncthreads();
+  int below = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < MGS_NWARP; w++) { const int c = mgs_cta_i[w]; if (w < (int)(threadIdx.x >> 5)) below += c; tot += c; }
+  __syncthreads();
+  *total = tot;
+  return below + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+}
+// smallest thread index with `p` set, -1 if none
+MGS_DEV int wfirst(int p) {
+  const unsigned m = __ballot_sync(0xffffffffu, p);
+  if ((threadIdx.x & 31) == 0) mgs_cta_i[threadIdx.x >> 5] = m ? (int)(threadIdx.x & ~31u) + __ffs(m) - 1 : 0x7fffffff;
+  __syncthreads();
+  int f = mgs_cta_i[0];
+#pragma unroll
+  for (int w = 1; w < MGS_NWARP; w++) f = min(f, mgs_cta_i[w]);
+  __syncthreads();
+  return f == 0x7fffffff ? -1 : f;
+}
+// arg-max over the CTA; ties go to the smaller index
+MGS_DEV void wargmax(real &v, int &idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const real v2 = __shfl_xor_sync(0xffffffffu, v, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
+  }
+  if ((threadIdx.x & 31) == 0) { mgs_cta_r[threadIdx.x >> 5] = v; mgs_cta_i[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  v = mgs_cta_r[0]; idx = mgs_cta_i[0];
+#pragma unroll
+  for (int w = 1; w < MGS_NWARP; w++) {
+    const real v2 = mgs_cta_r[w];
+    const int i2 = mgs_cta_i[w];
+    if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
+  }
+  __syncthreads();
+}
+MGS_DEV int wscan_excl(int x, int *total) {
+  const int lane = threadIdx.x & 31;
+  int v = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) mgs_cta_i[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int below = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < MGS_NWARP; w++) { const int c = mgs_cta_i[w]; if (w < (int)(threadIdx.x >> 5)) below += c; tot += c; }
+  __syncthreads();
+  *total = tot;
+  return below + v - x;
+}
 #else
 MGS_DEV real wsum(real x) {
 #pragma unroll
@@ -35,7 +138,7 @@ MGS_DEV int wsumi(int x) {
   return x;
 }
 MGS_DEV int wany(int p) { return __any_sync(0xffffffffu, p); }
-MGS_DEV unsigned wballot(int p) { return __ballot_sync(0xffffffffu, p); }
+MGS_DEV int wfirst(int p) { return __ffs(__ballot_sync(0xffffffffu, p)) - 1; }
 MGS_DEV real wbcast(real x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 MGS_DEV int wbcasti(int x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 // number of lanes below this one with `p` set (and the warp total)
@@ -144,7 +247,11 @@ struct Env { real *base; };
 #define EBASE (e.base)
 #else
 extern __shared__ __align__(16) unsigned char mgs_smem_raw[];
+#ifdef MGS_WIDE
+#define EBASE (reinterpret_cast<real *>(mgs_smem_raw))
+#else
 #define EBASE (reinterpret_cast<real *>(mgs_smem_raw) + (size_t)(threadIdx.x >> 5) * LY.total)
+#endif
 #endif
 #define EF(name) (EBASE + LY.name)
 #define EH (*reinterpret_cast<EnvHdr *>(EF(hdr)))
@@ -161,49 +268,60 @@ MGS_DEV void env_bind(Env &e, real *base) {
 #endif
 
 // ---------------------------------------------------------------------------------- dense linear algebra (warp)
-// `blocked` != 0: the matrix is block diagonal with one block per kinematic tree (the mass matrix M and
-// the implicit-integration matrix M - h dF/dv).  Lane i works on row i of ITS tree's block, all blocks
-// advance one column per step together, so the number of column steps is the largest tree, not nv.
-// In-place lower Cholesky of the n x n matrix A (row-major, only the lower triangle is read).
+// `blocked` != 0: the matrix is block diagonal with one block per kinematic tree (the mass matrix M and the implicit-integration
+// matrix M - h dF/dv) and is STORED as such (DevModel.dof_rowoff: a t x t tile per tree, nM words in all).  Lane i works on row i
+// of ITS tree's block, all blocks advance one column per step together, so the number of column steps is the largest tree, not nv.
+// `blocked` == 0: dense n x n row-major (the Newton Hessian).  Both cases address through (ro, s): entry (i, k) of lane i's own row
+// is A[ro + k], entry (k, j) of another row of the same tile / matrix is A[ro + (k - i) * s + j].
+// In-place lower Cholesky (only the lower triangle is read).
+MGS_DEV void row_addr(int i, int n, int blocked, int &ro, int &s, int &tadr, int &tnum) {
+  if (blocked) { ro = LDG(MD.dof_rowoff + i); tadr = LDG(MD.dof_treeadr + i); tnum = LDG(MD.dof_treenum + i); s = tnum; }
+  else { ro = i * n; s = n; tadr = 0; tnum = n; }
+}
 #ifdef MGS_HOST
 // 1-lane host build: the same factorisation written serially (per block)
 MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
   for (int j = 0; j < n; j++) {
-    const int hi = blocked ? MD.dof_treeadr[j] + MD.dof_treenum[j] : n;
-    real d = A[j * n + j];
+    int ro, s, tadr, tnum;
+    row_addr(j, n, blocked, ro, s, tadr, tnum);
+    const int hi = tadr + tnum;
+    real d = A[ro + j];
     d = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL);
     const real inv = R_(1.0) / d;
-    A[j * n + j] = d;
-    for (int i = j + 1; i < hi; i++) A[i * n + j] *= inv;
+    A[ro + j] = d;
+    for (int i = j + 1; i < hi; i++) A[ro + (i - j) * s + j] *= inv;
     for (int i = j + 1; i < hi; i++) {
-      const real lij = A[i * n + j];
-      for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+      const real lij = A[ro + (i - j) * s + j];
+      for (int k = j + 1; k <= i; k++) A[ro + (i - j) * s + k] -= lij * A[ro + (k - j) * s + j];
     }
   }
 }
 MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
   for (int k = 0; k < n; k++) {
-    const int hi = blocked ? MD.dof_treeadr[k] + MD.dof_treenum[k] : n;
-    const real xk = x[k] / L[k * n + k];
+    int ro, s, tadr, tnum;
+    row_addr(k, n, blocked, ro, s, tadr, tnum);
+    const int hi = tadr + tnum;
+    const real xk = x[k] / L[ro + k];
     x[k] = xk;
-    for (int i = k + 1; i < hi; i++) x[i] -= L[i * n + k] * xk;
+    for (int i = k + 1; i < hi; i++) x[i] -= L[ro + (i - k) * s + k] * xk;
   }
   for (int k = n - 1; k >= 0; k--) {
-    const int lo = blocked ? MD.dof_treeadr[k] : 0;
-    const real xk = x[k] / L[k * n + k];
+    int ro, s, tadr, tnum;
+    row_addr(k, n, blocked, ro, s, tadr, tnum);
+    const real xk = x[k] / L[ro + k];
     x[k] = xk;
-    for (int i = lo; i < k; i++) x[i] -= L[k * n + i] * xk;
+    for (int i = tadr; i < k; i++) x[i] -= L[ro + i] * xk;
   }
 }
 #else
-// GPU: lanes own rows (row i on lane i % 32); every diagonal block advances one pivot column per step.
-// n <= 32 (every in-scope model except Shadow): one row per lane, pivots kept in registers.
+// GPU: lanes own rows (row i on lane i % LANES); every diagonal block advances one pivot column per step.
+// Warp variants, n <= 32 (every in-scope single-object model except Shadow): one row per lane, pivots kept in registers.
 MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
   const int nsteps = blocked ? MD.max_tree_dofs : n;
-  if (n <= LANES) {
+  if (LANES == 32 && n <= LANES) {  // (warp variants only: pivots by shuffle)
     const int i = MGS_LANE;
-    int tadr = 0, tnum = n;
-    if (blocked && i < n) { tadr = LDG(MD.dof_treeadr + i); tnum = LDG(MD.dof_treenum + i); }
+    int tadr = 0, tnum = n, ro = i * n, s = n;
+    if (i < n) row_addr(i, n, blocked, ro, s, tadr, tnum);
     WSYNC();
     #pragma unroll 1
     for (int t = 0; t < nsteps; t++) {
@@ -213,18 +331,21 @@ MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
       // lane writes its square root back only after the column has been scaled (second phase)
       real d = 1, lij = 0;
       if (live) {
-        d = A[j * n + j];
+        d = A[ro + (j - i) * s + j];
         d = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL);
         // (IEEE sqrt and division on purpose: replacing them by MUFU.RSQ / __fdividef (<= 2 ulp) was measured - no speed-up on
         // Panda, +3 % on Robotiq, but the fp32 trajectory error of the 16-dof hands over the first 50 steps grew 4-13x)
-        if (i > j) { lij = A[i * n + j] * (R_(1.0) / d); A[i * n + j] = lij; }
+        if (i > j) { lij = A[ro + j] * (R_(1.0) / d); A[ro + j] = lij; }
       }
       WSYNC();
       if (live) {
-        if (i == j) A[j * n + j] = d;
+        if (i == j) A[ro + j] = d;
         else if (i > j) {
+          const real *col = A + ro + (j + 1 - i) * s + j;  // A[k][j], k = j + 1 ..
+          real *row = A + ro + j + 1;
+          const int cnt = i - j;
           MGS_UNROLL_INNER
-          for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+          for (int k = 0; k < cnt; k++) row[k] -= lij * col[k * s];
         }
       }
       WSYNC();
@@ -237,25 +358,31 @@ MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
     WSYNC();
     #pragma unroll 1
     PFOR(i, n) {  // pivot rows: sqrt of the diagonal
-      const int j = blocked ? LDG(MD.dof_treeadr + i) + t : t;
-      if (i == j) { const real d = A[j * n + j]; A[j * n + j] = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL); }
+      int ro, s, tadr, tnum;
+      row_addr(i, n, blocked, ro, s, tadr, tnum);
+      if (i == tadr + t) { const real d = A[ro + i]; A[ro + i] = sqrt(d > MGS_MINVAL ? d : MGS_MINVAL); }
     }
     WSYNC();
     #pragma unroll 1
     PFOR(i, n) {  // scale the pivot column
-      const int j = blocked ? LDG(MD.dof_treeadr + i) + t : t;
-      const int live = blocked ? (t < LDG(MD.dof_treenum + i)) : 1;
-      if (live && i > j) A[i * n + j] /= A[j * n + j];
+      int ro, s, tadr, tnum;
+      row_addr(i, n, blocked, ro, s, tadr, tnum);
+      const int j = tadr + t;
+      if (t < tnum && i > j) A[ro + j] /= A[ro + (j - i) * s + j];
     }
     WSYNC();
     #pragma unroll 1
     PFOR(i, n) {  // trailing update of this lane's rows
-      const int j = blocked ? LDG(MD.dof_treeadr + i) + t : t;
-      const int live = blocked ? (t < LDG(MD.dof_treenum + i)) : 1;
-      if (live && i > j) {
-        const real lij = A[i * n + j];
-        #pragma unroll 1
-        for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+      int ro, s, tadr, tnum;
+      row_addr(i, n, blocked, ro, s, tadr, tnum);
+      const int j = tadr + t;
+      if (t < tnum && i > j) {
+        const real lij = A[ro + j];
+        const real *col = A + ro + (j + 1 - i) * s + j;
+        real *row = A + ro + j + 1;
+        const int cnt = i - j;
+        MGS_UNROLL_INNER
+        for (int k = 0; k < cnt; k++) row[k] -= lij * col[k * s];
       }
     }
   }
@@ -264,10 +391,10 @@ MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
 // x <- (L L')^-1 x (column-oriented substitution)
 MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
   const int nsteps = blocked ? MD.max_tree_dofs : n;
-  if (n <= LANES) {
+  if (LANES == 32 && n <= LANES) {
     const int i = MGS_LANE;
-    int tadr = 0, tnum = n;
-    if (blocked && i < n) { tadr = LDG(MD.dof_treeadr + i); tnum = LDG(MD.dof_treenum + i); }
+    int tadr = 0, tnum = n, ro = i * n, s = n;
+    if (i < n) row_addr(i, n, blocked, ro, s, tadr, tnum);
     // the right-hand side lives in registers (lane i owns x[i]); x[k] travels by shuffle: no shared-memory
     // round trip and no warp barrier per column
     WSYNC();
@@ -277,9 +404,9 @@ MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
       const int k = tadr + t, live = (i < n) && (t < tnum);
       const real xs = __shfl_sync(0xffffffffu, xi, live ? k : i);
       if (live) {
-        const real xk = xs / L[k * n + k];
+        const real xk = xs / L[ro + (k - i) * s + k];
         if (i == k) xi = xk;
-        else if (i > k) xi -= L[i * n + k] * xk;
+        else if (i > k) xi -= L[ro + k] * xk;
       }
     }
     #pragma unroll 1
@@ -287,9 +414,9 @@ MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
       const int k = tadr + t, live = (i < n) && (t < tnum);
       const real xs = __shfl_sync(0xffffffffu, xi, live ? k : i);
       if (live) {
-        const real xk = xs / L[k * n + k];
+        const real xk = xs / L[ro + (k - i) * s + k];
         if (i == k) xi = xk;
-        else if (i < k) xi -= L[k * n + i] * xk;
+        else if (i < k) xi -= L[ro + (k - i) * s + i] * xk;
       }
     }
     if (i < n) x[i] = xi;
@@ -304,54 +431,60 @@ MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
       WSYNC();
       #pragma unroll 1
       PFOR(i, n) {
-        const int k = blocked ? LDG(MD.dof_treeadr + i) + t : t;
-        if (i == k) x[k] /= L[k * n + k];
+        int ro, s, tadr, tnum;
+        row_addr(i, n, blocked, ro, s, tadr, tnum);
+        if (i == tadr + t) x[i] /= L[ro + i];
       }
       WSYNC();
       #pragma unroll 1
       PFOR(i, n) {
-        const int k = blocked ? LDG(MD.dof_treeadr + i) + t : t;
-        const int live = blocked ? (t < LDG(MD.dof_treenum + i)) : 1;
-        if (!live) continue;
-        if (pass == 0 && i > k) x[i] -= L[i * n + k] * x[k];
-        else if (pass == 1 && i < k) x[i] -= L[k * n + i] * x[k];
+        int ro, s, tadr, tnum;
+        row_addr(i, n, blocked, ro, s, tadr, tnum);
+        const int k = tadr + t;
+        if (t >= tnum) continue;
+        if (pass == 0 && i > k) x[i] -= L[ro + k] * x[k];
+        else if (pass == 1 && i < k) x[i] -= L[ro + (k - i) * s + i] * x[k];
       }
     }
   }
   WSYNC();
 }
 #endif
-// Ainv <- (L L')^-1, one column per lane (serial substitution inside the lane)
-MGS_DEVN void chol_inverse_w(const real *L, real *Ainv, int n, int blocked) {
+// Ainv <- (L L')^-1 of a block-diagonal factor, both in block storage; one column per lane (serial substitution inside the lane)
+MGS_DEVN void chol_inverse_w(const real *L, real *Ainv, int n) {
   #pragma unroll 1
   PFOR(c, n) {
-    const int lo = blocked ? LDG(MD.dof_treeadr + c) : 0, hi = blocked ? lo + LDG(MD.dof_treenum + c) : n;
+    const int lo = LDG(MD.dof_treeadr + c), t = LDG(MD.dof_treenum + c);
+    const int bo = LDG(MD.dof_rowoff + lo) + lo;  // first word of the tile
+    const real *Lt = L + bo;
+    real *At = Ainv + bo;
+    const int cl = c - lo;
     #pragma unroll 1
-    for (int i = 0; i < n; i++) if (i < lo || i >= hi) Ainv[i * n + c] = 0;
-    #pragma unroll 1
-    for (int i = lo; i < hi; i++) {
-      real s = (i == c) ? R_(1.0) : R_(0.0);
+    for (int i = 0; i < t; i++) {
+      real sacc = (i == cl) ? R_(1.0) : R_(0.0);
       MGS_UNROLL_INNER
-      for (int k = lo; k < i; k++) s -= L[i * n + k] * Ainv[k * n + c];
-      Ainv[i * n + c] = s / L[i * n + i];
+      for (int k = 0; k < i; k++) sacc -= Lt[i * t + k] * At[k * t + cl];
+      At[i * t + cl] = sacc / Lt[i * t + i];
     }
     #pragma unroll 1
-    for (int i = hi - 1; i >= lo; i--) {
-      real s = Ainv[i * n + c];
+    for (int i = t - 1; i >= 0; i--) {
+      real sacc = At[i * t + cl];
       MGS_UNROLL_INNER
-      for (int k = i + 1; k < hi; k++) s -= L[k * n + i] * Ainv[k * n + c];
-      Ainv[i * n + c] = s / L[i * n + i];
+      for (int k = i + 1; k < t; k++) sacc -= Lt[k * t + i] * At[k * t + cl];
+      At[i * t + cl] = sacc / Lt[i * t + i];
     }
   }
   WSYNC();
 }
-// y <- A x for a dense n x n A (lane per row)
+// y <- A x for a block-diagonal A in block storage (lane per row; only the row's own tree contributes)
 MGS_DEVN void matvec_w(real *y, const real *A, const real *x, int n) {
   #pragma unroll 1
   PFOR(i, n) {
+    const int lo = LDG(MD.dof_treeadr + i), hi = lo + LDG(MD.dof_treenum + i);
+    const real *row = A + LDG(MD.dof_rowoff + i);
     real t = 0;
     MGS_UNROLL_INNER
-    for (int j = 0; j < n; j++) t += A[i * n + j] * x[j];
+    for (int j = lo; j < hi; j++) t += row[j] * x[j];
     y[i] = t;
   }
   WSYNC();
@@ -548,7 +681,7 @@ MGS_DEVN void inertia_w(Env &e) {
     }
   }
   #pragma unroll 1
-  PFOR(i, nv * nv) EF(M)[i] = 0;
+  PFOR(i, MD.nM) EF(M)[i] = 0;
   WSYNC();
   // composite inertias: parents absorb their children, deepest level first
   #pragma unroll 1
@@ -572,15 +705,15 @@ MGS_DEVN void inertia_w(Env &e) {
       real v = 0;
       for (int k = 0; k < 6; k++) v += EF(cdof)[6 * j + k] * buf[k];
       if (j == i) v += LDG(MD.dof_armature + i);
-      EF(M)[i * nv + j] = v;
-      EF(M)[j * nv + i] = v;
+      EF(M)[LDG(MD.dof_rowoff + i) + j] = v;
+      EF(M)[LDG(MD.dof_rowoff + j) + i] = v;
     }
   }
   WSYNC();
   #pragma unroll 1
-  PFOR(i, nv * nv) EF(H)[i] = EF(M)[i];
+  PFOR(i, MD.nM) EF(H)[i] = EF(M)[i];  // (block storage in the H scratch)
   chol_factor_w(EF(H), nv, 1);
-  chol_inverse_w(EF(H), EF(Minv), nv, 1);
+  chol_inverse_w(EF(H), EF(Minv), nv);
 }
 
 // fixed tendons + actuator transmission

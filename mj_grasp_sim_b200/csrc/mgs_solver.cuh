@@ -481,9 +481,11 @@ MGS_DEVN void eval_point_w(Env &e, const real *qacc) {
   }
   #pragma unroll 1
   PFOR(i, nv) {
+    const int lo = LDG(MD.dof_treeadr + i), hi = lo + LDG(MD.dof_treenum + i);
+    const real *Mrow = EF(M) + LDG(MD.dof_rowoff + i);
     acc_jar_t t = 0;
     MGS_UNROLL_INNER
-    for (int j = 0; j < nv; j++) t += (acc_jar_t)EF(M)[i * nv + j] * (acc_jar_t)qacc[j];
+    for (int j = lo; j < hi; j++) t += (acc_jar_t)Mrow[j] * (acc_jar_t)qacc[j];
     EF(Ma)[i] = (real)t;
   }
   WSYNC();
@@ -531,7 +533,8 @@ MGS_DEVN void newton_hessian_w(Env &e) {
   #pragma unroll 1
   PFOR(idx, npairs) {
     const int ab = LDG(MD.tri_ab + idx), a = ab >> 8, b = ab & 255;  // lower-triangle index table
-    acc_hess_t s = EF(M)[a * nv + b];
+    const int madr = LDG(MD.tri_madr + idx);  // M is block diagonal: zero between different kinematic trees
+    acc_hess_t s = madr >= 0 ? EF(M)[madr] : R_(0.0);
     const real *Ja = EF(J) + a, *Jb = EF(J) + b;
     MGS_UNROLL_INNER
     for (int i = 0; i < nefc; i++) s += (acc_hess_t)W[i] * (acc_hess_t)Ja[i * nv] * (acc_hess_t)Jb[i * nv];
@@ -851,7 +854,7 @@ MGS_DEV real noslip_contact_w(Env &e, int c, int i, int p, const real *AC, real 
   PFOR(d, nv) {
     const int lo = LDG(MD.dof_treeadr + d), hi = lo + LDG(MD.dof_treenum + d);
     real t = 0;
-    const real *Mrow = EF(Minv) + d * nv;
+    const real *Mrow = EF(Minv) + LDG(MD.dof_rowoff + d);
     MGS_UNROLL_INNER
     for (int k = lo; k < hi; k++) t += Mrow[k] * T[k];
     EF(wvec)[d] += t;
@@ -892,7 +895,7 @@ MGS_DEVN void solve_noslip_w(Env &e) {
   #pragma unroll 1
   PFOR(d, nv) {
     const int lo = LDG(MD.dof_treeadr + d), hi = lo + LDG(MD.dof_treenum + d);
-    const real *Mrow = EF(Minv) + d * nv;
+    const real *Mrow = EF(Minv) + LDG(MD.dof_rowoff + d);
     real t = 0;
     MGS_UNROLL_INNER
     for (int k = lo; k < hi; k++) t += Mrow[k] * T[k];
@@ -919,7 +922,7 @@ MGS_DEVN void solve_noslip_w(Env &e) {
       const int j = (r >= 2 * nv) ? 2 : (r >= nv ? 1 : 0), d = r - j * nv;
       // rows beyond the contact's friction dims are never read (dim 3: j < 2)
       const int lo = LDG(MD.dof_treeadr + d), hi = lo + LDG(MD.dof_treenum + d);
-      const real *Mrow = EF(Minv) + d * nv, *Jrow = EF(J) + (i + 1 + j) * nv;
+      const real *Mrow = EF(Minv) + LDG(MD.dof_rowoff + d), *Jrow = EF(J) + (i + 1 + j) * nv;
       real t = 0;
       MGS_UNROLL_INNER
       for (int k = lo; k < hi; k++) t += Mrow[k] * Jrow[k];
@@ -953,7 +956,7 @@ MGS_DEVN void solve_noslip_w(Env &e) {
         if (ja == 0) continue;
         const int lo = LDG(MD.dof_treeadr + a), hi = lo + LDG(MD.dof_treenum + a);
         real t = 0;
-        const real *Mrow = EF(Minv) + a * nv;
+        const real *Mrow = EF(Minv) + LDG(MD.dof_rowoff + a);
         MGS_UNROLL_INNER
         for (int b2 = lo; b2 < hi; b2++) t += Mrow[b2] * Jk[b2];
         acc += ja * t;
@@ -979,7 +982,9 @@ MGS_DEVN void solve_noslip_w(Env &e) {
     #pragma unroll 1
     for (int i = EH.ne; i < EH.ne + EH.nf; i++) {
       const int d = EFC_ID(i);
-      const real res = EF(qacc_smooth)[d] + EF(wvec)[d] - EF(efc_aref)[i], Aii = EF(Minv)[d * nv + d];
+      const real *Mrow = EF(Minv) + LDG(MD.dof_rowoff + d);  // row d of M^-1 (= column d: symmetric), nonzero inside d's tree
+      const int lo = LDG(MD.dof_treeadr + d), hi = lo + LDG(MD.dof_treenum + d);
+      const real res = EF(qacc_smooth)[d] + EF(wvec)[d] - EF(efc_aref)[i], Aii = Mrow[d];
       const real old = EF(efc_force)[i], fl = EF(efc_aux)[i];
       real fn = old - res / fmax(MGS_MINVAL, Aii);
       fn = fmax(-fl, fmin(fl, fn));
@@ -987,7 +992,7 @@ MGS_DEVN void solve_noslip_w(Env &e) {
       if (change > R_(1e-10)) { fn = old; delta = 0; change = 0; }
       WSYNC();
       #pragma unroll 1
-      PFOR(k, nv) EF(wvec)[k] += EF(Minv)[k * nv + d] * delta;
+      PFOR(k, nv) if (k >= lo && k < hi) EF(wvec)[k] += Mrow[k] * delta;
       PFOR(k, 1) EF(efc_force)[i] = fn;
       improvement -= change;
       WSYNC();
@@ -1067,8 +1072,8 @@ MGS_DEVN void integrate_w(Env &e) {
   const int nv = MD.nv;
   const real h = MD.timestep;
   #pragma unroll 1
-  PFOR(idx, nv * nv) {
-    int i = idx / nv, j = idx - i * nv;
+  PFOR(idx, MD.nM) {  // block storage: one entry of one tree's tile per lane
+    const int ij = LDG(MD.blk_ij + idx), i = ij >> 8, j = ij & 255;
     real a = EF(M)[idx];
     if (i == j) a += h * LDG(MD.dof_damping + i);
     #pragma unroll 1

@@ -28,7 +28,8 @@ class MgsRolloutCfg(C.Structure):
 
 class MgsModelInfo(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("nq", "nv", "nu", "nmocap", "state_stride", "diag_stride", "ncon_max", "nefc_max",
-                                       "smem_bytes_per_env", "warps_per_block", "blocks_per_sm", "num_sms", "real_bytes")]
+                                       "smem_bytes_per_env", "warps_per_block", "blocks_per_sm", "num_sms", "real_bytes",
+                                       "lanes_per_env")]
 
 
 class MgsError(RuntimeError):
@@ -64,9 +65,11 @@ def build(force: bool = False, f64: bool = False) -> str:
     stamp = source_stamp()
     if not force and os.path.exists(so) and _built_stamp(so) == stamp:
         return so
-    # two translation units = two variants of the rollout kernel (16 / 12 warps per CTA, see csrc/mgs_kernel_ops.h)
+    # three translation units = three variants of the rollout kernel (16 / 12 warps per CTA with one environment per warp,
+    # and one environment per 256-thread CTA; see csrc/mgs_kernel_ops.h)
     cmd = ["nvcc"] + NVCC_FLAGS + (["-DMGS_REAL_DOUBLE"] if f64 else []) + [f'-DMGS_BUILD_STAMP="{stamp}"', "-o", so,
-                                                                             os.path.join(CSRC, "mgs_b200.cu"), os.path.join(CSRC, "mgs_kernel_w12.cu")]
+                                                                             os.path.join(CSRC, "mgs_b200.cu"), os.path.join(CSRC, "mgs_kernel_w12.cu"),
+                                                                             os.path.join(CSRC, "mgs_kernel_wide.cu")]
     subprocess.check_call(cmd)
     with open(so + ".stamp", "w") as f:
         f.write(stamp)

@@ -44,7 +44,10 @@ XML = r"""
 </mujoco>
 """
 
-MAX_CAPS = (128, 0)  # escalation capacities: contacts (rows to match); 4-6x what a grasp normally produces
+# escalation capacities, tried in this order until the model fits one CTA's shared memory: contacts (0 rows = rows to match).
+# 256 holds every contact the pair lists of the two-finger grippers can produce (63 pairs x 4 points)
+ESCALATION_CAPS = (256, 128, 96, 64)
+MAX_CAPS = (ESCALATION_CAPS[0], 0)
 
 
 class EscalatingSim:
@@ -65,7 +68,17 @@ class EscalatingSim:
     @property
     def big(self) -> BatchSim:
         if self._big is None:
-            self._big = self._make(MAX_CAPS)
+            err = None
+            for nc in ESCALATION_CAPS:
+                if nc <= self.small.info.ncon_max:
+                    break
+                try:
+                    self._big = self._make((nc, 0))
+                    break
+                except Exception as ex:  # does not fit the shared memory of one CTA: next smaller capacity
+                    err = ex
+            if self._big is None:
+                raise err if err is not None else RuntimeError("no larger capacity than the first pass's")
         return self._big
 
     def close(self):
@@ -80,7 +93,13 @@ class EscalatingSim:
         aux = self.small.last_aux(n)
         over = np.nonzero(aux["overflow"])[0]
         self.last_overflow = dict(first_pass=int(len(over)), after_escalation=0)
+        big = None
         if len(over) and self.small.info.ncon_max < MAX_CAPS[0]:
+            try:
+                big = self.big
+            except Exception:
+                big = None
+        if big is not None:
             again = call(self.big, over)
             again = again if isinstance(again, tuple) else (again,)
             for o, a in zip(out, again):
@@ -92,7 +111,8 @@ class EscalatingSim:
             over = over[aux2["overflow"]]
             self.last_overflow["after_escalation"] = int(len(over))
         if len(over):
-            warnings.warn(f"{len(over)} of {n} environments needed more than {MAX_CAPS[0]} contacts: their labels were computed on a "
+            cap = (self._big or self.small).info.ncon_max
+            warnings.warn(f"{len(over)} of {n} environments needed more than {cap} contacts: their labels were computed on a "
                           "truncated contact set", RuntimeWarning, stacklevel=3)
         return (out[0] if len(out) == 1 else tuple(out)), aux
 

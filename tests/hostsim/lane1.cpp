@@ -31,7 +31,7 @@ extern "C" int l1_model_create(const MgsModelDesc *desc, L1Model **out) {
   M->dm = M->blob.dm;
   rebase_model(M->dm, M->blob.bytes.data());
   layout_compute(&M->L, desc->nq, desc->nv, desc->nu, desc->nbody, desc->njnt, desc->nmocap, desc->ntendon, desc->ncgeom,
-                 M->blob.ncon_max, M->blob.nefc_max, desc->npair);
+                 M->blob.ncon_max, M->blob.nefc_max, desc->npair, M->blob.dm.nM);
   M->state_stride = desc->nq + 2 * desc->nv + desc->nu + 7 * desc->nmocap;
   M->diag_stride = mgs_diag_stride(desc->nv, desc->nbody, M->blob.ncon_max, M->blob.nefc_max);
   M->scratch.assign(M->L.total, 0);

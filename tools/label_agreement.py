@@ -81,7 +81,7 @@ def measure_one(gripper, kind, seed, n, f64):
     free = G.collision_mask(pose7, joints, info["joint_qposadr"], info["base_qposadr"])
     sel = lambda idx: (pose7, joints) if idx is None else (pose7[idx], joints[idx])
     (lab, steps), over0, over1 = run_escalated(
-        G, lambda: BatchSim(m, f64=f64, ncon_max=128), lambda sim, idx: sim.stability(*sel(idx), info["joint_qposadr"], info["base_qposadr"],
+        G, lambda: BatchSim(m, f64=f64, ncon_max=256), lambda sim, idx: sim.stability(*sel(idx), info["joint_qposadr"], info["base_qposadr"],
                                                                                   info["close_ctrl"], MgsRolloutCfg(*SCHED(gripper))))
     lab = lab.astype(bool)
     G.close()
