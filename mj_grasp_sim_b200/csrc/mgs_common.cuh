@@ -130,6 +130,7 @@ struct DevModel {
   // is a dense t x t row-major tile, tiles back to back (nM = sum t^2 words instead of nv^2).  Entry (i, j) of one tree lives at
   // dof_rowoff[i] + j; rows of one tree are dof_treenum apart.
   const int *dof_rowoff;             // [nv]
+  const int *dof_blk;                // [nv]: dof_rowoff | dof_treeadr << 16 | dof_treenum << 24 (one load instead of three)
   const int *blk_ij;                 // [nM]: (i << 8) | j of every stored entry
   const int *tri_madr;               // [nv (nv + 1) / 2], parallel to tri_ab: address of M(a, b), -1 when a and b are in different trees
   const unsigned int *body_dofmask;  // [nbody][dofmask_words]: bit d set = dof d is on the path from the body to its root

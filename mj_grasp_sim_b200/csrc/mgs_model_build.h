@@ -105,6 +105,9 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
     }
     m.nM = nM;
     m.dof_rowoff = put<int>(b, rowoff.data(), nv);
+    std::vector<int> blkw(nv > 0 ? nv : 1, 0);
+    for (int i = 0; i < nv; i++) blkw[i] = (int)((unsigned)rowoff[i] | ((unsigned)tadr[i] << 16) | ((unsigned)tnum[i] << 24));
+    m.dof_blk = put<int>(b, blkw.data(), nv);
     m.blk_ij = put<int>(b, ij.data(), ij.size());
     std::vector<int> tm;
     for (int a = 0; a < nv; a++)

@@ -227,6 +227,7 @@ MGS_DEVN void write_diag_w(const Env &e, real *o) {
 // run one candidate / environment on this warp
 MGS_DEVN void run_env_w(Env &e, int env) {
   int steps = 0;
+  MGS_CLK_RESET();
   if (PRM.mode == MGS_MODE_STEP) {
     load_record_w(e, IO.state_in + (size_t)env * IO.state_stride);
     if (PRM.nstep > 0) step_w(e, PRM.nstep, &steps);
@@ -250,6 +251,7 @@ MGS_DEVN void run_env_w(Env &e, int env) {
       if (EH.overflow) atomicAdd(IO.work_counter + 1, 1u);
 #endif
     }
+    MGS_CLK_PRINT(env, steps);
     WSYNC();
     return;
   }
@@ -295,5 +297,6 @@ MGS_DEVN void run_env_w(Env &e, int env) {
     #pragma unroll 1
     PFOR(i, 7 * MD.nmocap) out[MD.nq + 2 * MD.nv + MD.nu + i] = EF(mocap)[i];
   }
+  MGS_CLK_PRINT(env, steps);
   WSYNC();
 }

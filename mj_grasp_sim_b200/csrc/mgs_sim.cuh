@@ -261,6 +261,21 @@ MGS_DEV void env_bind(Env &e, real *base) {
   WSYNC();
 }
 #define IARR(p) ((int *)(p))
+// -DMGS_STAGE_CLOCKS (profiling builds only): cycles per stage of the step, accumulated by thread 0 of each CTA and printed for
+// environment 0 at the end of its rollout (tools/README.md).  MGS_CLK(k) closes the interval that belongs to stage k.
+#if defined(MGS_STAGE_CLOCKS) && !defined(MGS_HOST)
+#include <stdio.h>
+static __shared__ long long mgs_clk_acc[16];
+static __shared__ long long mgs_clk_last;
+#define MGS_CLK(k) do { if (threadIdx.x == 0) { const long long t_ = clock64(); mgs_clk_acc[k] += t_ - mgs_clk_last; mgs_clk_last = t_; } } while (0)
+#define MGS_CLK_RESET() do { if (threadIdx.x == 0) { for (int q_ = 0; q_ < 16; q_++) mgs_clk_acc[q_] = 0; mgs_clk_last = clock64(); } } while (0)
+#define MGS_CLK_PRINT(env, steps) do { if (threadIdx.x == 0 && (env) == 0) { printf("stage cycles per step (env 0, %d steps):", (steps)); \
+  for (int q_ = 0; q_ < 12; q_++) printf(" [%d] %lld", q_, mgs_clk_acc[q_] / ((steps) > 0 ? (steps) : 1)); printf("\n"); } } while (0)
+#else
+#define MGS_CLK(k) ((void)0)
+#define MGS_CLK_RESET() ((void)0)
+#define MGS_CLK_PRINT(env, steps) ((void)0)
+#endif
 #ifdef MGS_QPOS_COMP
 #define QPOS_LO_CLEAR(i) (EF(qpos_lo)[i] = 0)
 #else
@@ -274,8 +289,13 @@ MGS_DEV void env_bind(Env &e, real *base) {
 // `blocked` == 0: dense n x n row-major (the Newton Hessian).  Both cases address through (ro, s): entry (i, k) of lane i's own row
 // is A[ro + k], entry (k, j) of another row of the same tile / matrix is A[ro + (k - i) * s + j].
 // In-place lower Cholesky (only the lower triangle is read).
+// (row offset, first dof, number of dofs) of dof i's tree tile: one packed word
+MGS_DEV void blk_row(int i, int &ro, int &lo, int &tn) {
+  const unsigned w = (unsigned)LDG(MD.dof_blk + i);
+  ro = (int)(w & 0xffffu); lo = (int)((w >> 16) & 255u); tn = (int)(w >> 24);
+}
 MGS_DEV void row_addr(int i, int n, int blocked, int &ro, int &s, int &tadr, int &tnum) {
-  if (blocked) { ro = LDG(MD.dof_rowoff + i); tadr = LDG(MD.dof_treeadr + i); tnum = LDG(MD.dof_treenum + i); s = tnum; }
+  if (blocked) { blk_row(i, ro, tadr, tnum); s = tnum; }
   else { ro = i * n; s = n; tadr = 0; tnum = n; }
 }
 #ifdef MGS_HOST
@@ -454,8 +474,9 @@ MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
 MGS_DEVN void chol_inverse_w(const real *L, real *Ainv, int n) {
   #pragma unroll 1
   PFOR(c, n) {
-    const int lo = LDG(MD.dof_treeadr + c), t = LDG(MD.dof_treenum + c);
-    const int bo = LDG(MD.dof_rowoff + lo) + lo;  // first word of the tile
+    int roc, lo, t;
+    blk_row(c, roc, lo, t);
+    const int bo = roc - (c - lo) * t + lo;  // first word of the tile
     const real *Lt = L + bo;
     real *At = Ainv + bo;
     const int cl = c - lo;
@@ -480,8 +501,10 @@ MGS_DEVN void chol_inverse_w(const real *L, real *Ainv, int n) {
 MGS_DEVN void matvec_w(real *y, const real *A, const real *x, int n) {
   #pragma unroll 1
   PFOR(i, n) {
-    const int lo = LDG(MD.dof_treeadr + i), hi = lo + LDG(MD.dof_treenum + i);
-    const real *row = A + LDG(MD.dof_rowoff + i);
+    int ro, lo, tn;
+    blk_row(i, ro, lo, tn);
+    const int hi = lo + tn;
+    const real *row = A + ro;
     real t = 0;
     MGS_UNROLL_INNER
     for (int j = lo; j < hi; j++) t += row[j] * x[j];

@@ -481,8 +481,10 @@ MGS_DEVN void eval_point_w(Env &e, const real *qacc) {
   }
   #pragma unroll 1
   PFOR(i, nv) {
-    const int lo = LDG(MD.dof_treeadr + i), hi = lo + LDG(MD.dof_treenum + i);
-    const real *Mrow = EF(M) + LDG(MD.dof_rowoff + i);
+    int ro, lo, tn;
+    blk_row(i, ro, lo, tn);
+    const int hi = lo + tn;
+    const real *Mrow = EF(M) + ro;
     acc_jar_t t = 0;
     MGS_UNROLL_INNER
     for (int j = lo; j < hi; j++) t += (acc_jar_t)Mrow[j] * (acc_jar_t)qacc[j];
@@ -564,6 +566,7 @@ MGS_DEVN void newton_hessian_w(Env &e) {
     }
   }
   WSYNC();
+  MGS_CLK(4);
   chol_factor_w(EF(H), nv, 0);
 }
 
@@ -616,8 +619,11 @@ MGS_DEVN void solve_newton_w(Env &e) {
 #else
     if (scale * sqrt(gn) < tol_eff) break;
 #endif
+    MGS_CLK(3);
     newton_hessian_w(e);
+    MGS_CLK(5);
     chol_solve_w(EF(H), EF(search), nv, 0);
+    MGS_CLK(6);
     #pragma unroll 1
     PFOR(d, nv) EF(search)[d] = -EF(search)[d];
     WSYNC();
@@ -852,9 +858,11 @@ MGS_DEV real noslip_contact_w(Env &e, int c, int i, int p, const real *AC, real 
   WSYNC();
   #pragma unroll 1
   PFOR(d, nv) {
-    const int lo = LDG(MD.dof_treeadr + d), hi = lo + LDG(MD.dof_treenum + d);
+    int ro, lo, tn;
+    blk_row(d, ro, lo, tn);
+    const int hi = lo + tn;
     real t = 0;
-    const real *Mrow = EF(Minv) + LDG(MD.dof_rowoff + d);
+    const real *Mrow = EF(Minv) + ro;
     MGS_UNROLL_INNER
     for (int k = lo; k < hi; k++) t += Mrow[k] * T[k];
     EF(wvec)[d] += t;
@@ -894,8 +902,10 @@ MGS_DEVN void solve_noslip_w(Env &e) {
   WSYNC();
   #pragma unroll 1
   PFOR(d, nv) {
-    const int lo = LDG(MD.dof_treeadr + d), hi = lo + LDG(MD.dof_treenum + d);
-    const real *Mrow = EF(Minv) + LDG(MD.dof_rowoff + d);
+    int ro, lo, tn;
+    blk_row(d, ro, lo, tn);
+    const int hi = lo + tn;
+    const real *Mrow = EF(Minv) + ro;
     real t = 0;
     MGS_UNROLL_INNER
     for (int k = lo; k < hi; k++) t += Mrow[k] * T[k];
@@ -921,8 +931,10 @@ MGS_DEVN void solve_noslip_w(Env &e) {
     PFOR(r, 3 * nv) {
       const int j = (r >= 2 * nv) ? 2 : (r >= nv ? 1 : 0), d = r - j * nv;
       // rows beyond the contact's friction dims are never read (dim 3: j < 2)
-      const int lo = LDG(MD.dof_treeadr + d), hi = lo + LDG(MD.dof_treenum + d);
-      const real *Mrow = EF(Minv) + LDG(MD.dof_rowoff + d), *Jrow = EF(J) + (i + 1 + j) * nv;
+      int ro, lo, tn;
+      blk_row(d, ro, lo, tn);
+      const int hi = lo + tn;
+      const real *Mrow = EF(Minv) + ro, *Jrow = EF(J) + (i + 1 + j) * nv;
       real t = 0;
       MGS_UNROLL_INNER
       for (int k = lo; k < hi; k++) t += Mrow[k] * Jrow[k];
@@ -954,9 +966,11 @@ MGS_DEVN void solve_noslip_w(Env &e) {
       for (int a = 0; a < nv; a++) {
         const real ja = Jj[a];
         if (ja == 0) continue;
-        const int lo = LDG(MD.dof_treeadr + a), hi = lo + LDG(MD.dof_treenum + a);
+        int ro, lo, tn;
+        blk_row(a, ro, lo, tn);
+        const int hi = lo + tn;
         real t = 0;
-        const real *Mrow = EF(Minv) + LDG(MD.dof_rowoff + a);
+        const real *Mrow = EF(Minv) + ro;
         MGS_UNROLL_INNER
         for (int b2 = lo; b2 < hi; b2++) t += Mrow[b2] * Jk[b2];
         acc += ja * t;
@@ -982,8 +996,10 @@ MGS_DEVN void solve_noslip_w(Env &e) {
     #pragma unroll 1
     for (int i = EH.ne; i < EH.ne + EH.nf; i++) {
       const int d = EFC_ID(i);
-      const real *Mrow = EF(Minv) + LDG(MD.dof_rowoff + d);  // row d of M^-1 (= column d: symmetric), nonzero inside d's tree
-      const int lo = LDG(MD.dof_treeadr + d), hi = lo + LDG(MD.dof_treenum + d);
+      int ro, lo, tn;
+      blk_row(d, ro, lo, tn);
+      const int hi = lo + tn;
+      const real *Mrow = EF(Minv) + ro;  // row d of M^-1 (= column d: symmetric), nonzero inside d's tree
       const real res = EF(qacc_smooth)[d] + EF(wvec)[d] - EF(efc_aref)[i], Aii = Mrow[d];
       const real old = EF(efc_force)[i], fl = EF(efc_aux)[i];
       real fn = old - res / fmax(MGS_MINVAL, Aii);
@@ -1022,14 +1038,18 @@ MGS_DEVN void solve_noslip_w(Env &e) {
 MGS_DEVN void forward_w(Env &e) {
   const int nv = MD.nv;
   MGS_STAGE_BARRIER(0);
+  MGS_CLK(11);
   kinematics_w(e);
   inertia_w(e);
   transmission_w(e);
+  MGS_CLK(0);
   MGS_STAGE_BARRIER(1);
   collision_w(e);
+  MGS_CLK(1);
   MGS_STAGE_BARRIER(2);
   smooth_forces_w(e);
   make_constraint_w(e);
+  MGS_CLK(2);
   MGS_STAGE_BARRIER(3);
   if (EH.nefc == 0) {
     #pragma unroll 1
@@ -1041,6 +1061,7 @@ MGS_DEVN void forward_w(Env &e) {
     PFOR(d, nv) EF(qacc_ws)[d] = EF(qacc)[d];
     WSYNC();
   }
+  MGS_CLK(3);
   MGS_STAGE_BARRIER(4);
   if (EH.nefc != 0) {
     if (MD.noslip_iterations > 0) solve_noslip_w(e);
@@ -1055,6 +1076,7 @@ MGS_DEVN void forward_w(Env &e) {
       WSYNC();
     }
   }
+  MGS_CLK(7);
 }
 
 MGS_DEVN int bad_state_w(const Env &e, int check_acc) {
@@ -1170,6 +1192,7 @@ MGS_DEVN int step_w(Env &e, int nstep, int *steps_done) {
     MGS_STAGE_BARRIER(5);
     if (bad_state_w(e, 1)) { EH.bad = 1; return 1; }
     integrate_w(e);
+    MGS_CLK(8);
     (*steps_done)++;
   }
   return 0;

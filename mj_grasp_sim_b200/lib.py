@@ -18,7 +18,7 @@ SO_PATH = os.path.join(_PKG, "libmgs_b200.so")
 SO_PATH_F64 = os.path.join(_PKG, "libmgs_b200_f64.so")
 CSRC = os.path.join(_PKG, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-t", "4"]
 
 
 class MgsRolloutCfg(C.Structure):

@@ -62,7 +62,13 @@ def run_escalated(G_small, make_big, call):
     over = np.nonzero(G_small.last_aux(n)["overflow"])[0]
     left = 0
     if len(over):
-        big = make_big()
+        big = None
+        for nc in (256, 128, 96, 64):  # the largest capacity that fits one CTA's shared memory (mgs.env EscalatingSim does the same)
+            try:
+                big = make_big(nc)
+                break
+            except Exception:
+                continue
         again = call(big, over)
         for o, a in zip(out, again):
             o[over] = a
@@ -81,7 +87,7 @@ def measure_one(gripper, kind, seed, n, f64):
     free = G.collision_mask(pose7, joints, info["joint_qposadr"], info["base_qposadr"])
     sel = lambda idx: (pose7, joints) if idx is None else (pose7[idx], joints[idx])
     (lab, steps), over0, over1 = run_escalated(
-        G, lambda: BatchSim(m, f64=f64, ncon_max=256), lambda sim, idx: sim.stability(*sel(idx), info["joint_qposadr"], info["base_qposadr"],
+        G, lambda nc: BatchSim(m, f64=f64, ncon_max=nc), lambda sim, idx: sim.stability(*sel(idx), info["joint_qposadr"], info["base_qposadr"],
                                                                                   info["close_ctrl"], MgsRolloutCfg(*SCHED(gripper))))
     lab = lab.astype(bool)
     G.close()

@@ -67,7 +67,7 @@ def clutter(n=296, n_or=8, caps=(48, 240)):
     from oracle import oracle as orc
     m, info = scenes.build_clutter_scene("shadow", list(range(10)))
     rec = None
-    for variant in ("wide", "w12"):
+    for variant in (("wide", "w12") if caps == (48, 240) else ("wide",)):
         G = sim(m, variant, ground_name="geom:table", ncon_max=caps[0], nefc_max=caps[1])
         print(variant, "model nv", m.nv, "pairs", len(m.pair_geom1), "| caps", G.info.ncon_max, G.info.nefc_max, "smem/env", G.info.smem_bytes_per_env,
               "lanes/env", G.info.lanes_per_env, "envs/SM", G.info.warps_per_block * G.info.blocks_per_sm, flush=True)
@@ -107,4 +107,5 @@ if __name__ == "__main__":
     elif what == "race":
         race()
     else:
-        clutter(*(int(x) for x in sys.argv[2:4]))
+        a = [int(x) for x in sys.argv[2:]]
+        clutter(*a[:2], caps=tuple(a[2:4]) if len(a) >= 4 else (48, 240))
