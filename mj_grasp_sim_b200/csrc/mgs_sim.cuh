@@ -300,7 +300,7 @@ MGS_DEV void row_addr(int i, int n, int blocked, int &ro, int &s, int &tadr, int
 }
 #ifdef MGS_HOST
 // 1-lane host build: the same factorisation written serially (per block)
-MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
+MGS_DEVN void chol_factor_w(real *A, int n, int blocked, real *colbuf = (real *)0) {
   for (int j = 0; j < n; j++) {
     int ro, s, tadr, tnum;
     row_addr(j, n, blocked, ro, s, tadr, tnum);
@@ -333,10 +333,120 @@ MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
     for (int i = tadr; i < k; i++) x[i] -= L[ro + i] * xk;
   }
 }
+#elif defined(MGS_WIDE)
+// ENVIRONMENT PER CTA.  Dense factor (the Newton Hessian, n up to 255): right-looking, the trailing update of every column spread
+// over all threads as a 16 x 16 grid over (row, column), ONE barrier per column: the column is used unscaled
+// (A[i][k] -= A[i][j] A[k][j] / A[j][j]) and scaled to L afterwards, while the next column's update runs (nobody reads it again).
+// ncu / stage clocks of the round-2 capture (Shadow + 10 objects, nv = 94): the row-per-lane version with three barriers per column
+// was 27 % of the step (3.4 k cycles per column).  Block-diagonal factor: rows per lane like the warp variants, same single barrier.
+MGS_DEVN void chol_factor_w(real *A, int n, int blocked, real *colbuf = (real *)0) {
+  WSYNC();
+  (void)colbuf;
+  if (!blocked) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    real dprev = 1;
+    #pragma unroll 1
+    for (int j = 0; j < n; j++) {
+      real d2 = A[j * n + j];
+      d2 = d2 > MGS_MINVAL ? d2 : MGS_MINVAL;
+      const real inv = R_(1.0) / d2;
+      // this thread's column entries A[k][j] (k = j + 1 + tx + 16 m) are the same for all of its rows: loaded once, four at a
+      // time, so that the read-modify-writes of a row are independent (a serial LDS-FFMA-STS chain per entry was 1.5 k cycles per column)
+      #pragma unroll 1
+      for (int k0 = j + 1 + tx; k0 < n; k0 += 64) {
+        const int k1 = k0 + 16, k2 = k0 + 32, k3 = k0 + 48;
+        const real c0 = A[k0 * n + j], c1 = k1 < n ? A[k1 * n + j] : R_(0.0), c2 = k2 < n ? A[k2 * n + j] : R_(0.0), c3 = k3 < n ? A[k3 * n + j] : R_(0.0);
+        int i = j + 1 + ty;
+        while (i < k0) i += 16;  // rows above the diagonal entry of the first column have nothing to update
+        #pragma unroll 1
+        for (; i < n; i += 16) {
+          real *row = A + i * n;
+          const real lij = row[j] * inv;
+          const real r0 = row[k0], r1 = k1 <= i ? row[k1] : R_(0.0), r2 = k2 <= i ? row[k2] : R_(0.0), r3 = k3 <= i ? row[k3] : R_(0.0);
+          row[k0] = r0 - lij * c0;
+          if (k1 <= i) row[k1] = r1 - lij * c1;
+          if (k2 <= i) row[k2] = r2 - lij * c2;
+          if (k3 <= i) row[k3] = r3 - lij * c3;
+        }
+      }
+      if (j > 0) {  // deferred scaling of column j - 1
+        const real sd = sqrt(dprev), rs = R_(1.0) / sd;
+        #pragma unroll 1
+        for (int i = j - 1 + (int)threadIdx.x; i < n; i += LANES) A[i * n + j - 1] = (i == j - 1) ? sd : A[i * n + j - 1] * rs;
+      }
+      dprev = d2;
+      WSYNC();
+    }
+    if (threadIdx.x == 0 && n > 0) A[(n - 1) * n + n - 1] = sqrt(dprev);
+    WSYNC();
+    return;
+  }
+  // block diagonal (n <= LANES: one row per thread): every tile advances one column per step, one barrier per step
+  const int nsteps = MD.max_tree_dofs, i = threadIdx.x;
+  int ro = 0, tadr = 0, tnum = 0;
+  if (i < n) blk_row(i, ro, tadr, tnum);
+  const int s = tnum;
+  #pragma unroll 1
+  for (int t = 0; t < nsteps; t++) {
+    const int j = tadr + t, act = (i < n) && (t < tnum) && (i >= j);
+    real d2 = 1, aij = 0;
+    if (act) {
+      d2 = A[ro + (j - i) * s + j];  // the pivot, unscaled (final: the previous step's trailing update is behind a barrier)
+      d2 = d2 > MGS_MINVAL ? d2 : MGS_MINVAL;
+      if (i > j) {
+        aij = A[ro + j];
+        const real lij = aij / d2;
+        const real *col = A + ro + (j + 1 - i) * s + j;
+        real *row = A + ro + j + 1;
+        const int cnt = i - j;
+        #pragma unroll 2
+        for (int k = 0; k < cnt; k++) row[k] -= lij * col[k * s];
+      }
+    }
+    WSYNC();  // every read of column j is done: scale it (the next step only reads column j + 1)
+    if (act) A[ro + j] = (i == j) ? sqrt(d2) : aij / sqrt(d2);
+  }
+  WSYNC();
+}
+// x <- (L L')^-1 x, one row per thread (n <= LANES), ONE barrier per pivot: the thread of row k + 1 finishes its own entry (last update,
+// then the division by its diagonal) inside step k, so step k + 1 can start right after the barrier.
+MGS_DEVN void chol_solve_w(const real *L, real *x, int n, int blocked) {
+  const int i = threadIdx.x;
+  int ro = 0, s = n, lo = 0, tn = n;
+  if (i < n) row_addr(i, n, blocked, ro, s, lo, tn);
+  const int hi = lo + tn;
+  WSYNC();
+  real xi = i < n ? x[i] : R_(0.0);
+  if (i < n && i == lo) { xi = xi / L[ro + i]; x[i] = xi; }  // first row of every tile: final
+  WSYNC();
+  const int nsteps = blocked ? MD.max_tree_dofs : n;
+  #pragma unroll 1
+  for (int t = 0; t + 1 < nsteps; t++) {  // forward: pivot k = lo + t of every tile
+    const int k = lo + t;
+    if (i < n && i > k && k < hi) {
+      xi -= L[ro + k] * x[k];
+      if (i == k + 1) { xi = xi / L[ro + i]; x[i] = xi; }
+    }
+    WSYNC();
+  }
+  // backward: the last row of every tile is final after its own division
+  if (i < n && i == hi - 1) { xi = xi / L[ro + i]; x[i] = xi; }
+  WSYNC();
+  #pragma unroll 1
+  for (int t = 0; t + 1 < nsteps; t++) {  // pivot k = hi - 1 - t
+    const int k = hi - 1 - t;
+    if (i < n && i < k && k >= lo) {
+      xi -= L[ro + (k - i) * s + i] * x[k];
+      if (i == k - 1) { xi = xi / L[ro + i]; x[i] = xi; }
+    }
+    WSYNC();
+  }
+  WSYNC();
+}
 #else
 // GPU: lanes own rows (row i on lane i % LANES); every diagonal block advances one pivot column per step.
 // Warp variants, n <= 32 (every in-scope single-object model except Shadow): one row per lane, pivots kept in registers.
-MGS_DEVN void chol_factor_w(real *A, int n, int blocked) {
+MGS_DEVN void chol_factor_w(real *A, int n, int blocked, real *colbuf = (real *)0) {
   const int nsteps = blocked ? MD.max_tree_dofs : n;
   if (LANES == 32 && n <= LANES) {  // (warp variants only: pivots by shuffle)
     const int i = MGS_LANE;

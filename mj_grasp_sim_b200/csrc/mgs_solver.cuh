@@ -567,7 +567,7 @@ MGS_DEVN void newton_hessian_w(Env &e) {
   }
   WSYNC();
   MGS_CLK(4);
-  chol_factor_w(EF(H), nv, 0);
+  chol_factor_w(EF(H), nv, 0, EF(nsB));  // (nsB: 3 nv words of noslip scratch, free during the Newton solve)
 }
 
 MGS_DEVN void solve_newton_w(Env &e) {
