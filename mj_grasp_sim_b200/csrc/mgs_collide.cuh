@@ -345,8 +345,51 @@ MGS_DEVN int best_face_w(int hull, real nx, real ny, real nz, real *align) {
   *align = bd;
   return best;
 }
-// best faces for every lane with `want` set (its geom `g`, world direction `n`): lanes are served one after the other
-MGS_DEV void best_face_lanes(int want, const GeomRef &g, const real *n, int *face, real *align) {
+// best faces for every lane with `want` set (its geom `g`, world direction `n`)
+#ifdef MGS_WIDE
+// env-per-CTA variant: the requests are compacted into a list and every WARP serves requests q = warp, warp + 8, ... with a
+// warp-level scan + arg-max: five CTA barriers per call.  (Serving the requesters one after the other with block-level broadcasts and
+// arg-max was ~12 barriers per requester, four calls per step, ~50 requesters each on the config-5 scene: most of its collision time.)
+MGS_DEV void best_face_lanes(const Env &e, int want, const GeomRef &g, const real *n, int *face, real *align) {
+  int nreq;
+  const int rank = wrank(want, &nreq);
+  if (nreq == 0) return;
+  real *rq = EF(req_off);
+  if (want) {
+    real nl[3];
+    mulmatTvec3(nl, g.R, n);
+    *IARR(rq + 6 * rank) = g.hull; rq[6 * rank + 1] = nl[0]; rq[6 * rank + 2] = nl[1]; rq[6 * rank + 3] = nl[2];
+  }
+  WSYNC();
+  const int l32 = threadIdx.x & 31;
+  #pragma unroll 1
+  for (int q = threadIdx.x >> 5; q < nreq; q += MGS_NWARP) {
+    const int hull = *IARR(rq + 6 * q);
+    const real nx = rq[6 * q + 1], ny = rq[6 * q + 2], nz = rq[6 * q + 3];
+    const int fa = LDG(MD.hull_faceadr + hull), fn = LDG(MD.hull_facenum + hull);
+    const real *FN = MD.hull_facenormal + 3 * fa;
+    real bd = R_(-1e30);
+    int best = 0x7fffffff;
+    #pragma unroll 2
+    for (int f = l32; f < fn; f += 32) {
+      const real t = LDG(FN + 3 * f) * nx + LDG(FN + 3 * f + 1) * ny + LDG(FN + 3 * f + 2) * nz;
+      if (t > bd) { bd = t; best = f; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const real v2 = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, best, o);
+      if (v2 > bd || (v2 == bd && i2 < best)) { bd = v2; best = i2; }
+    }
+    if (l32 == 0) { *IARR(rq + 6 * q + 4) = best; rq[6 * q + 5] = bd; }
+  }
+  WSYNC();
+  if (want) { *face = *IARR(rq + 6 * rank + 4); *align = rq[6 * rank + 5]; }
+  WSYNC();
+}
+#else
+MGS_DEV void best_face_lanes(const Env &e, int want, const GeomRef &g, const real *n, int *face, real *align) {
+  (void)e;
   real nl[3] = {0, 0, 0};
   if (want) mulmatTvec3(nl, g.R, n);
   int pending = want;
@@ -359,6 +402,7 @@ MGS_DEV void best_face_lanes(int want, const GeomRef &g, const real *n, int *fac
     if (MGS_LANE == src) { *face = f; *align = al; pending = 0; }
   }
 }
+#endif
 MGS_DEVN int face_polygon(const GeomRef &g, int f, real (*poly)[3], real *nw) {
   int gf = LDG(MD.hull_faceadr + g.hull) + f;
   int n = LDG(MD.hull_facevertnum + gf), fva = LDG(MD.hull_facevertadr + gf), va = LDG(MD.hull_vertadr + g.hull);
@@ -402,8 +446,8 @@ MGS_DEVN void collide_pair(Env &e, int pair, PairContacts &out) {
   const int poly = hit && (g1.type == GEOM_BOX || g1.type == GEOM_MESH) && (g2.type == GEOM_BOX || g2.type == GEOM_MESH);
   real a1 = 0, a2 = 0, nn[3] = {-n[0], -n[1], -n[2]};
   int f1 = 0, f2 = 0;
-  best_face_lanes(poly, g1, n, &f1, &a1);
-  best_face_lanes(poly, g2, nn, &f2, &a2);
+  best_face_lanes(e, poly, g1, n, &f1, &a1);
+  best_face_lanes(e, poly, g2, nn, &f2, &a2);
   const int clip = poly && fmax(a1, a2) >= MGS_FACE_ALIGN_MIN;
   const int ref_is_1 = a1 >= a2;
   const GeomRef &rg = ref_is_1 ? g1 : g2;
@@ -424,7 +468,7 @@ MGS_DEVN void collide_pair(Env &e, int pair, PairContacts &out) {
     int nr = 0, incf = 0;
     if (mine) nr = face_polygon(rg, ref_is_1 ? f1 : f2, ref, nref);
     mn[0] = -nref[0]; mn[1] = -nref[1]; mn[2] = -nref[2];
-    best_face_lanes(mine, ig, mn, &incf, &al);
+    best_face_lanes(e, mine, ig, mn, &incf, &al);
     if (mine) {
       real ninc[3];
       int na = face_polygon(ig, incf, A, ninc);

@@ -105,7 +105,7 @@ enum { MGS_MODE_STEP = 0, MGS_MODE_COLLISION = 1, MGS_MODE_STABILITY = 2, MGS_MO
 // Model constants on the device (all pointers into one read-only blob).
 struct DevModel {
   int nq, nv, nu, nbody, njnt, neq, nmocap, ntendon, nwrap, ncgeom, npair, nhull;
-  int maxdepth, max_tree_dofs, nM, ne_rows, nf_rows, ngravcomp, dofmask_words, cone_elliptic, iterations, ls_iterations, noslip_iterations, mpr_iterations, ground_geomid;
+  int maxdepth, max_tree_dofs, nM, ntree, ne_rows, nf_rows, ngravcomp, dofmask_words, cone_elliptic, iterations, ls_iterations, noslip_iterations, mpr_iterations, ground_geomid;
   real timestep, impratio, tolerance, ls_tolerance, noslip_tolerance, mpr_tolerance, meaninertia, gravity[3];
   const int *body_parentid, *body_rootid, *body_mocapid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_depth;
   const real *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0, *body_subtreemass, *body_gravcomp;
@@ -132,6 +132,7 @@ struct DevModel {
   const int *dof_rowoff;             // [nv]
   const int *dof_blk;                // [nv]: dof_rowoff | dof_treeadr << 16 | dof_treenum << 24 (one load instead of three)
   const int *blk_ij;                 // [nM]: (i << 8) | j of every stored entry
+  const int *dof_treeid, *body_treeid;  // kinematic tree index of a dof / of the dofs that move a body (-1: static body)
   const int *tri_madr;               // [nv (nv + 1) / 2], parallel to tri_ab: address of M(a, b), -1 when a and b are in different trees
   const unsigned int *body_dofmask;  // [nbody][dofmask_words]: bit d set = dof d is on the path from the body to its root
   const real *eq_data, *eq_solref, *eq_solimp;
@@ -149,14 +150,15 @@ struct DevModel {
   X(ten_length, ntendon) X(ten_J, ntendon * nv) X(act_moment, nu * nv) X(act_force, nu) X(act_length, nu)          \
   X(qfrc_smooth, nv) X(qacc_smooth, nv) X(qacc, nv) X(qfrc_constraint, nv) X(Ma, nv) X(grad, nv) X(search, nv)     \
   X(Mv, nv) X(wvec, nv) X(con_pos, 3 * ncon_max) X(con_normal, 3 * ncon_max) X(con_dist, ncon_max)                 \
-  X(con_mu, ncon_max) X(con_pair, ncon_max) X(con_efc, ncon_max) X(nsB, 3 * nv) X(nsS, lanes) X(mpr_cache, 4 * ncache)
+  X(con_mu, ncon_max) X(con_pair, ncon_max) X(con_efc, ncon_max) X(nsB, 3 * nv) X(nsS, lanes + (lanes > 32 ? 8 : 0)) X(mpr_cache, 4 * ncache)
 #define MGS_LAYOUT_TRANSIENT(X)                                                                                    \
   X(xipos, 3 * nbody) X(ximat, 9 * nbody) X(xanchor, 3 * njnt) X(xaxis, 3 * njnt) X(gxpos, 3 * ncgeom)             \
   X(gxmat, 9 * ncgeom) X(cinert, 10 * nbody) X(crb, 10 * nbody) X(cdof_dot, 6 * nv) X(cvel, 6 * nbody)             \
   X(cacc, 6 * nbody) X(cfrc, 6 * nbody)
 #define MGS_LAYOUT_SOLVER(X)                                                                                       \
   X(J, nefc_max * nv) X(efc_D, nefc_max) X(efc_R, nefc_max) X(efc_aref, nefc_max) X(efc_aux, nefc_max)             \
-  X(efc_force, nefc_max) X(efc_jar, nefc_max) X(efc_jv, nefc_max) X(efc_tsi, nefc_max)
+  X(efc_force, nefc_max) X(efc_jar, nefc_max) X(efc_jv, nefc_max) X(efc_tsi, nefc_max)                                       \
+  X(efc_key, (lanes > 32 ? nefc_max : 0)) X(efc_list, (lanes > 32 ? nefc_max : 0))
 #define MGS_LAYOUT_FIELDS(X) MGS_LAYOUT_PERSIST(X) MGS_LAYOUT_TRANSIENT(X) MGS_LAYOUT_SOLVER(X)
 
 struct Layout {
@@ -164,6 +166,7 @@ struct Layout {
   MGS_LAYOUT_FIELDS(X)
 #undef X
   int total, ncon_max, nefc_max, ncache;
+  int req_off;          // env-per-CTA variant: request / answer records of the face search (6 words per thread), behind the clipping slots
   int clip_off, nclip;  // face-clipping scratch: `nclip` slots of MGS_CLIP_STRIDE reals in the part of the SOLVER overlay that lies beyond the
                         // TRANSIENT arrays (free during collision: the constraint rows are built afterwards)
 };
@@ -193,6 +196,8 @@ static inline void layout_compute(Layout *L, int nq, int nv, int nu, int nbody, 
   L->nclip = (L->total - end_t) / MGS_CLIP_STRIDE;
   if (L->nclip < 1) { L->nclip = 1; L->total = end_t + MGS_CLIP_STRIDE; }
   if (L->nclip > 32) L->nclip = 32;
+  L->req_off = L->clip_off + L->nclip * MGS_CLIP_STRIDE;
+  if (lanes > 32 && L->total < L->req_off + 6 * lanes) L->total = L->req_off + 6 * lanes;
   L->total = (L->total + 3) & ~3;  // every environment's slice starts 16-byte aligned
   L->ncon_max = ncon_max;
   L->nefc_max = nefc_max;

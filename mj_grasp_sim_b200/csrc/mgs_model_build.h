@@ -104,6 +104,18 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
       i += t;
     }
     m.nM = nM;
+    // tree index of every dof and of every body (the tree of the nearest ancestor that has dofs; -1 for static bodies)
+    std::vector<int> dtree(nv > 0 ? nv : 1, 0), btree(nb, -1);
+    int ntree = 0;
+    for (int i = 0; i < nv;) { for (int k = 0; k < tnum[i]; k++) dtree[i + k] = ntree; ntree++; i += tnum[i]; }
+    for (int i = 1; i < nb; i++) {
+      int bb = i;
+      while (bb > 0 && d->body_dofnum[bb] == 0) bb = d->body_parentid[bb];
+      if (bb > 0) btree[i] = dtree[d->body_dofadr[bb]];
+    }
+    m.ntree = ntree;
+    m.dof_treeid = put<int>(b, dtree.data(), nv);
+    m.body_treeid = put<int>(b, btree.data(), nb);
     m.dof_rowoff = put<int>(b, rowoff.data(), nv);
     std::vector<int> blkw(nv > 0 ? nv : 1, 0);
     for (int i = 0; i < nv; i++) blkw[i] = (int)((unsigned)rowoff[i] | ((unsigned)tadr[i] << 16) | ((unsigned)tnum[i] << 24));

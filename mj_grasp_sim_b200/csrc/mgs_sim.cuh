@@ -23,13 +23,27 @@ MGS_DEV int wbcasti(int x, int src) { (void)src; return x; }
 MGS_DEV void wargmax(real &v, int &idx) { (void)v; (void)idx; }
 MGS_DEV int wrank(int p, int *total) { *total = p ? 1 : 0; return 0; }
 MGS_DEV int wfirst(int p) { return p ? 0 : -1; }
+MGS_DEV void wsum3(real &a, real &b, real &c) { (void)a; (void)b; (void)c; }
 #elif defined(MGS_WIDE)
 // block-level versions (environment per CTA).  Every collective is called by ALL threads of the CTA from converged code, like
 // the full-mask warp intrinsics of the warp variant; results are identical on every thread and do not depend on timing
 // (partial results are combined in warp order).  The trailing barrier of each lets the scratch be reused by the next call.
 #define MGS_NWARP (MGS_WIDE / 32)
-static __shared__ real mgs_cta_r[MGS_NWARP];
+static __shared__ real mgs_cta_r[3 * MGS_NWARP];
 static __shared__ int mgs_cta_i[MGS_NWARP];
+// three sums with the two barriers of one
+MGS_DEV void wsum3(real &a, real &b, real &c) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) { mgs_cta_r[threadIdx.x >> 5] = a; mgs_cta_r[MGS_NWARP + (threadIdx.x >> 5)] = b; mgs_cta_r[2 * MGS_NWARP + (threadIdx.x >> 5)] = c; }
+  __syncthreads();
+  a = mgs_cta_r[0]; b = mgs_cta_r[MGS_NWARP]; c = mgs_cta_r[2 * MGS_NWARP];
+#pragma unroll
+  for (int w = 1; w < MGS_NWARP; w++) { a += mgs_cta_r[w]; b += mgs_cta_r[MGS_NWARP + w]; c += mgs_cta_r[2 * MGS_NWARP + w]; }
+  __syncthreads();
+}
 MGS_DEV real wsum(real x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -139,6 +153,12 @@ MGS_DEV int wsumi(int x) {
 }
 MGS_DEV int wany(int p) { return __any_sync(0xffffffffu, p); }
 MGS_DEV int wfirst(int p) { return __ffs(__ballot_sync(0xffffffffu, p)) - 1; }
+MGS_DEV void wsum3(real &a, real &b, real &c) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+}
 MGS_DEV real wbcast(real x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 MGS_DEV int wbcasti(int x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 // number of lanes below this one with `p` set (and the warp total)

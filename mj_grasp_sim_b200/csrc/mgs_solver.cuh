@@ -524,6 +524,74 @@ MGS_DEVN void cone_hessian(const Env &e, int c, int i, int dim, real *h) {
     }
 }
 
+#ifdef MGS_WIDE
+// Rows of the constraint Jacobian touch at most two kinematic trees (a contact between two objects: 12 of the 94 columns of the
+// config-5 scene), so H = M + J' D J only receives row i in the tile (tree, tree') of its two trees.  Rows are bucketed by their
+// tree pair once per step (deterministic counting sort: key = lower tree * ntree + upper tree); an entry (a, b) of H then walks
+// only the rows of the bucket(s) that can contribute.  Dense, the product was 19 % of the config-5 step (stage clocks).
+#define MGS_SPARSE_H_MAXTREE 16
+MGS_DEV int row_key(const Env &e, int r) {
+  const int type = EFC_TYPE(r), id = EFC_ID(r);
+  int ta = -1, tb = -1;
+  if (type == CT_EQUALITY) {
+    if (LDG(MD.eq_type + id) == EQ_JOINT) {
+      const int j2 = LDG(MD.eq_obj2id + id);
+      ta = LDG(MD.dof_treeid + LDG(MD.jnt_dofadr + LDG(MD.eq_obj1id + id)));
+      if (j2 >= 0) tb = LDG(MD.dof_treeid + LDG(MD.jnt_dofadr + j2));
+    } else { ta = LDG(MD.body_treeid + LDG(MD.eq_obj1id + id)); tb = LDG(MD.body_treeid + LDG(MD.eq_obj2id + id)); }
+  } else if (type == CT_FRICTION_DOF) ta = LDG(MD.dof_treeid + id);
+  else if (type == CT_LIMIT) ta = LDG(MD.dof_treeid + LDG(MD.jnt_dofadr + id));
+  else {
+    const int p = IARR(EF(con_pair))[id];
+    ta = LDG(MD.body_treeid + LDG(MD.cgeom_bodyid + LDG(MD.pair_geom1 + p)));
+    tb = LDG(MD.body_treeid + LDG(MD.cgeom_bodyid + LDG(MD.pair_geom2 + p)));
+  }
+  if (ta < 0) { ta = tb; tb = -1; }
+  if (ta < 0) return 0;  // a row between two static bodies has no dofs: any bucket will do (its Jacobian row is zero)
+  if (tb < 0) tb = ta;
+  if (ta > tb) { const int t = ta; ta = tb; tb = t; }
+  return ta * MD.ntree + tb;
+}
+MGS_DEVN void bucket_rows_w(Env &e) {
+  const int nefc = EH.nefc, nkey = MD.ntree * MD.ntree;
+  int *key = IARR(EF(efc_key)), *list = IARR(EF(efc_list)), *start = IARR(EF(nsS));
+  #pragma unroll 1
+  PFOR(r, nefc) key[r] = row_key(e, r);
+  WSYNC();
+  // (nkey <= LANES: one key per thread) rows per key, then the exclusive scan
+  int cnt = 0;
+  if (MGS_LANE < nkey) {
+    #pragma unroll 4
+    for (int r = 0; r < nefc; r++) cnt += (key[r] == MGS_LANE);
+  }
+  int total;
+  const int off = wscan_excl(cnt, &total);
+  if (MGS_LANE < nkey) start[MGS_LANE] = off;
+  if (MGS_LANE == 0) start[nkey] = total;
+  WSYNC();
+  // position of row r = start of its bucket + number of earlier rows with the same key (row order is kept inside a bucket)
+  #pragma unroll 1
+  PFOR(r, nefc) {
+    const int k = key[r];
+    int pos = start[k];
+    #pragma unroll 4
+    for (int q = 0; q < r; q++) pos += (key[q] == k);
+    list[pos] = r;
+  }
+  WSYNC();
+}
+MGS_DEV real hess_bucket(const Env &e, int k, int a, int b, const real *W, real s) {
+  const int *list = IARR(EF(efc_list)), *start = IARR(EF(nsS));
+  const int q1 = start[k + 1], nv = MD.nv;
+  #pragma unroll 2
+  for (int q = start[k]; q < q1; q++) {
+    const int i = list[q];
+    s += W[i] * EF(J)[i * nv + a] * EF(J)[i * nv + b];
+  }
+  return s;
+}
+#endif
+
 MGS_DEVN void newton_hessian_w(Env &e) {
   const int nv = MD.nv, npairs = nv * (nv + 1) / 2, nefc = EH.nefc;
   // row weights (D for rows in their quadratic zone, else 0) make the accumulation loop branch-free; efc_jv is
@@ -532,6 +600,24 @@ MGS_DEVN void newton_hessian_w(Env &e) {
   #pragma unroll 1
   PFOR(i, nefc) W[i] = (EFC_STATE(i) == ST_QUADRATIC) ? EF(efc_D)[i] : R_(0.0);
   WSYNC();
+#ifdef MGS_WIDE
+  if (MD.ntree <= MGS_SPARSE_H_MAXTREE) {
+    const int T = MD.ntree;
+    #pragma unroll 1
+    PFOR(idx, npairs) {
+      const int ab = LDG(MD.tri_ab + idx), a = ab >> 8, b = ab & 255;
+      const int madr = LDG(MD.tri_madr + idx);
+      const int ta = LDG(MD.dof_treeid + a), tb = LDG(MD.dof_treeid + b);  // ta >= tb (a >= b, trees are contiguous dof ranges)
+      real s = madr >= 0 ? EF(M)[madr] : R_(0.0);
+      if (ta != tb) s = hess_bucket(e, tb * T + ta, a, b, W, s);
+      else {
+        #pragma unroll 1
+        for (int x = 0; x < T; x++) s = hess_bucket(e, x <= ta ? x * T + ta : ta * T + x, a, b, W, s);
+      }
+      EF(H)[a * nv + b] = s;
+    }
+  } else
+#endif
   #pragma unroll 1
   PFOR(idx, npairs) {
     const int ab = LDG(MD.tri_ab + idx), a = ab >> 8, b = ab & 255;  // lower-triangle index table
@@ -550,6 +636,46 @@ MGS_DEVN void newton_hessian_w(Env &e) {
     const int dim = LDG(MD.pair_condim + IARR(EF(con_pair))[c]);
     real h[16];
     cone_hessian(e, c, i, dim, h);
+#ifdef MGS_WIDE
+    {
+      // only the entries (a, b) whose two dofs lie in the contact's (at most two) kinematic trees can change: enumerate the lower
+      // triangle of that index set instead of all nv (nv + 1) / 2 entries (config 5: <= 820 of 4465, usually 78 or 21)
+      const int p = IARR(EF(con_pair))[c];
+      int t1 = LDG(MD.body_treeid + LDG(MD.cgeom_bodyid + LDG(MD.pair_geom1 + p))), t2 = LDG(MD.body_treeid + LDG(MD.cgeom_bodyid + LDG(MD.pair_geom2 + p)));
+      if (t1 < 0) { t1 = t2; t2 = -1; }
+      if (t1 >= 0) {
+        if (t2 == t1) t2 = -1;
+        if (t2 >= 0 && t2 < t1) { const int t = t1; t1 = t2; t2 = t; }
+        // first dof / size of the two trees: found from the contact's own Jacobian support is not needed - the tree tables give them
+        int lo1 = 0, n1 = 0, lo2 = 0, n2 = 0;
+        #pragma unroll 1
+        for (int d = 0; d < nv; d += LDG(MD.dof_treenum + d)) {
+          const int t = LDG(MD.dof_treeid + d);
+          if (t == t1) { lo1 = d; n1 = LDG(MD.dof_treenum + d); }
+          if (t == t2) { lo2 = d; n2 = LDG(MD.dof_treenum + d); }
+        }
+        const int m = n1 + n2, ne2 = m * (m + 1) / 2;
+        #pragma unroll 1
+        PFOR(e2, ne2) {
+          int u = (int)((sqrtf(8.0f * (float)e2 + 1.0f) - 1.0f) * 0.5f);
+          while (u * (u + 1) / 2 > e2) u--;
+          while ((u + 1) * (u + 2) / 2 <= e2) u++;
+          const int v = e2 - u * (u + 1) / 2;
+          const int a = u < n1 ? lo1 + u : lo2 + (u - n1), b = v < n1 ? lo1 + v : lo2 + (v - n1);
+          real s = 0;
+          #pragma unroll 1
+          for (int j = 0; j < dim; j++) {
+            const real ja = EF(J)[(i + j) * nv + a];
+            if (ja == 0) continue;
+            real t = 0;
+            for (int k = 0; k < 4; k++) t += (k < dim) ? h[j * 4 + k] * EF(J)[(i + k) * nv + b] : R_(0.0);
+            s += ja * t;
+          }
+          EF(H)[a * nv + b] += s;
+        }
+      }
+    }
+#else
     #pragma unroll 1
     PFOR(idx, npairs) {
       const int ab = LDG(MD.tri_ab + idx), a = ab >> 8, b = ab & 255;
@@ -564,6 +690,7 @@ MGS_DEVN void newton_hessian_w(Env &e) {
       }
       EF(H)[a * nv + b] += s;
     }
+#endif
   }
   WSYNC();
   MGS_CLK(4);
@@ -620,6 +747,9 @@ MGS_DEVN void solve_newton_w(Env &e) {
     if (scale * sqrt(gn) < tol_eff) break;
 #endif
     MGS_CLK(3);
+#ifdef MGS_WIDE
+    if (iter == 0 && MD.ntree <= MGS_SPARSE_H_MAXTREE) bucket_rows_w(e);
+#endif
     newton_hessian_w(e);
     MGS_CLK(5);
     chol_solve_w(EF(H), EF(search), nv, 0);
@@ -797,10 +927,15 @@ MGS_DEV real noslip_contact_w(Env &e, int c, int i, int p, const real *AC, real 
     for (int j = 0; j < N; j++) res[j] += EF(J)[(i + 1 + j) * nv + d] * u;
   }
   {
+    // (one combined reduction: in the env-per-CTA variant every reduction costs two CTA barriers)
+    real r0 = res[0], r1 = res[1], r2 = N > 2 ? res[N - 1] : R_(0.0);
+    wsum3(r0, r1, r2);
+    res[0] = r0; res[1] = r1;
+    if (N > 2) res[N - 1] = r2;
     int q = 0;
 #pragma unroll
     for (int j = 0; j < N; j++) {
-      res[j] = wsum(res[j]) - EF(efc_aref)[i + 1 + j];
+      res[j] = res[j] - EF(efc_aref)[i + 1 + j];
       old[j] = EF(efc_force)[i + 1 + j];
       fr[j] = LDG(MD.pair_friction + 5 * p + j);
 #pragma unroll
