@@ -1,6 +1,10 @@
 """Summarise an .ncu-rep of mgs_rollout_kernel: headline metrics + per-function instruction/stall shares.
 
 usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [libmgs_b200.so]  (needs ncu, cuobjdump, nvdisasm; no GPU)
+       MGS_VARIANT=w16|w12|wide selects the kernel variant whose SASS is joined (default w16)
+       MGS_ISSUE_JSON=profiles/issue_slots_r2.json MGS_ISSUE_KEY=robotiq MGS_ENV_STEPS=<env-steps of the captured launch>
+         additionally records warp-instructions per env-step (smsp__inst_executed.sum / env-steps) under that key: bench.py's
+         issue_slots block reads the file, so the figure is derived by this script from the committed capture, not typed in.
 """
 import collections, csv, io, os, re, subprocess, sys, tempfile
 
@@ -19,6 +23,21 @@ print("== headline")
 for h, u, v in zip(hdr, units, vals):
     if h in want or (h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio") and float(v or 0) > 0.05):
         print(f"{h} [{u}] {v}")
+if os.environ.get("MGS_ISSUE_JSON"):
+    import json
+    path, key, steps = os.environ["MGS_ISSUE_JSON"], os.environ["MGS_ISSUE_KEY"], float(os.environ["MGS_ENV_STEPS"])
+    d = {}
+    try:
+        d = json.load(open(path))
+    except Exception:
+        pass
+    m = dict(zip(hdr, vals))
+    inst = float(m["smsp__inst_executed.sum"].replace(",", ""))
+    d[key] = {"warp_instr_per_env_step": inst / steps, "env_steps_of_capture": steps, "smsp__inst_executed.sum": inst,
+              "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+              "thread_inst_per_inst": float(m["smsp__thread_inst_executed_per_inst_executed.ratio"]),
+              "source": f"{os.path.basename(rep)}: steady hold-phase launch (tools/profile_steady.py), summarised by tools/ncu_summary.py"}
+    json.dump(d, open(path, "w"), indent=1)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 srows = list(csv.reader(io.StringIO(src)))
 shdr = srows[1]

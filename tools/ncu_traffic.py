@@ -24,5 +24,5 @@ for arg in sys.argv[1:]:
     t = vals["gpu__time_duration.sum"]
     out[key] = {"bytes_per_launch": b, "seconds_under_ncu": t, "gbs": b / t / 1e9, "read_bytes": vals["dram__bytes_read.sum"], "write_bytes": vals["dram__bytes_write.sum"],
                 "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of one full 4096-candidate rollout launch ({os.path.basename(path)})"}
-json.dump(out, open(os.path.join(ROOT, "profiles", "traffic_r1.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "profiles", os.environ.get("MGS_TRAFFIC_OUT", "traffic_r2.json")), "w"), indent=1)
 print(json.dumps(out, indent=1))

@@ -2,7 +2,7 @@
 of the close phase (launch 1, not profiled: use `ncu --launch-skip 1 --launch-count 1`), then `nstep` more
 steps of the HOLD phase run as launch 2 - the regime that makes up >90 % of the 8000-step schedule.
 
-usage: python tools/profile_steady.py [gripper] [n_env] [settle_steps] [nstep]
+usage: python tools/profile_steady.py [gripper] [n_env] [settle_steps] [nstep] [ncon_max nefc_max]
 """
 import os, sys, time
 import numpy as np
@@ -16,7 +16,10 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 2368
 settle = int(sys.argv[3]) if len(sys.argv) > 3 else 1200
 nstep = int(sys.argv[4]) if len(sys.argv) > 4 else 200
 m, info, pose7, joints = scenes.workload(gripper, "hull", 0, n)
-caps = dict(ncon_max=20, nefc_max=90) if gripper == "panda" else {}
+# capacities: argv[5], argv[6] (default: bench.py's for the two bench grippers)
+caps = {"panda": dict(ncon_max=24, nefc_max=100), "robotiq2f85": dict(ncon_max=24, nefc_max=110)}.get(gripper, {})
+if len(sys.argv) > 6:
+    caps = dict(ncon_max=int(sys.argv[5]), nefc_max=int(sys.argv[6]))
 G = BatchSim(m, **caps)
 qpos = np.tile(m.qpos0, (n, 1))
 b = info["base_qposadr"]
