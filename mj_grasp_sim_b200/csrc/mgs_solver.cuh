@@ -629,6 +629,9 @@ MGS_DEVN void newton_hessian_w(Env &e) {
     EF(H)[a * nv + b] = (real)s;
   }
   // contacts on the cone surface (usually few): every lane rebuilds the small block, lanes split (a,b)
+#ifdef MGS_WIDE
+  WSYNC();  // the entries change hands below (per-contact enumeration): the products above must have landed
+#endif
   #pragma unroll 1
   for (int c = 0; c < EH.ncon; c++) {
     const int i = IARR(EF(con_efc))[c];
@@ -674,6 +677,7 @@ MGS_DEVN void newton_hessian_w(Env &e) {
           EF(H)[a * nv + b] += s;
         }
       }
+      WSYNC();  // the next contact enumerates the entries differently: another thread may own (a, b) then
     }
 #else
     #pragma unroll 1
@@ -968,6 +972,9 @@ MGS_DEV real noslip_contact_w(Env &e, int c, int i, int p, const real *AC, real 
     change = 0;
   }
   // w += M^-1 (J_c' delta): with the precomputed B_c = M^-1 J_c' (Bc != 0) three FMAs per dof
+#ifdef MGS_WIDE
+  WSYNC();  // every warp has read `old` / the residual inputs before the forces are overwritten
+#endif
   if (MGS_LANE == 0) {
 #pragma unroll
     for (int j = 0; j < N; j++) EF(efc_force)[i + 1 + j] = v[j];
