@@ -370,8 +370,11 @@ def run_ours(args, rank, world, local_rank):
             return run
         buckets = [Bucket(s["name"], N_CAND, runner(s), 1.0) for s in sets]
         info0 = sets[0]["sim"].info
-        chunk = 2 * info0.warps_per_block * info0.blocks_per_sm * info0.num_sms  # two waves of resident environments per hand-out
-        chunk = min(N_CAND, chunk)
+        # one hand-out = one wave of resident environments at the CTA size a whole-bucket launch would use (4096 Panda candidates
+        # run as 2 waves of 14 environments per SM: chunk = 14 x 148 = 2072), so a chunk costs the same per candidate as a full launch
+        slots = info0.warps_per_block * info0.blocks_per_sm * info0.num_sms
+        waves = -(-N_CAND // slots)
+        chunk = min(N_CAND, -(-N_CAND // (waves * info0.num_sms)) * info0.num_sms)
         for _ in range(warmup):
             flush.fill_(1)
             run_mixed(buckets[:2 * min(world, N_OBJECTS)], N_CAND, device=dev)  # warm-up: one launch of each model per rank

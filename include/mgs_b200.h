@@ -125,6 +125,14 @@ const char *mgs_build_stamp(void);
 long long mgs_launch_count(void);
 const char *mgs_last_error(void);
 
+/* Ray casting of the antipodal grasp sampler (replaces the per-point trimesh ray queries of
+ * /root/reference/mgs/sampler/antipodal.py:115-151).  For every point i: rays from p1[i] along +dirs[i] and -dirs[i] against the
+ * nface triangles tri[nface][3][3] (host arrays, float64); hits closer than eps are dropped; of the nvalid_out[i] remaining hits
+ * (ordered: +dir faces 0..nface-1, then -dir faces) number floor(pick_u[i] * nvalid) is chosen and its signed distance along dirs[i]
+ * is written to signed_t_out[i] (NaN when there is no valid hit).  One warp per point, triangles staged through shared memory. */
+int mgs_antipodal_hits(int device, int n, const double *p1, const double *dirs, int nface, const double *tri, double eps,
+                       const double *pick_u, double *signed_t_out, int *nvalid_out);
+
 #ifdef __cplusplus
 }
 #endif

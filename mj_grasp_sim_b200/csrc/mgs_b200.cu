@@ -32,6 +32,7 @@ static std::vector<char> g_have_last;
 #endif
 
 static int fail(const std::string &msg) { g_err = msg; return -1; }
+int mgs_set_error(const char *msg) { return fail(msg); }  // for the other translation units of the library
 #define CU(call)                                                                                  \
   do {                                                                                            \
     cudaError_t e_ = (call);                                                                      \

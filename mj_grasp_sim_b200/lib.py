@@ -69,7 +69,7 @@ def build(force: bool = False, f64: bool = False) -> str:
     # and one environment per 256-thread CTA; see csrc/mgs_kernel_ops.h)
     cmd = ["nvcc"] + NVCC_FLAGS + (["-DMGS_REAL_DOUBLE"] if f64 else []) + [f'-DMGS_BUILD_STAMP="{stamp}"', "-o", so,
                                                                              os.path.join(CSRC, "mgs_b200.cu"), os.path.join(CSRC, "mgs_kernel_w12.cu"),
-                                                                             os.path.join(CSRC, "mgs_kernel_wide.cu")]
+                                                                             os.path.join(CSRC, "mgs_kernel_wide.cu"), os.path.join(CSRC, "mgs_sampler.cu")]
     subprocess.check_call(cmd)
     with open(so + ".stamp", "w") as f:
         f.write(stamp)
@@ -99,6 +99,7 @@ def bind(L, prefix="mgs_"):
         L.mgs_launch_count.restype = C.c_longlong
         L.mgs_overflow_count.argtypes = [vp]
         L.mgs_build_stamp.restype = C.c_char_p
+        L.mgs_antipodal_hits.argtypes = [C.c_int, C.c_int, dp, dp, C.c_int, dp, C.c_double, dp, dp, ip]
     else:
         L.l1_model_create.argtypes = [C.POINTER(MgsModelDesc), C.POINTER(vp)]
         L.l1_rollout_host.argtypes = [vp, C.c_int, C.c_int, fp, fp, C.c_int, ip, C.c_int, dp, C.POINTER(MgsRolloutCfg), u8p, ip]
@@ -315,3 +316,14 @@ class BatchSim:
         cc = np.ascontiguousarray(close_ctrl if close_ctrl is not None else np.zeros(max(1, self.model.nu)), dtype=np.float64)
         self._check(self.L.mgs_rollout_device(self.h, mode, n, d_pose7_ptr, d_joints_ptr, nj, _ip(jadr), int(base_qposadr), _dp(cc),
                                               C.byref(cfg) if cfg is not None else None, d_labels_ptr, d_steps_ptr, stream_ptr))
+
+
+def antipodal_hits(p1, dirs, tri, eps, pick_u, device: int = 0):
+    """mgs_antipodal_hits (include/mgs_b200.h): (signed distance along dirs of the chosen hit [n] (NaN: none), number of valid hits [n])."""
+    L = load()
+    p1, dirs, tri, pick_u = (np.ascontiguousarray(a, dtype=np.float64) for a in (p1, dirs, tri, pick_u))
+    n = len(p1)
+    t, nv = np.full(n, np.nan), np.zeros(n, dtype=np.int32)
+    if n and L.mgs_antipodal_hits(device, n, _dp(p1), _dp(dirs), len(tri), _dp(tri), float(eps), _dp(pick_u), _dp(t), _ip(nv)) != 0:
+        raise MgsError(L.mgs_last_error().decode())
+    return t, nv

@@ -67,7 +67,14 @@ class AntipodalGraspGenerator(GraspGenerator):
     def denormalize_points(self, points):
         return (points - self.offset) * self.scale
 
-    # ---- ray casting: every ray against every face ---------------------------------------------------------------
+    def _use_kernel(self) -> bool:
+        """CUDA kernel when a device is there and the caller did not ask for the host expression (device="cpu")."""
+        if self.device == "cpu":
+            return False
+        import torch
+        return torch.cuda.is_available()
+
+    # ---- ray casting: every ray against every face (host / torch expression; the reference check of the kernel) ---------
     def _ray_hits(self, origins: np.ndarray, dirs: np.ndarray) -> np.ndarray:
         """distance along each ray to each face, inf where the ray misses: float64 [n_rays, n_faces]"""
         import torch
@@ -104,14 +111,23 @@ class AntipodalGraspGenerator(GraspGenerator):
         p1 = T[f, 0] + r1[:, None] * (T[f, 1] - T[f, 0]) + r2[:, None] * (T[f, 2] - T[f, 0])
         dirs = _vmf3(-fn[f], kappa, rng)
         # two rays per point (+dir, -dir); valid hits are at least eps away; one valid hit chosen uniformly at random
-        t = np.concatenate([self._ray_hits(p1, dirs), self._ray_hits(p1, -dirs)], axis=1)  # [num, 2 * faces]
-        sign = np.concatenate([np.ones(len(self.tris)), -np.ones(len(self.tris))])
-        valid = np.isfinite(t) & (t >= eps)
-        nvalid = valid.sum(axis=1)
-        pick = (rng.uniform(size=num) * np.maximum(nvalid, 1)).astype(int)
-        order = np.argsort(~valid, axis=1, kind="stable")  # valid hits first, in face order
-        col = order[np.arange(num), np.minimum(pick, np.maximum(nvalid - 1, 0))]
-        p2 = p1 + (sign[col] * t[np.arange(num), col])[:, None] * dirs
+        pick_u = rng.uniform(size=num)
+        if self._use_kernel():
+            # the hand-written kernel (csrc/mgs_sampler.cu through mgs_antipodal_hits): one warp per point, triangles in shared memory
+            from ...lib import antipodal_hits
+            import torch
+            dev = torch.cuda.current_device() if self.device in (None, "cuda") else int(str(self.device).split(":")[1])
+            st, nvalid = antipodal_hits(p1, dirs, T, eps, pick_u, device=dev)
+            p2 = p1 + np.where(nvalid > 0, st, 0.0)[:, None] * dirs
+        else:
+            t = np.concatenate([self._ray_hits(p1, dirs), self._ray_hits(p1, -dirs)], axis=1)  # [num, 2 * faces]
+            sign = np.concatenate([np.ones(len(self.tris)), -np.ones(len(self.tris))])
+            valid = np.isfinite(t) & (t >= eps)
+            nvalid = valid.sum(axis=1)
+            pick = (pick_u * np.maximum(nvalid, 1)).astype(int)
+            order = np.argsort(~valid, axis=1, kind="stable")  # valid hits first, in face order
+            col = order[np.arange(num), np.minimum(pick, np.maximum(nvalid - 1, 0))]
+            p2 = p1 + (sign[col] * t[np.arange(num), col])[:, None] * dirs
         nohit = nvalid == 0
         p2[nohit] = p1[nohit] + rng.uniform(-0.05, 0.05, size=(int(nohit.sum()), 3))
         Hs = self.denorm_grasp_pose(self.define_gripper_pose(p1, p2, rng))

@@ -641,3 +641,24 @@ def test_config5_shadow_hand_in_ten_object_clutter(libs):
     assert np.array_equal(free, ofree)
     assert (lab == olab)[~over].mean() >= 0.8, (lab == olab).mean()
     assert 0.2 <= olab.mean() <= 0.9
+
+
+def test_antipodal_sampler_kernel_matches_the_host_expression(libs):
+    """the ray casting of the antipodal sampler as a CUDA kernel (mgs_antipodal_hits) against the batched host
+    expression of mgs/sampler/antipodal.py on the same seeds: same number of valid hits per point, same chosen hit, same frames."""
+    from mj_grasp_sim_b200.mgs.obj.selector import get_object
+    from mj_grasp_sim_b200.mgs.sampler.antipodal import AntipodalGraspGenerator
+    mlib, _ = libs
+    for oid, n in (("cube", 2000), ("hull:3", 3000), ("hull:5:64", 1111)):
+        obj = get_object(oid)
+        Hk, ak = AntipodalGraspGenerator(obj, device="cuda", seed=11).generate_grasps(n)
+        Hh, ah = AntipodalGraspGenerator(obj, device="cpu", seed=11).generate_grasps(n)
+        assert np.array_equal(ak["fallback"], ah["fallback"])
+        assert np.abs(Hk - Hh).max() < 1e-9 and np.abs(ak["width"] - ah["width"]).max() < 1e-9
+    # the raw entry point: ragged sizes, rays that miss everything
+    v, t = get_object("hull:3").mesh()
+    tri = np.asarray(v)[np.asarray(t)]
+    p1 = np.array([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [0.0, 0.0, 0.0]])
+    d = np.array([[0.0, 0.0, 1.0], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]])
+    st, nv = mlib.antipodal_hits(p1, d, tri, 1e-5, np.array([0.0, 0.5, 0.999]))
+    assert nv[0] == 2 and nv[1] == 0 and nv[2] == 2 and np.isnan(st[1]) and st[0] > 0 and st[2] < 0
