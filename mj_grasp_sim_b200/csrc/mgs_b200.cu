@@ -51,6 +51,7 @@ struct MgsModel {
   // staging for the host-pointer entry points (grown on demand)
   void *d_stage, *h_stage;
   size_t stage_bytes;
+  int *d_mpr_cache;  // env-per-CTA variant: global MPR cache, one slab of npair x 4 words per CTA of the persistent grid
   float *d_aux;  // [aux_cap][4] per-candidate auxiliary results of the most recent rollout launch (flags, drift)
   int aux_cap, aux_n;
   double qvel_clip;
@@ -136,6 +137,8 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
     CU(ops->occupancy(&occ, ops->lanes_per_env, (size_t)env_bytes));
     best_warps = occ;
     M->warps_per_block = 1; M->blocks_per_sm = occ; M->ops = ops;
+    if (desc->npair > M->L.ncache && occ > 0)
+      CU(cudaMalloc(&M->d_mpr_cache, (size_t)M->num_sms * occ * desc->npair * 4 * sizeof(int)));
   }
   if (best_warps == 0) { delete M; return fail("kernel does not fit on this device"); }
   M->smem_per_block = env_bytes * M->warps_per_block;
@@ -152,6 +155,7 @@ extern "C" void mgs_model_destroy(MgsModel *M) {
   cudaSetDevice(M->device);
   cudaFree(M->d_blob);
   cudaFree(M->d_counter);
+  if (M->d_mpr_cache) cudaFree(M->d_mpr_cache);
   if (M->d_aux) cudaFree(M->d_aux);
   if (M->d_stage) cudaFree(M->d_stage);
   if (M->h_stage) cudaFreeHost(M->h_stage);
@@ -209,6 +213,7 @@ static int launch(MgsModel *M, const RolloutParams &prm, const BatchIO &io_in, c
     M->aux_cap = cap;
   }
   io.aux = M->d_aux;
+  io.mpr_cache_g = M->d_mpr_cache;
   M->aux_n = prm.n;
   // Wave quantisation: every candidate of a batch costs about the same, so what matters is the number of
   // "waves" of resident environments.  If fewer warps per CTA give the same number of waves, use fewer: each

@@ -433,13 +433,21 @@ MGS_DEVN void collide_pair(Env &e, int pair, PairContacts &out) {
   geomref_init(g2, e, c2);
   real depth = 0, n[3], pos[3];
   int *cache = (active && pair < LY.ncache) ? IARR(EF(mpr_cache)) + 4 * pair : (int *)0;
+#ifdef MGS_WIDE
+  // config 5 lists 1,198 pairs, the shared-memory cache holds 128: the others keep their warm start in a global slab of this CTA
+  // (stage clocks: cold-started MPR was 410 k of the step's 1.9 M cycles - every iteration of the lockstep loop costs two hull supports
+  // out of L2, and a cold pair needs 20-30 of them where a warm one needs 1-3)
+  if (active && pair >= LY.ncache && IO.mpr_cache_g) cache = IO.mpr_cache_g + ((size_t)blockIdx.x * MD.npair + pair) * 4;
+#endif
 #ifdef MGS_NO_MPR_WARMSTART
   cache = (int *)0;
 #endif
   // hull supports resume their hill climb from the vertices this pair ended on at the previous step (word 3:
   // two 16-bit vertex ids, 0 after reset); poses change by micrometres per step, so the climb is 0-1 moves
   if (cache && active) { g1.cur = cache[3] & 0xffff; g2.cur = (cache[3] >> 16) & 0xffff; }
+  MGS_CLK(1);
   int hit = mpr_penetration(g1, g2, active, cache, &depth, n, pos);
+  MGS_CLK(9);
   hit = hit && (depth > 0);
   // polytope pairs: multi-point manifold from the two most-aligned faces.  The face searches are warp-cooperative,
   // so no lane leaves before them (the clipping itself stays per lane).
@@ -555,6 +563,7 @@ MGS_DEVN void collide_pair(Env &e, int pair, PairContacts &out) {
     }
     WSYNC();
   }
+  MGS_CLK(10);
   if (!hit || done) return;
   out.n = 1;
   copy3(out.normal, n);
@@ -604,6 +613,12 @@ MGS_DEVN void collision_w(Env &e) {
       const real rr = LDG(MD.cgeom_rbound + c1) + LDG(MD.cgeom_rbound + c2) + LDG(MD.pair_margin + p);
       active = dot3(dc, dc) <= rr * rr;
       if (!active && p < LY.ncache) IARR(EF(mpr_cache))[4 * p + 2] = -1;  // a culled pair forgets its portal / axis
+#ifdef MGS_WIDE
+      if (!active && p >= LY.ncache && IO.mpr_cache_g) {
+        int *cg = IO.mpr_cache_g + ((size_t)blockIdx.x * MD.npair + p) * 4;
+        if (cg[2] != -1) cg[2] = -1;
+      }
+#endif
     }
     int k, rank = wrank(active, &k);
     if (k == 0) continue;

@@ -14,6 +14,16 @@ static inline int mgs_diag_stride(int nv, int nbody, int ncon_max, int nefc_max)
   return MGS_DIAG_HEADER + 3 * nv + nv * nv + 7 * nbody + 5 * ncon_max + 4 * nefc_max;
 }
 
+MGS_DEV void mpr_cache_g_reset_w() {
+#ifdef MGS_WIDE
+  if (IO.mpr_cache_g) {
+    int *g = IO.mpr_cache_g + (size_t)blockIdx.x * MD.npair * 4;
+    #pragma unroll 1
+    PFOR(i, 4 * MD.npair) g[i] = (i & 3) == 3 ? 0 : -1;
+  }
+#endif
+}
+
 MGS_DEVN void reset_w(Env &e) {
   #pragma unroll 1
   PFOR(i, MD.nq) { EF(qpos)[i] = LDG(MD.qpos0 + i); QPOS_LO_CLEAR(i); }
@@ -29,6 +39,7 @@ MGS_DEVN void reset_w(Env &e) {
   EH.bad = 0; EH.overflow = 0; EH.ncon = 0; EH.nefc = 0;
   #pragma unroll 1
   PFOR(i, 4 * LY.ncache) IARR(EF(mpr_cache))[i] = (i & 3) == 3 ? 0 : -1;
+  mpr_cache_g_reset_w();
   WSYNC();
 }
 
@@ -146,6 +157,7 @@ MGS_DEVN void load_record_w(Env &e, const real *in) {
   EH.bad = 0; EH.overflow = 0; EH.ncon = 0; EH.nefc = 0;
   #pragma unroll 1
   PFOR(i, 4 * LY.ncache) IARR(EF(mpr_cache))[i] = (i & 3) == 3 ? 0 : -1;
+  mpr_cache_g_reset_w();
   #pragma unroll 1
   PFOR(i, MD.nq) { EF(qpos)[i] = in[i]; QPOS_LO_CLEAR(i); }
   #pragma unroll 1
