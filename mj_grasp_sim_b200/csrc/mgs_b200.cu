@@ -51,7 +51,7 @@ struct MgsModel {
   // staging for the host-pointer entry points (grown on demand)
   void *d_stage, *h_stage;
   size_t stage_bytes;
-  int *d_mpr_cache;  // env-per-CTA variant: global MPR cache, one slab of npair x 4 words per CTA of the persistent grid
+  int *d_mpr_cache;  // global MPR cache (models with more pairs than the shared-memory cache holds): npair x 4 words per environment slot
   float *d_aux;  // [aux_cap][4] per-candidate auxiliary results of the most recent rollout launch (flags, drift)
   int aux_cap, aux_n;
   double qvel_clip;
@@ -137,8 +137,11 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
     CU(ops->occupancy(&occ, ops->lanes_per_env, (size_t)env_bytes));
     best_warps = occ;
     M->warps_per_block = 1; M->blocks_per_sm = occ; M->ops = ops;
-    if (desc->npair > M->L.ncache && occ > 0)
-      CU(cudaMalloc(&M->d_mpr_cache, (size_t)M->num_sms * occ * desc->npair * 4 * sizeof(int)));
+  }
+  if (best_warps > 0 && desc->npair > M->L.ncache) {
+    // global MPR cache: one slab per environment slot (CTA of the wide variant, warp slot of the warp variants)
+    const size_t slots = (size_t)M->num_sms * M->blocks_per_sm * (M->ops->lanes_per_env > 32 ? 1 : M->ops->max_warps);
+    CU(cudaMalloc(&M->d_mpr_cache, slots * desc->npair * 4 * sizeof(int)));
   }
   if (best_warps == 0) { delete M; return fail("kernel does not fit on this device"); }
   M->smem_per_block = env_bytes * M->warps_per_block;

@@ -433,11 +433,12 @@ MGS_DEVN void collide_pair(Env &e, int pair, PairContacts &out) {
   geomref_init(g2, e, c2);
   real depth = 0, n[3], pos[3];
   int *cache = (active && pair < LY.ncache) ? IARR(EF(mpr_cache)) + 4 * pair : (int *)0;
-#ifdef MGS_WIDE
-  // config 5 lists 1,198 pairs, the shared-memory cache holds 128: the others keep their warm start in a global slab of this CTA
-  // (stage clocks: cold-started MPR was 410 k of the step's 1.9 M cycles - every iteration of the lockstep loop costs two hull supports
-  // out of L2, and a cold pair needs 20-30 of them where a warm one needs 1-3)
-  if (active && pair >= LY.ncache && IO.mpr_cache_g) cache = IO.mpr_cache_g + ((size_t)blockIdx.x * MD.npair + pair) * 4;
+#ifndef MGS_HOST
+  // config 5 lists 1,198 pairs (LEAP 1,764), the shared-memory cache holds 128: the others keep their warm start in a global, L2-resident
+  // slab of this environment slot (stage clocks of config 5: cold-started MPR was 410 k of the step's 1.9 M cycles - every iteration of
+  // the lockstep loop costs two hull supports out of L2, a cold pair needs 20-30 of them where a warm one needs 1-3 - and in fp32 a
+  // cold start against the 20 m table box stops at the iteration cap with a noisy depth: lift labels 57/64 -> 64/64 equal to the oracle)
+  if (active && pair >= LY.ncache && IO.mpr_cache_g) cache = IO.mpr_cache_g + ((size_t)MGS_ENV_SLOT * MD.npair + pair) * 4;
 #endif
 #ifdef MGS_NO_MPR_WARMSTART
   cache = (int *)0;
@@ -613,9 +614,9 @@ MGS_DEVN void collision_w(Env &e) {
       const real rr = LDG(MD.cgeom_rbound + c1) + LDG(MD.cgeom_rbound + c2) + LDG(MD.pair_margin + p);
       active = dot3(dc, dc) <= rr * rr;
       if (!active && p < LY.ncache) IARR(EF(mpr_cache))[4 * p + 2] = -1;  // a culled pair forgets its portal / axis
-#ifdef MGS_WIDE
+#ifndef MGS_HOST
       if (!active && p >= LY.ncache && IO.mpr_cache_g) {
-        int *cg = IO.mpr_cache_g + ((size_t)blockIdx.x * MD.npair + p) * 4;
+        int *cg = IO.mpr_cache_g + ((size_t)MGS_ENV_SLOT * MD.npair + p) * 4;
         if (cg[2] != -1) cg[2] = -1;
       }
 #endif

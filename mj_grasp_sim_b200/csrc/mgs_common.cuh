@@ -231,7 +231,7 @@ struct BatchIO {
                    // (position [m], rotation [deg]; gravityless_object_grasping.py:175-200), reserved
   int state_stride, diag_stride;
   unsigned int *work_counter;
-  // env-per-CTA variant: per-pair MPR cache of the pairs beyond the shared-memory one (4 words per pair, one slab of npair pairs per
-  // CTA; L2 resident) - null for the warp variants
+  // per-pair MPR cache of the pairs beyond the shared-memory one (4 words per pair, one slab of npair pairs per environment slot of the
+  // persistent grid; L2 resident) - null for models whose pairs all fit the shared-memory cache
   int *mpr_cache_g;
 };

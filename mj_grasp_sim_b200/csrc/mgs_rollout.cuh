@@ -15,9 +15,9 @@ static inline int mgs_diag_stride(int nv, int nbody, int ncon_max, int nefc_max)
 }
 
 MGS_DEV void mpr_cache_g_reset_w() {
-#ifdef MGS_WIDE
+#ifndef MGS_HOST
   if (IO.mpr_cache_g) {
-    int *g = IO.mpr_cache_g + (size_t)blockIdx.x * MD.npair * 4;
+    int *g = IO.mpr_cache_g + (size_t)MGS_ENV_SLOT * MD.npair * 4;
     #pragma unroll 1
     PFOR(i, 4 * MD.npair) g[i] = (i & 3) == 3 ? 0 : -1;
   }

@@ -269,8 +269,10 @@ struct Env { real *base; };
 extern __shared__ __align__(16) unsigned char mgs_smem_raw[];
 #ifdef MGS_WIDE
 #define EBASE (reinterpret_cast<real *>(mgs_smem_raw))
+#define MGS_ENV_SLOT ((int)blockIdx.x)  // index of this environment slot in the persistent grid
 #else
 #define EBASE (reinterpret_cast<real *>(mgs_smem_raw) + (size_t)(threadIdx.x >> 5) * LY.total)
+#define MGS_ENV_SLOT ((int)(blockIdx.x * MGS_MAX_WARPS_PER_BLOCK + (threadIdx.x >> 5)))
 #endif
 #endif
 #define EF(name) (EBASE + LY.name)
