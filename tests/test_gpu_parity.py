@@ -588,6 +588,8 @@ def test_env_per_cta_variant_against_oracle_and_warp_variant(libs, request, fixt
     sched = (300, 100, 20, 1 if fixture == "allegro_hull" else 0, 0.02, 0.02)
     args = (pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], mlib.MgsRolloutCfg(*sched))
     lw, sw = W.stability(*args)
+    lw2, sw2 = W.stability(*args)
+    assert np.array_equal(lw, lw2) and np.array_equal(sw, sw2)  # block-level reductions combine partial sums in a fixed order: deterministic
     la, sa = A.stability(*args)
     olab, osteps = _oracle_batch(orc, m, info, 1, pose7, joints, sched)
     assert np.array_equal(W.collision_mask(*args[:4]), A.collision_mask(*args[:4]))
@@ -634,6 +636,8 @@ def test_config5_shadow_hand_in_ten_object_clutter(libs):
     lab, steps = G.clutter_stable_mask(rec, pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], mlib.MgsRolloutCfg(*sched))
     over = G.last_aux(n)["overflow"]
     assert over.sum() == G.overflow_count() <= 0.05 * n
+    lab2, steps2 = G.clutter_stable_mask(rec, pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], mlib.MgsRolloutCfg(*sched))
+    assert np.array_equal(lab, lab2) and np.array_equal(steps, steps2)  # deterministic (also through the global MPR cache)
     a = (pose7.astype(np.float64), info["base_qposadr"], joints.astype(np.float64), info["joint_qposadr"], info["close_ctrl"], orc.RolloutCfg(*sched),
          os.cpu_count() or 1)
     ofree, _ = orc.batch(m, 2, *a, scene=rec, ground_name="geom:table")
