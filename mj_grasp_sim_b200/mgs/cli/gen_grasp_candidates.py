@@ -2,8 +2,9 @@
 
 Antipodal candidates for the parallel-jaw grippers the reference serves this way (Panda, VX300: `all_gripper`, :23-28):
 poses from `AntipodalGraspGenerator`, finger joints from the contact distance through `_clamp_width` + `width_to_joints`
-(:62-64), written as <MGS_OUTPUT_DIR>/<gripper name>/<object id>/candidates.npz {pose [N,4,4], joints [N,2]}.  The
-dexterous hands use the reference's differentiable contact sampler, which is out of scope.
+(:62-64), written as <MGS_OUTPUT_DIR>/<gripper name>/<object id>/candidates.npz {pose [N,4,4], joints [N,2]}.  The LEAP and Shadow
+hands get theirs from the contact-based differentiable sampler (`mgs.sampler.contact.ContactBasedDiff`, :30-40, :71-78): palm poses
+and joint postures, joints [N, 16 / 22].
 
   python -m mj_grasp_sim_b200.mgs.cli.gen_grasp_candidates gripper=PandaGripper object=hull:0 [num_grasps=10000] [seed=0]
 """
@@ -17,15 +18,24 @@ from ..sampler.antipodal import AntipodalGraspGenerator
 from ._common import cfg_get, gripper_name_from_cfg, object_id_from_cfg, parse_kv
 
 
+HANDS = {"LeapGripper": "leap", "LeapHand": "leap", "ShadowHand": "shadow"}  # hands served by the contact-based sampler
+
+
 def run(gripper_name: str, object_id: str, num_grasps: int = 10000, output_dir: str | None = None, seed: int | None = None):
-    if gripper_name not in ("PandaGripper", "VXGripper"):
-        raise NotImplementedError(f"{gripper_name}: only PandaGripper and VXGripper have antipodal candidates (gen_grasp_candidates.py:23-28)")
+    if gripper_name not in ("PandaGripper", "VXGripper") and gripper_name not in HANDS:
+        raise NotImplementedError(f"{gripper_name}: Panda / VX300 have antipodal candidates, LEAP / Shadow contact-based ones (gen_grasp_candidates.py:23-40)")
     print(f"Generating grasp candidates for gripper: {gripper_name}")
-    gripper = get_gripper(gripper_name)
     obj = get_object(object_id)
-    Hs, aux = AntipodalGraspGenerator(obj, seed=seed).generate_grasps(num_grasps)
-    j1, j2 = gripper.width_to_joints(gripper._clamp_width(aux["width"]))
-    joints = np.stack([j1, j2], axis=-1)
+    if gripper_name in HANDS:
+        from ..sampler.contact import ContactBasedDiff
+        from ..sampler.kin import HandKinematics
+        Hs, aux = ContactBasedDiff(obj, seed=seed if seed is not None else 0).generate_grasps(num_grasps, HandKinematics(HANDS[gripper_name]))
+        joints = aux["joints"]
+    else:
+        gripper = get_gripper(gripper_name)
+        Hs, aux = AntipodalGraspGenerator(obj, seed=seed).generate_grasps(num_grasps)
+        j1, j2 = gripper.width_to_joints(gripper._clamp_width(aux["width"]))
+        joints = np.stack([j1, j2], axis=-1)
     out = os.path.join(output_dir or os.getenv("MGS_OUTPUT_DIR") or ".", gripper_name, object_id)
     os.makedirs(out, exist_ok=True)
     np.savez(os.path.join(out, "candidates.npz"), pose=Hs, joints=joints)

@@ -666,3 +666,27 @@ def test_antipodal_sampler_kernel_matches_the_host_expression(libs):
     d = np.array([[0.0, 0.0, 1.0], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]])
     st, nv = mlib.antipodal_hits(p1, d, tri, 1e-5, np.array([0.0, 0.5, 0.999]))
     assert nv[0] == 2 and nv[1] == 0 and nv[2] == 2 and np.isnan(st[1]) and st[0] > 0 and st[2] < 0
+
+
+def test_contact_sampler_candidates_feed_the_hot_path(libs):
+    """SURVEY 8(f) row 4 end to end: LEAP candidates from the contact-based sampler (torch on the GPU) go through the env mirror's
+    collision mask and a shortened stability rollout (fp64 product path of the hands); the masks are deterministic and the
+    sampler's postures are inside the joint ranges the simulator enforces."""
+    from mj_grasp_sim_b200.mgs.env.gravityless_object_grasping import GravitylessObjectGrasping
+    from mj_grasp_sim_b200.mgs.gripper.selector import get_gripper
+    from mj_grasp_sim_b200.mgs.obj.selector import get_object
+    from mj_grasp_sim_b200.mgs.sampler.contact import ContactBasedDiff
+    from mj_grasp_sim_b200.mgs.sampler.kin import HandKinematics
+    from mj_grasp_sim_b200.mgs.util.geo.transforms import SE3Pose
+    obj = get_object("hull:3")
+    kin = HandKinematics("leap")
+    H, aux = ContactBasedDiff(obj, device="cuda", seed=2).generate_grasps(48, kin)
+    assert H.shape == (48, 4, 4) and aux["joints"].shape == (48, 16) and np.isfinite(H).all()
+    env = GravitylessObjectGrasping(get_gripper("LeapGripper"), obj)
+    assert env.compute_f64 and env.sim.info.real_bytes == 8
+    poses = SE3Pose.from_mat(H, type="wxyz")
+    free = env.grasp_collision_mask(poses, aux["joints"])
+    assert free.shape == (48,) and np.array_equal(free, env.grasp_collision_mask(poses, aux["joints"]))
+    env.gripper.NSTEP_CLOSE = 300
+    lab = env.grasp_stability_evaluation_from_joints(poses, aux["joints"], nstep_lift=100, lift_dist=0.02, shake_steps=10)
+    assert lab.shape == (48,) and lab.dtype == bool and env.last_overflow["after_escalation"] == 0

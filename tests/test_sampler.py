@@ -75,5 +75,5 @@ def test_gen_grasp_candidates_cli(tmp_path):
     env = GravitylessObjectGrasping(get_gripper("PandaGripper"), get_object("hull:0"))
     pose7, j32, jadr = env._process(SE3Pose.from_mat(f["pose"], type="wxyz"), f["joints"])
     assert pose7.shape == (256, 7) and j32.shape == (256, 2) and np.isfinite(pose7).all()
-    with pytest.raises(NotImplementedError):
-        gen_grasp_candidates.run("ShadowHand", "hull:0", 8, str(tmp_path))
+    with pytest.raises(NotImplementedError):  # Allegro has neither an antipodal nor a contact-based producer in the reference
+        gen_grasp_candidates.run("AllegroGripper", "hull:0", 8, str(tmp_path))
