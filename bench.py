@@ -74,7 +74,8 @@ def rollout_cfg(gripper):
 
 def make_object_workload(gripper, k, n=N_CAND):
     from mj_grasp_sim_b200 import scenes
-    return scenes.workload(gripper, "hull", k, n, n_v=HULL_NV[k % len(HULL_NV)])
+    nv = int(os.environ.get("MGS_BENCH_HULL_NV", "0")) or HULL_NV[k % len(HULL_NV)]  # (MGS_BENCH_HULL_NV=32 MGS_BENCH_OBJECTS=1: round 1's workload)
+    return scenes.workload(gripper, "hull", k, n, n_v=nv)
 
 
 class ClockSampler:
@@ -242,7 +243,7 @@ def run_ours(args, rank, world, local_rank):
             ncon_max, nefc_max = (int(x) for x in args.caps.split(","))
         f64 = gripper in scenes.F64_GRIPPERS and os.environ.get("MGS_PRECISION", "").lower() != "f32"  # precision policy of the product path
         cfg = MgsRolloutCfg(**rollout_cfg(gripper))
-        nobj = min(W["objects"], max(steps, 1))
+        nobj = min(int(os.environ.get("MGS_BENCH_OBJECTS", "0")) or W["objects"], max(steps, 1))
         sets = []
         for k in range(nobj):
             model, info, pose7, joints = make_object_workload(gripper, k, N_CAND)
