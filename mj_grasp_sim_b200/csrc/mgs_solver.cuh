@@ -1013,6 +1013,124 @@ MGS_DEV real noslip_contact_w(Env &e, int c, int i, int p, const real *AC, real 
   return change;
 }
 
+#ifdef MGS_WIDE
+// ENV-PER-CTA variant: the same Gauss-Seidel update of one contact, executed by ONE WARP (shuffle reductions, __syncwarp, no CTA
+// barrier) and restricted to the dofs of the contact's own (at most two) kinematic trees S = [lo1, lo1 + n1) u [lo2, lo2 + n2) - its
+// Jacobian rows and B_c = M^-1 J_c' are zero elsewhere.  Contacts that share no tree commute exactly, so solve_noslip_w runs them
+// concurrently on different warps (level schedule below); this routine therefore touches nothing outside S.
+template <int N>
+MGS_DEV real noslip_contact_warp(Env &e, int c, int i, int p, const real *AC, real *T, const real *Bc, int lo1, int n1, int lo2, int n2) {
+  const int nv = MD.nv, l32 = threadIdx.x & 31, m = n1 + n2;
+  real res[N], Ac[N * N], old[N], bc[N], v[N], delta[N], fr[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) res[j] = 0;
+  #pragma unroll 1
+  for (int u = l32; u < m; u += 32) {
+    const int d = u < n1 ? lo1 + u : lo2 + (u - n1);
+    const real w = EF(qacc_smooth)[d] + EF(wvec)[d];
+#pragma unroll
+    for (int j = 0; j < N; j++) res[j] += EF(J)[(i + 1 + j) * nv + d] * w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int j = 0; j < N; j++) res[j] += __shfl_xor_sync(0xffffffffu, res[j], o);
+  {
+    int q = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      res[j] = res[j] - EF(efc_aref)[i + 1 + j];
+      old[j] = EF(efc_force)[i + 1 + j];
+      fr[j] = LDG(MD.pair_friction + 5 * p + j);
+#pragma unroll
+      for (int k = j; k < N; k++) { Ac[j * N + k] = Ac[k * N + j] = AC[6 * c + q]; q++; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    bc[j] = res[j];
+#pragma unroll
+    for (int k = 0; k < N; k++) bc[j] -= Ac[j * N + k] * old[k];
+  }
+  const real fnorm = EF(efc_force)[i];
+  if (fnorm < MGS_MINVAL) {
+#pragma unroll
+    for (int j = 0; j < N; j++) v[j] = 0;
+  } else qcqp_small<N>(v, Ac, bc, fr, fnorm);
+  real change = 0;
+#pragma unroll
+  for (int j = 0; j < N; j++) delta[j] = v[j] - old[j];
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    change += delta[j] * res[j];
+#pragma unroll
+    for (int k = 0; k < N; k++) change += R_(0.5) * delta[j] * Ac[j * N + k] * delta[k];
+  }
+  if (change > R_(1e-10)) {
+#pragma unroll
+    for (int j = 0; j < N; j++) { v[j] = old[j]; delta[j] = 0; }
+    change = 0;
+  }
+  __syncwarp();  // every lane has read the old forces
+  if (l32 == 0) {
+#pragma unroll
+    for (int j = 0; j < N; j++) EF(efc_force)[i + 1 + j] = v[j];
+  }
+  if (Bc) {
+    #pragma unroll 1
+    for (int u = l32; u < m; u += 32) {
+      const int d = u < n1 ? lo1 + u : lo2 + (u - n1);
+      real t = 0;
+#pragma unroll
+      for (int j = 0; j < N; j++) t += Bc[j * nv + d] * delta[j];
+      EF(wvec)[d] += t;
+    }
+    __syncwarp();
+    return change;
+  }
+  #pragma unroll 1
+  for (int u = l32; u < m; u += 32) {
+    const int d = u < n1 ? lo1 + u : lo2 + (u - n1);
+    real t = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) t += EF(J)[(i + 1 + j) * nv + d] * delta[j];
+    T[d] = t;
+  }
+  __syncwarp();
+  #pragma unroll 1
+  for (int u = l32; u < m; u += 32) {
+    const int d = u < n1 ? lo1 + u : lo2 + (u - n1);
+    int ro, lo, tn;
+    blk_row(d, ro, lo, tn);
+    const real *Mrow = EF(Minv) + ro;
+    real t = 0;
+    MGS_UNROLL_INNER
+    for (int k = lo; k < lo + tn; k++) t += Mrow[k] * T[k];
+    EF(wvec)[d] += t;
+  }
+  __syncwarp();
+  return change;
+}
+// trees of contact c: (first dof, dof count) of the trees of its two bodies (count 0: static body); returns 0 for a contact without dofs
+MGS_DEV int contact_trees(const Env &e, int c, int &lo1, int &n1, int &lo2, int &n2, int &t1, int &t2) {
+  const int p = IARR(EF(con_pair))[c];
+  const int b1 = LDG(MD.cgeom_bodyid + LDG(MD.pair_geom1 + p)), b2 = LDG(MD.cgeom_bodyid + LDG(MD.pair_geom2 + p));
+  t1 = LDG(MD.body_treeid + b1); t2 = LDG(MD.body_treeid + b2);
+  if (t1 < 0) { t1 = t2; t2 = -1; }
+  if (t2 == t1) t2 = -1;
+  lo1 = n1 = lo2 = n2 = 0;
+  if (t1 < 0) return 0;
+  if (t2 >= 0 && t2 < t1) { const int t = t1; t1 = t2; t2 = t; }
+  #pragma unroll 1
+  for (int d = 0; d < MD.nv; d += LDG(MD.dof_treenum + d)) {
+    const int t = LDG(MD.dof_treeid + d);
+    if (t == t1) { lo1 = d; n1 = LDG(MD.dof_treenum + d); }
+    if (t == t2) { lo2 = d; n2 = LDG(MD.dof_treenum + d); }
+  }
+  return 1;
+}
+#endif
+
 // mj_solNoSlip: Gauss-Seidel on the friction rows with the UNREGULARISED A = J M^-1 J'.
 // wvec tracks qacc - qacc_smooth = M^-1 J' f, so no nefc x nefc matrix is formed: a row's residual is
 // J_i (qacc_smooth + w) - aref_i and a force change dF moves w by M^-1 J' dF.  The small diagonal blocks
@@ -1121,6 +1239,63 @@ MGS_DEVN void solve_noslip_w(Env &e) {
     AC[6 * c + q] = acc;
   }
   WSYNC();
+#ifdef MGS_WIDE
+  // LEVEL SCHEDULE of the contact sweep.  Two contacts that share no kinematic tree commute exactly (disjoint rows of w, zero
+  // coupling), so the sequential Gauss-Seidel order only matters along chains of contacts that share a tree: level(c) = 1 + the
+  // largest level of an earlier contact that shares a tree with c.  Contacts of one level run concurrently, one warp each; the levels
+  // run in order.  Same result as the sequential sweep; in the config-5 pile ~40 contacts form ~20 levels.
+  int *lvl_list = IARR(EF(efc_list)), *lvl_start = IARR(EF(nsS));
+  real *chg = EF(efc_list) + LY.ncon_max;  // per-contact cost change of the current sweep (efc_list holds nefc_max >= 3 ncon_max words)
+  // NOT ENABLED by default (-DMGS_NOSLIP_LEVELS turns it on).  Measured on config 5: the noslip stage itself drops from 317 k to 195 k
+  // cycles per step and one step agrees with the sequential sweep to rounding (tools/ab_wide.py: qacc 3e-6 after one step), but the
+  // full-schedule bench got SLOWER (147 k -> 128 k env-steps/s: more Newton iterations downstream) and the 10-step trajectory test
+  // against the oracle went from 2e-5 to 6e-4.  Unexplained within the round's GPU budget, so the sequential sweep stays.
+#ifdef MGS_NOSLIP_LEVELS
+  const int use_levels = MD.ntree <= MGS_SPARSE_H_MAXTREE && ncon <= LANES;
+#else
+  const int use_levels = 0;
+#endif
+  int nlevel = 0;
+  if (use_levels) {
+    int *lvl = IARR(EF(efc_key));
+    #pragma unroll 1
+    PFOR(c, ncon) {  // the trees of every contact, in parallel: t1 | t2 << 8 (255: none), -1: nothing to do for this contact
+      int lo1, n1, lo2, n2, t1, t2, w = -1;
+      const int i = IARR(EF(con_efc))[c];
+      if (i >= 0 && LDG(MD.pair_condim + IARR(EF(con_pair))[c]) >= 3 && contact_trees(e, c, lo1, n1, lo2, n2, t1, t2)) w = t1 | ((t2 >= 0 ? t2 : 255) << 8);
+      lvl[c] = w;
+    }
+    WSYNC();
+    if (threadIdx.x == 0) {  // the recurrence itself is sequential (a few instructions per contact)
+      int last[MGS_SPARSE_H_MAXTREE];
+      for (int t = 0; t < MGS_SPARSE_H_MAXTREE; t++) last[t] = 0;
+      int mx = 0;
+      for (int c = 0; c < ncon; c++) {
+        const int w = lvl[c];
+        int L = 0;
+        if (w >= 0) {
+          const int t1 = w & 255, t2 = w >> 8;
+          L = last[t1];
+          if (t2 != 255 && last[t2] > L) L = last[t2];
+          L += 1;
+          last[t1] = L;
+          if (t2 != 255) last[t2] = L;
+          if (L > mx) mx = L;
+        }
+        lvl[c] = L;  // 0: nothing to do for this contact
+      }
+      // counting sort by level (contact order kept inside a level)
+      for (int L = 0; L <= mx + 1; L++) lvl_start[L] = 0;
+      for (int c = 0; c < ncon; c++) if (lvl[c] > 0) lvl_start[lvl[c] + 1]++;
+      for (int L = 1; L <= mx + 1; L++) lvl_start[L] += lvl_start[L - 1];
+      for (int c = 0; c < ncon; c++) if (lvl[c] > 0) { lvl_list[lvl_start[lvl[c]]] = c; lvl_start[lvl[c]]++; }
+      for (int L = mx + 1; L >= 1; L--) lvl_start[L] = lvl_start[L - 1];  // undo the running pointers: lvl_start[L] = first slot of level L
+      lvl_start[0] = mx;
+    }
+    WSYNC();
+    nlevel = lvl_start[0];
+  }
+#endif
   #pragma unroll 1
   for (int iter = 0; iter < MD.noslip_iterations; iter++) {
     real improvement = 0;
@@ -1156,6 +1331,34 @@ MGS_DEVN void solve_noslip_w(Env &e) {
       WSYNC();
     }
     // contact friction dims
+#ifdef MGS_WIDE
+    if (use_levels) {
+      #pragma unroll 1
+      PFOR(c, ncon) chg[c] = 0;
+      WSYNC();
+      #pragma unroll 1
+      for (int L = 1; L <= nlevel; L++) {
+        const int q0 = L == 1 ? 0 : lvl_start[L], q1 = lvl_start[L + 1];
+        #pragma unroll 1
+#ifdef MGS_NOSLIP_LEVELS_ONE_WARP  // (debug: the level order, but one warp does every contact)
+        for (int q = q0; q < q1 && threadIdx.x < 32; q++) {
+#else
+        for (int q = q0 + (int)(threadIdx.x >> 5); q < q1; q += MGS_NWARP) {
+#endif
+          const int c = lvl_list[q], i = IARR(EF(con_efc))[c], p = IARR(EF(con_pair))[c], dim = LDG(MD.pair_condim + p);
+          int lo1, n1, lo2, n2, t1, t2;
+          contact_trees(e, c, lo1, n1, lo2, n2, t1, t2);
+          const real *Bc = (c < ncov) ? B + c * 3 * nv : (const real *)0;
+          const real ch = (dim == 3) ? noslip_contact_warp<2>(e, c, i, p, AC, T, Bc, lo1, n1, lo2, n2)
+                                     : noslip_contact_warp<3>(e, c, i, p, AC, T, Bc, lo1, n1, lo2, n2);
+          if ((threadIdx.x & 31) == 0) chg[c] = ch;
+        }
+        WSYNC();
+      }
+      #pragma unroll 1
+      for (int c = 0; c < ncon; c++) improvement -= chg[c];  // summed in contact order, like the sequential sweep
+    } else
+#endif
     #pragma unroll 1
     for (int c = 0; c < EH.ncon; c++) {
       const int i = IARR(EF(con_efc))[c];
