@@ -345,6 +345,20 @@ MGS_DEVN int best_face_w(int hull, real nx, real ny, real nz, real *align) {
   *align = bd;
   return best;
 }
+// a cylinder has two faces, its caps (0: +z, 1: -z): answered by the lane itself, no hull scan
+MGS_DEV void cap_face(const GeomRef &g, const real *n, int *face, real *align) {
+  const real nz = g.R[2] * n[0] + g.R[5] * n[1] + g.R[8] * n[2];
+  *face = nz >= 0 ? 0 : 1;
+  *align = fabs(nz);
+}
+// Does geom g offer a flat face to a contact with normal n?  Polytopes always, a cylinder when n is along its axis (a cap).
+MGS_DEV int has_face(const GeomRef &g, const real *n) {
+  if (g.type == GEOM_BOX || g.type == GEOM_MESH) return 1;
+#ifndef MGS_NO_CYLINDER_CAPS
+  if (g.type == GEOM_CYLINDER) return fabs(g.R[2] * n[0] + g.R[5] * n[1] + g.R[8] * n[2]) >= MGS_FACE_ALIGN_MIN;
+#endif
+  return 0;
+}
 // best faces for every lane with `want` set (its geom `g`, world direction `n`)
 #ifdef MGS_WIDE
 // env-per-CTA variant: the requests are compacted into a list and every WARP serves requests q = warp, warp + 8, ... with a
@@ -352,6 +366,7 @@ MGS_DEVN int best_face_w(int hull, real nx, real ny, real nz, real *align) {
 // arg-max was ~12 barriers per requester, four calls per step, ~50 requesters each on the config-5 scene: most of its collision time.)
 MGS_DEV void best_face_lanes(const Env &e, int want, const GeomRef &g, const real *n, int *face, real *align) {
   int nreq;
+  if (want && g.type == GEOM_CYLINDER) { cap_face(g, n, face, align); want = 0; }
   const int rank = wrank(want, &nreq);
   if (nreq == 0) return;
   real *rq = EF(req_off);
@@ -391,6 +406,7 @@ MGS_DEV void best_face_lanes(const Env &e, int want, const GeomRef &g, const rea
 MGS_DEV void best_face_lanes(const Env &e, int want, const GeomRef &g, const real *n, int *face, real *align) {
   (void)e;
   real nl[3] = {0, 0, 0};
+  if (want && g.type == GEOM_CYLINDER) { cap_face(g, n, face, align); want = 0; }
   if (want) mulmatTvec3(nl, g.R, n);
   int pending = want;
   #pragma unroll 1
@@ -404,6 +420,24 @@ MGS_DEV void best_face_lanes(const Env &e, int want, const GeomRef &g, const rea
 }
 #endif
 MGS_DEVN int face_polygon(const GeomRef &g, int f, real (*poly)[3], real *nw) {
+  if (g.type == GEOM_CYLINDER) {
+    // the cap enters the clipping as the octagon inscribed in its rim, counter-clockwise seen from outside like the hull faces
+    const real rc = LDG(MD.cgeom_size + 3 * g.cg), z = f == 0 ? LDG(MD.cgeom_size + 3 * g.cg + 1) : -LDG(MD.cgeom_size + 3 * g.cg + 1);
+    const real h = R_(0.70710678118654752);
+    #pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+      const int k = f == 0 ? i : 7 - i;
+      // cos, sin of k * 45 deg
+      const real c = (k == 0) ? R_(1.0) : (k == 4) ? R_(-1.0) : (k == 2 || k == 6) ? R_(0.0) : (k == 1 || k == 7) ? h : -h;
+      const real sn = (k == 2) ? R_(1.0) : (k == 6) ? R_(-1.0) : (k == 0 || k == 4) ? R_(0.0) : (k == 1 || k == 3) ? h : -h;
+      const real v[3] = {rc * c, rc * sn, z};
+      mulmatvec3(poly[i], g.R, v);
+      add3(poly[i], poly[i], g.p);
+    }
+    const real s = f == 0 ? R_(1.0) : R_(-1.0);
+    nw[0] = g.R[2] * s; nw[1] = g.R[5] * s; nw[2] = g.R[8] * s;
+    return 8;
+  }
   int gf = LDG(MD.hull_faceadr + g.hull) + f;
   int n = LDG(MD.hull_facevertnum + gf), fva = LDG(MD.hull_facevertadr + gf), va = LDG(MD.hull_vertadr + g.hull);
   #pragma unroll 1
@@ -419,12 +453,233 @@ MGS_DEVN int face_polygon(const GeomRef &g, int f, real (*poly)[3], real *nw) {
   return n;
 }
 
-struct PairContacts { int n; real normal[3], pos[4][3], dist[4]; };
+struct PairContacts { int n, own2; real normal[3], pos[4][3], dist[4], normal2[3]; };  // own2: point 1 carries its own normal (normal2)
+
+#ifndef MGS_NO_ANALYTIC_PRIMS
+// ---- closed-form primitive pairs, one pair per lane (no collectives inside).  The pairs MuJoCo's collision table sends to
+// engine_collision_primitive.c / engine_collision_box.c: sphere-sphere, sphere-capsule, sphere-cylinder, sphere-box, capsule-capsule,
+// capsule-box; everything else convex stays on the MPR path.  Every case ends in the sphere-sphere primitive at the closest feature.
+// Why not MPR for these as well (round 1 did): MPR reports the depth along the surface normal where the centre-to-centre ray leaves the
+// Minkowski difference - off a capsule's end cap that is 15-20 % too deep with the normal tens of degrees off
+// (tests/test_primitive_colliders.py) - and its portal resolution on a curved surface (chord sqrt(8 r tol) ~ 0.4 mm) is the size of
+// the penetrations themselves.  Mirrors oracle/mgs_oracle.c prim_pair (written separately; same case analysis).
+struct PrimHit { real pos[3], n[3], dist; };
+
+MGS_DEVN int prim_sphere_sphere(const real *p1, real r1, const real *p2, real r2, real margin, PrimHit &h) {
+  real dif[3];
+  sub3(dif, p2, p1);
+  const real cd = sqrt(dot3(dif, dif));
+  if (cd > margin + r1 + r2) return 0;
+  h.dist = cd - r1 - r2;
+  if (cd < MGS_MINVAL) { h.n[0] = 1; h.n[1] = 0; h.n[2] = 0; } else scl3(h.n, dif, R_(1.0) / cd);
+  copy3(h.pos, p1);
+  addscl3(h.pos, h.n, r1 + R_(0.5) * h.dist);
+  return 1;
+}
+MGS_DEV real clampr(real x, real lo, real hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// sphere (centre ps, radius rs) against the box with pose (Rb, pb) and half sizes sz; normal from the sphere to the box
+MGS_DEVN int prim_sphere_box(const real *ps, real rs, const real *Rb, const real *pb, const real *sz, real margin, PrimHit &h) {
+  real t[3], c[3], d[3], nl[3];
+  sub3(t, ps, pb);
+  mulmatTvec3(c, Rb, t);
+  for (int k = 0; k < 3; k++) d[k] = clampr(c[k], -sz[k], sz[k]) - c[k];
+  const real dn = sqrt(dot3(d, d));
+  if (dn > MGS_MINVAL) {
+    if (dn > rs + margin) return 0;
+    scl3(nl, d, R_(1.0) / dn);
+    h.dist = dn - rs;
+  } else {  // centre inside the box: out through the nearest face
+    int k = 0;
+    real fd = sz[0] - fabs(c[0]);
+    if (sz[1] - fabs(c[1]) < fd) { fd = sz[1] - fabs(c[1]); k = 1; }
+    if (sz[2] - fabs(c[2]) < fd) { fd = sz[2] - fabs(c[2]); k = 2; }
+    const real sg = (k == 0 ? c[0] : (k == 1 ? c[1] : c[2])) >= 0 ? R_(-1.0) : R_(1.0);
+    nl[0] = k == 0 ? sg : 0; nl[1] = k == 1 ? sg : 0; nl[2] = k == 2 ? sg : 0;
+    h.dist = -(rs + fd);
+  }
+  addscl3(c, nl, rs + R_(0.5) * h.dist);
+  mulmatvec3(h.pos, Rb, c);
+  add3(h.pos, h.pos, pb);
+  mulmatvec3(h.n, Rb, nl);
+  return 1;
+}
+
+// d/dt of the squared distance between the box and the point c + t a (box frame): piecewise linear in t
+MGS_DEV real seg_box_slope(const real *c, const real *a, const real *sz, real t) {
+  real g = 0;
+  for (int k = 0; k < 3; k++) {
+    const real p = c[k] + t * a[k], ex = fabs(p) - sz[k];
+    if (ex > 0) g += 2 * (p > 0 ? ex : -ex) * a[k];
+  }
+  return g;
+}
+
+MGS_DEV int is_prim_pair(int t1, int t2) {
+  const int ta = t1 < t2 ? t1 : t2, tb = t1 < t2 ? t2 : t1;
+  if (ta == GEOM_SPHERE) return tb == GEOM_SPHERE || tb == GEOM_CAPSULE || tb == GEOM_CYLINDER || tb == GEOM_BOX;
+  if (ta == GEOM_CAPSULE) return tb == GEOM_CAPSULE || tb == GEOM_BOX;
+  return 0;
+}
+
+MGS_DEV void prim_emit(PairContacts &out, const PrimHit &h, real sign) {
+  if (out.n == 0) {
+    scl3(out.normal, h.n, sign);
+    copy3(out.pos[0], h.pos);
+    out.dist[0] = h.dist;
+    out.n = 1;
+  } else if (out.n == 1) {
+    scl3(out.normal2, h.n, sign);
+    copy3(out.pos[1], h.pos);
+    out.dist[1] = h.dist;
+    out.n = 2;
+    out.own2 = 1;
+  }
+}
+
+MGS_DEVN void prim_pair(const GeomRef &g1, const GeomRef &g2, real margin, PairContacts &out) {
+  // written for type(a) <= type(b); the pair's normal points from g1 to g2
+  const int swap = g1.type > g2.type;
+  const GeomRef &a = swap ? g2 : g1, &b = swap ? g1 : g2;
+  const real sign = swap ? R_(-1.0) : R_(1.0);
+  real sa[3], sb[3];
+  ld3(sa, MD.cgeom_size + 3 * a.cg);
+  ld3(sb, MD.cgeom_size + 3 * b.cg);
+  PrimHit h;
+  if (a.type == GEOM_SPHERE) {
+    if (b.type == GEOM_SPHERE) {
+      if (prim_sphere_sphere(a.p, sa[0], b.p, sb[0], margin, h)) prim_emit(out, h, sign);
+    } else if (b.type == GEOM_BOX) {
+      if (prim_sphere_box(a.p, sa[0], b.R, b.p, sb, margin, h)) prim_emit(out, h, sign);
+    } else {  // capsule or cylinder: position along the axis, distance from it
+      const real ax[3] = {b.R[2], b.R[5], b.R[8]};
+      real v[3], q[3];
+      sub3(v, a.p, b.p);
+      const real x = dot3(v, ax);
+      if (b.type == GEOM_CAPSULE) {
+        copy3(q, b.p);
+        addscl3(q, ax, clampr(x, -sb[1], sb[1]));
+        if (prim_sphere_sphere(a.p, sa[0], q, sb[0], margin, h)) prim_emit(out, h, sign);
+      } else {
+        const real Rc = sb[0], hc = sb[1];
+        addscl3(v, ax, -x);  // v: radial part
+        const real rho = sqrt(dot3(v, v));
+        int side = fabs(x) < hc, cap = rho < Rc;
+        if (side && cap) { if (hc - fabs(x) < Rc - rho) side = 0; else cap = 0; }
+        if (side) {
+          copy3(q, b.p);
+          addscl3(q, ax, x);
+          if (prim_sphere_sphere(a.p, sa[0], q, Rc, margin, h)) prim_emit(out, h, sign);
+        } else if (cap) {
+          h.dist = fabs(x) - hc - sa[0];
+          if (h.dist <= margin) {
+            scl3(h.n, ax, x >= 0 ? R_(-1.0) : R_(1.0));
+            copy3(h.pos, a.p);
+            addscl3(h.pos, h.n, sa[0] + R_(0.5) * h.dist);
+            prim_emit(out, h, sign);
+          }
+        } else {
+          copy3(q, b.p);
+          addscl3(q, ax, x >= 0 ? hc : -hc);
+          if (rho > MGS_MINVAL) addscl3(q, v, Rc / rho);
+          if (prim_sphere_sphere(a.p, sa[0], q, 0, margin, h)) prim_emit(out, h, sign);
+        }
+      }
+    }
+    return;
+  }
+  // a is a capsule
+  const real a1[3] = {a.R[2], a.R[5], a.R[8]};
+  if (b.type == GEOM_CAPSULE) {
+    const real a2[3] = {b.R[2], b.R[5], b.R[8]};
+    real dif[3], q1[3], q2[3];
+    sub3(dif, a.p, b.p);
+    const real l1 = sa[1], l2 = sb[1], mb = -dot3(a1, a2), u = -dot3(a1, dif), v = dot3(a2, dif), det = 1 - mb * mb;
+    if (fabs(det) >= MGS_MINVAL) {
+      real x1 = (u - mb * v) / det, x2 = (v - mb * u) / det;
+      if (x1 > l1) { x1 = l1; x2 = v - mb * x1; } else if (x1 < -l1) { x1 = -l1; x2 = v - mb * x1; }
+      if (x2 > l2) { x2 = l2; x1 = clampr(u - mb * x2, -l1, l1); } else if (x2 < -l2) { x2 = -l2; x1 = clampr(u - mb * x2, -l1, l1); }
+      copy3(q1, a.p); addscl3(q1, a1, x1);
+      copy3(q2, b.p); addscl3(q2, a2, x2);
+      if (prim_sphere_sphere(q1, sa[0], q2, sb[0], margin, h)) prim_emit(out, h, sign);
+    } else {  // parallel axes: ends of capsule 1 against segment 2, then ends of capsule 2 against segment 1; two points at most
+      #pragma unroll 1
+      for (int k = 0; k < 4 && out.n < 2; k++) {
+        real x1, x2;
+        if (k < 2) { x1 = k ? -l1 : l1; x2 = clampr(v - mb * x1, -l2, l2); }
+        else {
+          x2 = (k & 1) ? -l2 : l2; x1 = clampr(u - mb * x2, -l1, l1);
+          if (fabs(fabs(x1) - l1) < MGS_MINVAL) continue;
+        }
+        copy3(q1, a.p); addscl3(q1, a1, x1);
+        copy3(q2, b.p); addscl3(q2, a2, x2);
+        if (prim_sphere_sphere(q1, sa[0], q2, sb[0], margin, h)) prim_emit(out, h, sign);
+      }
+    }
+    return;
+  }
+  // capsule-box: closest point of the axis segment c + t a, t in [-1, 1] (box frame).  f(t) = squared distance to the box is convex,
+  // f' piecewise linear with kinks where a coordinate crosses a face plane: bracket the sign change of f' between two kinks (or
+  // segment ends) and interpolate linearly - exact, no iteration.
+  real t3[3], c[3], av[3];
+  sub3(t3, a.p, b.p);
+  mulmatTvec3(c, b.R, t3);
+  mulmatTvec3(av, b.R, a1);
+  scl3(av, av, sa[1]);
+  real tl = -2, tr = 2, gl = 0, gr = 0;
+  #pragma unroll 1
+  for (int i = 0; i < 8; i++) {
+    real t;
+    if (i < 2) t = i ? R_(1.0) : R_(-1.0);
+    else {
+      const int k = (i - 2) >> 1;
+      const real ak = k == 0 ? av[0] : (k == 1 ? av[1] : av[2]), ck = k == 0 ? c[0] : (k == 1 ? c[1] : c[2]), sk = k == 0 ? sb[0] : (k == 1 ? sb[1] : sb[2]);
+      if (!(fabs(ak) > MGS_MINVAL)) continue;
+      t = (((i & 1) ? sk : -sk) - ck) / ak;
+      if (!(t > -1 && t < 1)) continue;
+    }
+    const real g = seg_box_slope(c, av, sb, t);
+    if (g <= 0 && t > tl) { tl = t; gl = g; }
+    if (g >= 0 && t < tr) { tr = t; gr = g; }
+  }
+  real ts;
+  if (tl < R_(-1.5)) ts = -1; else if (tr > R_(1.5)) ts = 1;
+  else if (gr - gl > MGS_MINVAL) ts = tl + (tr - tl) * (-gl) / (gr - gl);
+  else ts = R_(0.5) * (tl + tr);
+  // candidates: the two ends, then the closest point.  First contact: the deepest (earlier candidate on ties); second: the deepest
+  // other candidate in contact that is a different point of the segment.
+  PrimHit hc[3];
+  int hit[3];
+  #pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const real ti = i == 0 ? R_(-1.0) : (i == 1 ? R_(1.0) : ts);
+    real q[3];
+    copy3(q, a.p);
+    addscl3(q, a1, sa[1] * ti);
+    hit[i] = prim_sphere_box(q, sa[0], b.R, b.p, sb, margin, hc[i]);
+  }
+  int i1 = -1, i2 = -1;
+  #pragma unroll
+  for (int i = 0; i < 3; i++) if (hit[i] && (i1 < 0 || hc[i].dist < (i1 == 0 ? hc[0].dist : hc[1].dist))) i1 = i;
+  if (i1 < 0) return;
+  const real t1 = i1 == 0 ? R_(-1.0) : (i1 == 1 ? R_(1.0) : ts);
+  #pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const real ti = i == 0 ? R_(-1.0) : (i == 1 ? R_(1.0) : ts);
+    if (i != i1 && hit[i] && fabs(ti - t1) > R_(0.05) && (i2 < 0 || hc[i].dist < (i2 == 0 ? hc[0].dist : hc[1].dist))) i2 = i;
+  }
+  #pragma unroll
+  for (int i = 0; i < 3; i++) if (i == i1) prim_emit(out, hc[i], sign);
+  #pragma unroll
+  for (int i = 0; i < 3; i++) if (i == i2) prim_emit(out, hc[i], sign);
+}
+#endif
 
 // narrowphase for candidate pair `pair`, which already passed the bounding-sphere test (pair < 0: lane idle); fills up
 // to 4 contacts.  Called by all lanes of the warp together: the MPR stage inside is warp-converged.
 MGS_DEVN void collide_pair(Env &e, int pair, PairContacts &out) {
   out.n = 0;
+  out.own2 = 0;
   const int active = pair >= 0;
   int c1 = 0, c2 = 0;
   if (active) { c1 = LDG(MD.pair_geom1 + pair); c2 = LDG(MD.pair_geom2 + pair); }
@@ -447,12 +702,20 @@ MGS_DEVN void collide_pair(Env &e, int pair, PairContacts &out) {
   // two 16-bit vertex ids, 0 after reset); poses change by micrometres per step, so the climb is 0-1 moves
   if (cache && active) { g1.cur = cache[3] & 0xffff; g2.cur = (cache[3] >> 16) & 0xffff; }
   MGS_CLK(1);
-  int hit = mpr_penetration(g1, g2, active, cache, &depth, n, pos);
+  int prim = 0;
+#ifndef MGS_NO_ANALYTIC_PRIMS
+  // sphere / capsule pairs with a closed form leave the MPR path here (a warp vote keeps the code out of the way of models without
+  // such geoms: the three parallel-jaw grippers and LEAP never enter)
+  prim = active && is_prim_pair(g1.type, g2.type);
+  if (wany(prim)) { if (prim) prim_pair(g1, g2, LDG(MD.pair_margin + pair), out); }
+#endif
+  int hit = mpr_penetration(g1, g2, active && !prim, cache, &depth, n, pos);
   MGS_CLK(9);
   hit = hit && (depth > 0);
   // polytope pairs: multi-point manifold from the two most-aligned faces.  The face searches are warp-cooperative,
   // so no lane leaves before them (the clipping itself stays per lane).
-  const int poly = hit && (g1.type == GEOM_BOX || g1.type == GEOM_MESH) && (g2.type == GEOM_BOX || g2.type == GEOM_MESH);
+  // (a cylinder joins through its caps; cap against cap stays a single point)
+  const int poly = hit && has_face(g1, n) && has_face(g2, n) && (g1.type != GEOM_CYLINDER || g2.type != GEOM_CYLINDER);
   real a1 = 0, a2 = 0, nn[3] = {-n[0], -n[1], -n[2]};
   int f1 = 0, f2 = 0;
   best_face_lanes(e, poly, g1, n, &f1, &a1);
@@ -589,7 +852,7 @@ MGS_DEV void emit_contacts(Env &e, const PairContacts &pc, int p, int &base) {
     int c = base + off + k;
     if (c >= LY.ncon_max) break;
     copy3(EF(con_pos) + 3 * c, pc.pos[k]);
-    copy3(EF(con_normal) + 3 * c, pc.normal);
+    copy3(EF(con_normal) + 3 * c, (k == 1 && pc.own2) ? pc.normal2 : pc.normal);
     EF(con_dist)[c] = pc.dist[k];
     IARR(EF(con_pair))[c] = p;
   }

@@ -16,7 +16,8 @@
  * invariants (tests/test_oracle_invariants.py) and by the one MuJoCo-recorded vector the reference holds:
  * the Robotiq closed-state mjSTATE_INTEGRATION record of mgs/cli/config/gripper/robotiq_2f_85.yaml:11
  * (tests/golden/robotiq_2f85_state_close.json, tests/test_golden_robotiq.py).  Known deliberate difference: convex narrowphase builds
- * its multi-point manifold by MPR + face clipping instead of libccd MPR + multiccd perturbation.
+ * its multi-point manifold by MPR + face clipping instead of libccd MPR + multiccd perturbation / the analytic box-box routine; the
+ * sphere / capsule pairs of MuJoCo's primitive table have closed forms here as well (prim_pair, tests/test_primitive_colliders.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (libmgs_b200.so) never links or calls it.
@@ -67,6 +68,7 @@ typedef struct OrcSim {
   int efc_type[NEFC_MAX], efc_id[NEFC_MAX], efc_state[NEFC_MAX];
   /* diagnostics */
   int solver_niter, bad, nstep_done, ncon_overflow, ncon_peak, nefc_peak;
+  int no_analytic; /* tests only: 1 = send primitive pairs through MPR as well (orc_set_analytic) */
   double qvel_clip; /* > 0: clamp qvel to +-qvel_clip before every step (ClutterTableEnv.gen_clutter, clutter_table.py:215-221) */
   /* scratch */
   double *w1, *w2, *w3, *w4, *w5, *w6, *jtmp;
@@ -560,8 +562,9 @@ static void jac_point(const OrcSim *s, int body, const double *point, double *ja
  * multiccd perturbation; box-box has an analytic routine.  This restatement treats boxes and
  * hulls uniformly as convex polytopes: MPR supplies the penetration direction/depth, then the
  * most-aligned faces of the two polytopes are clipped against each other (Sutherland-Hodgman)
- * to produce up to 4 contact points on the reference face.  Round shapes get the single MPR
- * point. */
+ * to produce up to 4 contact points on the reference face (a cylinder offers its caps as faces).  Pairs of
+ * MuJoCo's primitive table (sphere / capsule against sphere / capsule / box, sphere-cylinder) have closed
+ * forms further down (prim_pair); the remaining round pairs get the single MPR point. */
 typedef struct { double v[3], v1[3], v2[3]; } SupPt;
 
 static int is_polytope(int type) { return type == GEOM_BOX || type == GEOM_MESH; }
@@ -742,6 +745,10 @@ static int best_face(const OrcSim *s, int g, const double *n, double *align) {
   int h = m->cgeom_hullid[g], best = 0;
   double nl[3], bd = -1e300;
   mulmatTvec3(nl, s->gxmat + 9 * g, n);
+  if (m->cgeom_type[g] == GEOM_CYLINDER) { /* two faces: the caps (0: +z, 1: -z) */
+    *align = fabs(nl[2]);
+    return nl[2] >= 0 ? 0 : 1;
+  }
   const double *FN = m->hull_facenormal + 3 * m->hull_faceadr[h];
   for (int f = 0; f < m->hull_facenum[h]; f++) {
     double t = dot3(FN + 3 * f, nl);
@@ -750,8 +757,23 @@ static int best_face(const OrcSim *s, int g, const double *n, double *align) {
   *align = bd;
   return best;
 }
+/* cos, sin of k * 45 deg: a cylinder cap enters the clipping as the octagon inscribed in its rim */
+static const double OCT[8][2] = {{1, 0}, {0.70710678118654752, 0.70710678118654752}, {0, 1}, {-0.70710678118654752, 0.70710678118654752},
+                                 {-1, 0}, {-0.70710678118654752, -0.70710678118654752}, {0, -1}, {0.70710678118654752, -0.70710678118654752}};
 static int face_polygon(const OrcSim *s, int g, int f, double poly[][3], double *nw) {
   const MgsModelDesc *m = &s->m;
+  if (m->cgeom_type[g] == GEOM_CYLINDER) {
+    const double *sz = m->cgeom_size + 3 * g, z = f == 0 ? sz[1] : -sz[1];
+    for (int i = 0; i < 8; i++) { /* counter-clockwise seen from outside, like the hull faces */
+      const double *cs = OCT[f == 0 ? i : 7 - i];
+      double v[3] = {sz[0] * cs[0], sz[0] * cs[1], z};
+      mulmatvec3(poly[i], s->gxmat + 9 * g, v);
+      add3(poly[i], poly[i], s->gxpos + 3 * g);
+    }
+    double nl[3] = {0, 0, f == 0 ? 1.0 : -1.0};
+    mulmatvec3(nw, s->gxmat + 9 * g, nl);
+    return 8;
+  }
   int h = m->cgeom_hullid[g], gf = m->hull_faceadr[h] + f;
   int n = m->hull_facevertnum[gf];
   const double *V = m->hull_vert + 3 * m->hull_vertadr[h];
@@ -788,7 +810,231 @@ static void add_contact(OrcSim *s, int pair, const double *pos, const double *no
   c->mu = c->friction[0]; c->efc = -1;
 }
 
+/* ---- analytic primitive pairs.  MuJoCo's collision table (engine_collision_driver.c, mjCOLLISIONFUNC) sends sphere-sphere,
+ * sphere-capsule, sphere-cylinder, sphere-box, capsule-capsule and capsule-box to closed-form routines of
+ * engine_collision_primitive.c / engine_collision_box.c and everything else that is convex to the ccd path.  The routines below
+ * restate the published closed forms: every case reduces to the sphere-sphere (or plane-sphere) primitive at the closest feature;
+ * capsule-capsule gives two points only for parallel axes, capsule-box up to two (the deepest point of the axis segment plus the
+ * segment end that also touches: the reference implementation's choice of the second point is not reproducible without its source,
+ * the COUNT is).  The Allegro (4 capsules) and Shadow (3 spheres, 10 capsules, 7 cylinders) hands are the users, mostly in
+ * self-collision and against the ground / table box; their contacts with mesh objects stay on the convex path like in MuJoCo.
+ * Normals point from the pair's first geom to its second; dist < 0 is penetration; pos is the midpoint of the overlap. */
+typedef struct { int n; double pos[2][3], normal[2][3], dist[2]; } PrimCon;
+
+static int raw_sphere_sphere(const double *p1, double r1, const double *p2, double r2, double margin, double *pos, double *normal, double *dist) {
+  double dif[3];
+  sub3(dif, p2, p1);
+  double cd = norm3(dif);
+  if (cd > margin + r1 + r2) return 0;
+  *dist = cd - r1 - r2;
+  if (cd < MINVAL) { normal[0] = 1; normal[1] = 0; normal[2] = 0; } else scl3(normal, dif, 1.0 / cd);
+  copy3(pos, p1);
+  addscl3(pos, normal, r1 + 0.5 * *dist);
+  return 1;
+}
+static void geom_axis(const OrcSim *s, int g, double *axis) { const double *R = s->gxmat + 9 * g; axis[0] = R[2]; axis[1] = R[5]; axis[2] = R[8]; }
+static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+/* sphere centre ps (world), radius rs, against box geom gb; normal from the sphere to the box */
+static int raw_sphere_box(const OrcSim *s, const double *ps, double rs, int gb, double margin, double *pos, double *normal, double *dist) {
+  const double *R = s->gxmat + 9 * gb, *sz = s->m.cgeom_size + 3 * gb;
+  double t[3], c[3], cl[3], d[3], nl[3];
+  sub3(t, ps, s->gxpos + 3 * gb);
+  mulmatTvec3(c, R, t);
+  for (int k = 0; k < 3; k++) cl[k] = clampd(c[k], -sz[k], sz[k]);
+  sub3(d, cl, c);
+  double dn = norm3(d);
+  if (dn > MINVAL) { /* centre outside the box: closest point of the box */
+    if (dn > rs + margin) return 0;
+    scl3(nl, d, 1.0 / dn);
+    *dist = dn - rs;
+  } else { /* centre inside: leave through the nearest face */
+    int k = 0;
+    double fd = sz[0] - fabs(c[0]);
+    for (int i = 1; i < 3; i++) if (sz[i] - fabs(c[i]) < fd) { fd = sz[i] - fabs(c[i]); k = i; }
+    nl[0] = nl[1] = nl[2] = 0;
+    nl[k] = c[k] >= 0 ? -1.0 : 1.0;
+    *dist = -(rs + fd);
+  }
+  double pl[3];
+  copy3(pl, c);
+  addscl3(pl, nl, rs + 0.5 * *dist);
+  mulmatvec3(pos, R, pl);
+  add3(pos, pos, s->gxpos + 3 * gb);
+  mulmatvec3(normal, R, nl);
+  return 1;
+}
+
+/* derivative of the squared distance between the box and the point c + t * a (box frame) */
+static double seg_box_dfdt(const double *c, const double *a, const double *sz, double t) {
+  double g = 0;
+  for (int k = 0; k < 3; k++) {
+    double p = c[k] + t * a[k], ex = fabs(p) - sz[k];
+    if (ex > 0) g += 2 * (p > 0 ? ex : -ex) * a[k];
+  }
+  return g;
+}
+
+static void prim_push(PrimCon *o, const double *pos, const double *normal, double dist, double sign) {
+  if (o->n >= 2) return;
+  copy3(o->pos[o->n], pos);
+  scl3(o->normal[o->n], normal, sign);
+  o->dist[o->n] = dist;
+  o->n++;
+}
+
+/* returns 1 when the pair's types have a closed-form routine (contacts, possibly none, in *o) */
+static int prim_pair(const OrcSim *s, int pair, PrimCon *o) {
+  const MgsModelDesc *m = &s->m;
+  int ga = m->pair_geom1[pair], gb = m->pair_geom2[pair];
+  int ta = m->cgeom_type[ga], tb = m->cgeom_type[gb];
+  double sign = 1.0; /* the routines are written for type(ga) <= type(gb) */
+  if (ta > tb) { int t = ga; ga = gb; gb = t; t = ta; ta = tb; tb = t; sign = -1.0; }
+  const double margin = m->pair_margin[pair];
+  const double *pa = s->gxpos + 3 * ga, *pb = s->gxpos + 3 * gb, *sa = m->cgeom_size + 3 * ga, *sb = m->cgeom_size + 3 * gb;
+  double pos[3], nrm[3], dist;
+  o->n = 0;
+  if (ta == GEOM_SPHERE && tb == GEOM_SPHERE) {
+    if (raw_sphere_sphere(pa, sa[0], pb, sb[0], margin, pos, nrm, &dist)) prim_push(o, pos, nrm, dist, sign);
+    return 1;
+  }
+  if (ta == GEOM_SPHERE && tb == GEOM_CAPSULE) { /* closest point of the capsule's axis segment */
+    double ax[3], t[3], q[3];
+    geom_axis(s, gb, ax);
+    sub3(t, pa, pb);
+    double x = clampd(dot3(ax, t), -sb[1], sb[1]);
+    copy3(q, pb);
+    addscl3(q, ax, x);
+    if (raw_sphere_sphere(pa, sa[0], q, sb[0], margin, pos, nrm, &dist)) prim_push(o, pos, nrm, dist, sign);
+    return 1;
+  }
+  if (ta == GEOM_SPHERE && tb == GEOM_CYLINDER) { /* side, cap or rim of the cylinder */
+    double ax[3], v[3], pr[3], q[3];
+    geom_axis(s, gb, ax);
+    sub3(v, pa, pb);
+    double x = dot3(v, ax), R = sb[0], h = sb[1];
+    copy3(pr, v);
+    addscl3(pr, ax, -x);
+    double rho = norm3(pr);
+    int side = fabs(x) < h, cap = rho < R;
+    if (side && cap) { if (h - fabs(x) < R - rho) side = 0; else cap = 0; } /* centre inside: nearest surface */
+    if (side) {
+      copy3(q, pb);
+      addscl3(q, ax, x);
+      if (raw_sphere_sphere(pa, sa[0], q, R, margin, pos, nrm, &dist)) prim_push(o, pos, nrm, dist, sign);
+    } else if (cap) { /* plane of the nearer cap; normal from the sphere into the cylinder */
+      double sg = x >= 0 ? 1.0 : -1.0;
+      dist = fabs(x) - h - sa[0];
+      if (dist <= margin) {
+        scl3(nrm, ax, -sg);
+        copy3(pos, pa);
+        addscl3(pos, nrm, sa[0] + 0.5 * dist);
+        prim_push(o, pos, nrm, dist, sign);
+      }
+    } else { /* rim circle */
+      copy3(q, pb);
+      addscl3(q, ax, x >= 0 ? h : -h);
+      if (rho > MINVAL) addscl3(q, pr, R / rho);
+      if (raw_sphere_sphere(pa, sa[0], q, 0.0, margin, pos, nrm, &dist)) prim_push(o, pos, nrm, dist, sign);
+    }
+    return 1;
+  }
+  if (ta == GEOM_SPHERE && tb == GEOM_BOX) {
+    if (raw_sphere_box(s, pa, sa[0], gb, margin, pos, nrm, &dist)) prim_push(o, pos, nrm, dist, sign);
+    return 1;
+  }
+  if (ta == GEOM_CAPSULE && tb == GEOM_CAPSULE) {
+    double a1[3], a2[3], dif[3], q1[3], q2[3];
+    geom_axis(s, ga, a1);
+    geom_axis(s, gb, a2);
+    sub3(dif, pa, pb);
+    const double l1 = sa[1], l2 = sb[1];
+    double mb = -dot3(a1, a2), u = -dot3(a1, dif), v = dot3(a2, dif), det = 1.0 - mb * mb;
+    if (fabs(det) >= MINVAL) { /* general position: closest points of the two segments */
+      double x1 = (u - mb * v) / det, x2 = (v - mb * u) / det;
+      if (x1 > l1) { x1 = l1; x2 = v - mb * x1; } else if (x1 < -l1) { x1 = -l1; x2 = v - mb * x1; }
+      if (x2 > l2) { x2 = l2; x1 = clampd(u - mb * x2, -l1, l1); } else if (x2 < -l2) { x2 = -l2; x1 = clampd(u - mb * x2, -l1, l1); }
+      copy3(q1, pa); addscl3(q1, a1, x1);
+      copy3(q2, pb); addscl3(q2, a2, x2);
+      if (raw_sphere_sphere(q1, sa[0], q2, sb[0], margin, pos, nrm, &dist)) prim_push(o, pos, nrm, dist, sign);
+    } else { /* parallel axes: the ends of capsule 1 against segment 2, then the ends of capsule 2 against segment 1, two points at most */
+      for (int e = 0; e < 2 && o->n < 2; e++) {
+        double x1 = e ? -l1 : l1, x2 = clampd(v - mb * x1, -l2, l2);
+        copy3(q1, pa); addscl3(q1, a1, x1);
+        copy3(q2, pb); addscl3(q2, a2, x2);
+        if (raw_sphere_sphere(q1, sa[0], q2, sb[0], margin, pos, nrm, &dist)) prim_push(o, pos, nrm, dist, sign);
+      }
+      for (int e = 0; e < 2 && o->n < 2; e++) {
+        double x2 = e ? -l2 : l2, x1 = clampd(u - mb * x2, -l1, l1);
+        if (fabs(fabs(x1) - l1) < MINVAL) continue; /* that end of capsule 1 was tested above */
+        copy3(q1, pa); addscl3(q1, a1, x1);
+        copy3(q2, pb); addscl3(q2, a2, x2);
+        if (raw_sphere_sphere(q1, sa[0], q2, sb[0], margin, pos, nrm, &dist)) prim_push(o, pos, nrm, dist, sign);
+      }
+    }
+    return 1;
+  }
+  if (ta == GEOM_CAPSULE && tb == GEOM_BOX) {
+    /* axis segment p(t) = c + t a, t in [-1, 1], in the box frame.  f(t) = squared distance to the box is convex and its derivative
+     * piecewise linear with kinks where a coordinate crosses a face plane: the minimiser is bracketed by the two kinks (or segment
+     * ends) around the sign change of f' and found by linear interpolation between them. */
+    const double *R = s->gxmat + 9 * gb;
+    double ax[3], t3[3], c[3], a[3], T[8];
+    geom_axis(s, ga, ax);
+    sub3(t3, pa, pb);
+    mulmatTvec3(c, R, t3);
+    mulmatTvec3(a, R, ax);
+    scl3(a, a, sa[1]);
+    int nT = 0;
+    T[nT++] = -1; T[nT++] = 1;
+    for (int k = 0; k < 3; k++)
+      if (fabs(a[k]) > MINVAL)
+        for (int sg = -1; sg <= 1; sg += 2) { double t = (sg * sb[k] - c[k]) / a[k]; if (t > -1 && t < 1) T[nT++] = t; }
+    double tl = -2, tr = 2, gl = 0, gr = 0;
+    for (int i = 0; i < nT; i++) {
+      double g = seg_box_dfdt(c, a, sb, T[i]);
+      if (g <= 0 && T[i] > tl) { tl = T[i]; gl = g; }
+      if (g >= 0 && T[i] < tr) { tr = T[i]; gr = g; }
+    }
+    double ts;
+    if (tl < -1.5) ts = -1; else if (tr > 1.5) ts = 1;
+    else if (gr - gl > MINVAL) ts = tl + (tr - tl) * (-gl) / (gr - gl);
+    else ts = 0.5 * (tl + tr);
+    /* candidates: the two ends, then the closest point; first contact = deepest (earlier candidate on ties), second = the deepest
+     * other candidate in contact that is not the same point of the segment */
+    double ct[3] = {-1, 1, ts}, cpos[3][3], cn[3][3], cd[3];
+    int hit[3];
+    for (int i = 0; i < 3; i++) {
+      double q[3];
+      copy3(q, pa);
+      addscl3(q, ax, sa[1] * ct[i]);
+      hit[i] = raw_sphere_box(s, q, sa[0], gb, margin, cpos[i], cn[i], &cd[i]);
+    }
+    int i1 = -1, i2 = -1;
+    for (int i = 0; i < 3; i++) if (hit[i] && (i1 < 0 || cd[i] < cd[i1])) i1 = i;
+    if (i1 >= 0) {
+      for (int i = 0; i < 3; i++) if (i != i1 && hit[i] && fabs(ct[i] - ct[i1]) > 0.05 && (i2 < 0 || cd[i] < cd[i2])) i2 = i;
+      prim_push(o, cpos[i1], cn[i1], cd[i1], sign);
+      if (i2 >= 0) prim_push(o, cpos[i2], cn[i2], cd[i2], sign);
+    }
+    return 1;
+  }
+  return 0;
+}
+
 #define FACE_ALIGN_MIN 0.9990 /* below this the contact is edge/vertex-like: single MPR point */
+
+static int has_face(const OrcSim *s, int g, const double *n) {
+  int t = s->m.cgeom_type[g];
+  if (is_polytope(t)) return 1;
+#ifndef ORC_NO_CYLINDER_CAPS
+  if (t == GEOM_CYLINDER && !s->no_analytic) {
+    const double *R = s->gxmat + 9 * g;
+    return fabs(R[2] * n[0] + R[5] * n[1] + R[8] * n[2]) >= FACE_ALIGN_MIN;
+  }
+#endif
+  return 0;
+}
 
 static void collide_pair(OrcSim *s, int pair) {
   const MgsModelDesc *m = &s->m;
@@ -797,9 +1043,21 @@ static void collide_pair(OrcSim *s, int pair) {
   sub3(dc, s->gxpos + 3 * g1, s->gxpos + 3 * g2);
   double rr = m->cgeom_rbound[g1] + m->cgeom_rbound[g2] + m->pair_margin[pair];
   if (dot3(dc, dc) > rr * rr) return;
+#ifndef ORC_NO_ANALYTIC_PRIMS
+  if (!s->no_analytic) {
+    PrimCon pc;
+    if (prim_pair(s, pair, &pc)) {
+      for (int k = 0; k < pc.n; k++) add_contact(s, pair, pc.pos[k], pc.normal[k], pc.dist[k]);
+      return;
+    }
+  }
+#endif
   if (!mpr_penetration(s, g1, g2, &depth, n, pos)) return;
   if (!(depth > 0)) return;
-  if (is_polytope(m->cgeom_type[g1]) && is_polytope(m->cgeom_type[g2])) {
+  /* multi-point manifold: both geoms must offer a flat face - polytopes always do, a cylinder when the contact normal is along its
+   * axis (a cap).  MuJoCo gets the extra points of flat ccd contacts from the multiccd perturbation (enabled by the reference's scene
+   * options); here the two most-aligned faces are clipped against each other (cap against cap is left a single point). */
+  if (has_face(s, g1, n) && has_face(s, g2, n) && (is_polytope(m->cgeom_type[g1]) || is_polytope(m->cgeom_type[g2]))) {
     double a1, a2, nn[3] = {-n[0], -n[1], -n[2]};
     int f1 = best_face(s, g1, n, &a1), f2 = best_face(s, g2, nn, &a2);
     if (fmax(a1, a2) >= FACE_ALIGN_MIN) {
@@ -1517,6 +1775,7 @@ static void integrate(OrcSim *s) {
   s->time += h;
 }
 
+void orc_set_analytic(OrcSim *s, int on) { s->no_analytic = !on; }
 void orc_set_qvel_clip(OrcSim *s, double clip) { s->qvel_clip = clip > 0 ? clip : 0; }
 
 int orc_step(OrcSim *s, int nstep) {

@@ -52,6 +52,8 @@ def lib():
             getattr(L, "orc_" + name).restype = C.c_int
         L.orc_set_qvel_clip.argtypes = [C.c_void_p, C.c_double]
         L.orc_set_qvel_clip.restype = None
+        L.orc_set_analytic.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_analytic.restype = None
         L.orc_step.argtypes = [C.c_void_p, C.c_int]
         L.orc_step.restype = C.c_int
         L.orc_contact.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
@@ -145,6 +147,8 @@ class OracleSim:
     def step(self, n=1): return self.L.orc_step(self.h, n)
     def set_qvel_clip(self, clip): self.L.orc_set_qvel_clip(self.h, float(clip))
     def kinematics(self): self.L.orc_kinematics_only(self.h)
+    def collision_only(self): self.L.orc_collision_only(self.h)
+    def set_analytic(self, on): self.L.orc_set_analytic(self.h, int(bool(on)))
     def contact_with_object(self): return bool(self.L.orc_contact_with_object(self.h))
 
     def record_size(self):
