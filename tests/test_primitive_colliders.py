@@ -2,6 +2,8 @@
 engine_collision_primitive.c) checked against two things that share no code with them: the oracle's own MPR on the same shallow
 penetrations, and hand-computed known answers.  The kernel's copy of the same routines is checked against the oracle in
 tests/test_lane1_vs_oracle.py (1-lane host build) and tests/test_gpu_parity.py (-m gpu)."""
+import os
+
 import numpy as np
 import pytest
 from scipy.spatial.transform import Rotation as R
@@ -202,27 +204,24 @@ def test_cylinder_cap_is_a_face_and_its_side_is_not():
     assert len(ca) == 1 and np.array_equal(ca, cm)
 
 
-@pytest.mark.parametrize("a,b", [("sphere", "sphere2"), ("capsule", "sphere"), ("sphere", "cylinder"), ("box", "sphere"),
-                                 ("capsule", "capsule2"), ("capsule", "box"), ("box", "capsule"), ("cylinder", "box"), ("box", "cylinder")])
-def test_kernel_source_matches_the_oracle_on_primitive_pairs(a, b):
-    """The kernel's own copy of the closed forms (csrc/mgs_collide.cuh prim_pair, here through the fp64 1-lane host build of the
-    kernel source) against the oracle: 8 random ~1 mm penetrations per pair, 5 steps each - contact counts equal at every step and
-    the states (which feel every contact's position, normal and depth through the solver) equal to 1e-9."""
-    from hostsim import lane1
-    m = compile_mjcf(PAIR.format(a=GEOMS[a][0], b=GEOMS[b][0]))
-    s, k = OracleSim(m), lane1.sim(m, f64=True)
+KERNEL_PAIRS = [("sphere", "sphere2"), ("capsule", "sphere"), ("sphere", "cylinder"), ("box", "sphere"), ("capsule", "capsule2"),
+                ("capsule", "box"), ("box", "capsule"), ("cylinder", "box"), ("box", "cylinder")]
+
+
+def _shallow_configs(a, b, s):
+    """qpos of random ~1 mm penetrations of the pair (found by bisection on the oracle's closed forms); the first one of capsule-box
+    is the two-point case (capsule flat on the top face, tilted by 1 mrad), of cylinder-box the cap manifold (cylinder standing on /
+    under a box face).  cylinder-box: only that one - its other contacts are MPR answers, where the kernel's warm-started hill
+    climbing and the oracle's cold exhaustive search agree to mpr_tolerance, not to rounding (tests/test_lane1_vs_oracle.py)."""
     rng = np.random.default_rng(abs(hash((b, a))) % 2**31)
-    done = 0
-    flat = R.from_euler("y", np.pi / 2).as_quat()[[3, 0, 1, 2]]
-    # (cylinder-box: only the cap manifold, which is exact; its other contacts are MPR answers, where the kernel's warm-started hill
-    # climbing and the oracle's cold exhaustive search agree to mpr_tolerance, not to rounding - tests/test_lane1_vs_oracle.py)
+    out = []
     for trial in range(1 if {a, b} == {"cylinder", "box"} else 12):
         qa = np.r_[rng.normal(size=3) * 0.01, _rand_quat(rng)]
         d = rng.normal(size=3); d /= np.linalg.norm(d)
         quat_b = _rand_quat(rng)
-        if trial == 0 and {a, b} == {"cylinder", "box"}:  # the cap manifold: cylinder standing on / under a box face, axes aligned
+        if trial == 0 and {a, b} == {"cylinder", "box"}:
             qa = np.r_[0.002, 0.001, 0, 1.0, 0, 0, 0]; d = np.array([0, 0, -1.0 if a == "cylinder" else 1.0]); quat_b = np.array([1.0, 0, 0, 0])
-        if trial == 0 and (a, b) == ("capsule", "box"):  # the two-point case: capsule flat on the top face, tilted by 1 mrad
+        if trial == 0 and (a, b) == ("capsule", "box"):
             qa = np.r_[0, 0, 0, R.from_euler("y", np.pi / 2 + 1e-3).as_quat()[[3, 0, 1, 2]]]; d = np.array([0, 0, -1.0]); quat_b = np.array([1.0, 0, 0, 0])
         lo, hi = 0.0, GEOMS[a][1] + GEOMS[b][1] + 0.01
         for _ in range(50):
@@ -238,15 +237,59 @@ def test_kernel_source_matches_the_oracle_on_primitive_pairs(a, b):
             assert len(c) == 2
         if trial == 0 and {a, b} == {"cylinder", "box"}:
             assert len(c) == 4
+        out.append(qpos)
+    assert len(out) >= (1 if {a, b} == {"cylinder", "box"} else 6)
+    return out
+
+
+@pytest.mark.parametrize("a,b", KERNEL_PAIRS)
+def test_kernel_source_matches_the_oracle_on_primitive_pairs(a, b):
+    """The kernel's own copy of the closed forms (csrc/mgs_collide.cuh prim_pair, here through the fp64 1-lane host build of the
+    kernel source) against the oracle: random ~1 mm penetrations per pair, 5 steps each - contact counts equal at every step and
+    the states (which feel every contact's position, normal and depth through the solver) equal to 1e-9."""
+    from hostsim import lane1
+    m = compile_mjcf(PAIR.format(a=GEOMS[a][0], b=GEOMS[b][0]))
+    s, k = OracleSim(m), lane1.sim(m, f64=True)
+    for qpos in _shallow_configs(a, b, s):
         s.reset(); s.set_analytic(True)
         s.qpos[:] = qpos
         st = k.pack_state(qpos[None], np.zeros((1, 12)))
         for step in range(5):
             s.step(1)
             st, dg = k.step(st, 1, want_diag=True)
-            assert int(dg["ncon"][0]) == s.ncon, (trial, step)
+            assert int(dg["ncon"][0]) == s.ncon, step
             u = k.unpack_state(st); q2, v2 = u["qpos"], u["qvel"]
-            tol = 1e-9
-            assert np.abs(q2[0] - s.qpos).max() < tol and np.abs(v2[0] - s.qvel).max() < 100 * tol, (trial, step)
-        done += 1
-    assert done >= (1 if {a, b} == {"cylinder", "box"} else 6)
+            assert np.abs(q2[0] - s.qpos).max() < 1e-9 and np.abs(v2[0] - s.qvel).max() < 1e-7, step
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("a,b", KERNEL_PAIRS)
+def test_cuda_builds_match_the_oracle_on_primitive_pairs(a, b):
+    """The same configurations through the CUDA library (one batch per pair type, every configuration its own environment): the
+    fp64 build to 1e-9 like the host build of the source, the fp32 build to 1e-6 in qpos / 1e-3 in qvel after five steps of contact
+    response (the 1-lane fp32 host build of the same source measures 2e-7 / 7.5e-5)."""
+    from mj_grasp_sim_b200 import lib as mlib
+    m = compile_mjcf(PAIR.format(a=GEOMS[a][0], b=GEOMS[b][0]))
+    s = OracleSim(m)
+    qs = np.array(_shallow_configs(a, b, s))
+    ref_q, ref_v, ref_n = [], [], []
+    for qpos in qs:
+        s.reset(); s.set_analytic(True)
+        s.qpos[:] = qpos
+        ns = []
+        for step in range(5):
+            s.step(1); ns.append(s.ncon)
+        ref_q.append(np.array(s.qpos)); ref_v.append(np.array(s.qvel)); ref_n.append(ns)
+    ref_q, ref_v, ref_n = np.array(ref_q), np.array(ref_v), np.array(ref_n)
+    for f64, tol in ((True, 1e-9), (False, 1e-6)):
+        if f64 and not os.path.exists(mlib.SO_PATH_F64):
+            pytest.fail("the fp64 build is missing")
+        G = mlib.BatchSim(m, f64=f64)
+        st = G.pack_state(qs, np.zeros((len(qs), 12)))
+        for step in range(5):
+            st, dg = G.step(st, 1, want_diag=True)
+            if f64:
+                assert np.array_equal(dg["ncon"], ref_n[:, step]), (step, dg["ncon"], ref_n[:, step])
+        u = G.unpack_state(st)
+        assert np.abs(u["qpos"] - ref_q).max() < tol and np.abs(u["qvel"] - ref_v).max() < 1000 * tol, (f64, np.abs(u["qpos"] - ref_q).max(), np.abs(u["qvel"] - ref_v).max())
+        G.close()
