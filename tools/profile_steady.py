@@ -2,7 +2,7 @@
 of the close phase (launch 1, not profiled: use `ncu --launch-skip 1 --launch-count 1`), then `nstep` more
 steps of the HOLD phase run as launch 2 - the regime that makes up >90 % of the 8000-step schedule.
 
-usage: python tools/profile_steady.py [gripper] [n_env] [settle_steps] [nstep] [ncon_max nefc_max]
+usage: [MGS_STEADY_F64=1] python tools/profile_steady.py [gripper] [n_env] [settle_steps] [nstep] [ncon_max nefc_max]
 """
 import os, sys, time
 import numpy as np
@@ -20,7 +20,7 @@ m, info, pose7, joints = scenes.workload(gripper, "hull", 0, n)
 caps = {"panda": dict(ncon_max=24, nefc_max=100), "robotiq2f85": dict(ncon_max=24, nefc_max=110)}.get(gripper, {})
 if len(sys.argv) > 6:
     caps = dict(ncon_max=int(sys.argv[5]), nefc_max=int(sys.argv[6]))
-G = BatchSim(m, **caps)
+G = BatchSim(m, f64=os.environ.get("MGS_STEADY_F64", "0") == "1", **caps)  # MGS_STEADY_F64=1: the fp64 build (product path of the hands)
 qpos = np.tile(m.qpos0, (n, 1))
 b = info["base_qposadr"]
 qpos[:, b:b + 7] = pose7
