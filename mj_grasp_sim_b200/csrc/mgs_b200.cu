@@ -99,7 +99,7 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   M->num_sms = prop.multiProcessorCount;
-  int env_bytes = make_layout(32);
+  int env_bytes = 0;
   // Warp-per-environment variants: CTA size = the warps-per-block that gives the most resident warps per SM (shared memory per
   // environment and the per-CTA reservation decide).  First with the 16-warp variant; if at most 12 environments fit per SM
   // anyway, the 12-warp variant (more registers per thread) takes over.  Scenes that leave room for fewer than
@@ -110,20 +110,45 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
   std::lock_guard<std::mutex> lock(g_launch_mu);  // the occupancy sweep changes the variants' shared-memory attribute
   const MgsKernelOps *variants[2] = {mgs_kernel_ops_w16(), mgs_kernel_ops_w12()};
   int best_warps = 0;
-  for (int v = 0; v < 2 && !force_wide && (size_t)env_bytes <= prop.sharedMemPerBlockOptin; v++) {
-    const MgsKernelOps *ops = variants[v];
-    if (force_var && std::string(force_var) != (v == 0 ? "w16" : "w12")) continue;
-    if (v == 1 && !force_var && (best_warps == 0 || best_warps > ops->max_warps || M->blocks_per_sm != 1)) break;
-    int vb = 0, vw = 0, vo = 0;
-    for (int w = 1; w <= ops->max_warps; w++) {
-      if (force_wpb && atoi(force_wpb) != w) continue;
-      if ((size_t)env_bytes * w > prop.sharedMemPerBlockOptin) break;
-      CU(ops->prepare(env_bytes * w));
-      int occ = 0;
-      CU(ops->occupancy(&occ, w * 32, (size_t)env_bytes * w));
-      if (occ * w >= vb && occ > 0) { vb = occ * w; vw = w; vo = occ; }  // ties go to the LARGER CTA: one CTA per SM keeps all resident warps stage-aligned
+  // FIRST-PASS CAPACITY of single-object scenes, when the caller left the capacities to the library: if the default contact
+  // capacity leaves room for fewer than MGS_WIDE_BELOW_ENVS warp-environments per SM, smaller ones are tried (24, 20, 16 contacts)
+  // and the first that fits that many is taken.  Measured on the Allegro hand in the fp64 build (its product path): 32 contacts =
+  // 90 KB per environment = the environment-per-CTA variant at 0.54 M env-steps/s; 16 contacts = 57 KB = four warp-environments
+  // per SM at 0.94 M, no environment of 1,024 over capacity, identical labels (profiles/caps_sweep_r2c_f64_hands.log).  An
+  // environment that does exceed its capacity is flagged per candidate as always and re-run on larger capacities by the callers
+  // (mgs.env EscalatingSim, tools/label_agreement.py).  MGS_NO_AUTO_CAPS=1 keeps the default capacity.
+  const bool auto_caps = ncon_max <= 0 && nefc_max <= 0 && !force_var && !force_wpb && blob.nfreeobj <= 1 && !getenv("MGS_NO_AUTO_CAPS");
+  const int default_nc = blob.ncon_max, default_ne = blob.nefc_max;
+  const int try_nc[4] = {default_nc, 24, 20, 16};
+  for (int attempt = 0; attempt < 4; attempt++) {
+    if (attempt > 0) {
+      if (!auto_caps || force_wide || try_nc[attempt] >= default_nc) break;
+      blob.ncon_max = try_nc[attempt];
+      blob.nefc_max = blob.rows_static + blob.ncon_max * blob.rows_per_contact;
     }
-    if (vb >= best_warps && vb > 0) { best_warps = vb; M->warps_per_block = vw; M->blocks_per_sm = vo; M->ops = ops; }
+    env_bytes = make_layout(32);
+    best_warps = 0;
+    for (int v = 0; v < 2 && !force_wide && (size_t)env_bytes <= prop.sharedMemPerBlockOptin; v++) {
+      const MgsKernelOps *ops = variants[v];
+      if (force_var && std::string(force_var) != (v == 0 ? "w16" : "w12")) continue;
+      if (v == 1 && !force_var && (best_warps == 0 || best_warps > ops->max_warps || M->blocks_per_sm != 1)) break;
+      int vb = 0, vw = 0, vo = 0;
+      for (int w = 1; w <= ops->max_warps; w++) {
+        if (force_wpb && atoi(force_wpb) != w) continue;
+        if ((size_t)env_bytes * w > prop.sharedMemPerBlockOptin) break;
+        CU(ops->prepare(env_bytes * w));
+        int occ = 0;
+        CU(ops->occupancy(&occ, w * 32, (size_t)env_bytes * w));
+        if (occ * w >= vb && occ > 0) { vb = occ * w; vw = w; vo = occ; }  // ties go to the LARGER CTA: one CTA per SM keeps all resident warps stage-aligned
+      }
+      if (vb >= best_warps && vb > 0) { best_warps = vb; M->warps_per_block = vw; M->blocks_per_sm = vo; M->ops = ops; }
+    }
+    if (best_warps >= MGS_WIDE_BELOW_ENVS) break;
+  }
+  if (best_warps < MGS_WIDE_BELOW_ENVS && blob.ncon_max != default_nc) {  // no smaller capacity helped: back to the default (wide variant)
+    blob.ncon_max = default_nc;
+    blob.nefc_max = default_ne;
+    env_bytes = make_layout(32);
   }
   if (force_wide || (!force_var && best_warps < MGS_WIDE_BELOW_ENVS)) {
     const MgsKernelOps *ops = mgs_kernel_ops_wide();

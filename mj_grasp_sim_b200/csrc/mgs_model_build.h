@@ -13,6 +13,7 @@ struct ModelBlob {
   DevModel dm;  // pointers hold byte OFFSETS until rebase()
   int ncon_max, nefc_max;
   int rows_static, rows_per_contact;  // nefc_max default = rows_static + ncon_max * rows_per_contact
+  int nfreeobj;                       // free-floating leaf bodies (grasped / cluttered objects)
 };
 
 namespace mgs_detail {
@@ -199,6 +200,7 @@ inline bool build_model_blob(const MgsModelDesc *d, ModelBlob &out, std::string 
   if (nv > 24 && nfreeobj <= 1) nc = 32;
   nc = (nc + 3) & ~3;
   out.ncon_max = nc;
+  out.nfreeobj = nfreeobj;
   out.rows_static = ne + nfr + nlim;
   out.rows_per_contact = maxdim < 3 ? 3 : maxdim;
   out.nefc_max = out.rows_static + nc * out.rows_per_contact;  // every contact slot can hold the largest cone
