@@ -313,7 +313,8 @@ def run_ours(args, rank, world, local_rank):
                               "l2": "flushed between timed iterations (256 MiB fill)",
                               "stable_fraction": sum(stable_l) / (world * N_CAND * steps),
                               "capacity": {"ncon_max": sim0.info.ncon_max, "nefc_max": sim0.info.nefc_max, "envs_overflowed": int(sum(over_l)),
-                                           "of_candidates": world * N_CAND * steps},
+                                           "of_candidates": world * N_CAND * steps,
+                                           "policy": "first-pass capacities; an environment over capacity is flagged per candidate and the product path (mgs.env) re-runs it on larger ones - not done inside this timed region"},
                               "envs_per_sm": sim0.info.warps_per_block * sim0.info.blocks_per_sm, "smem_bytes_per_env": sim0.info.smem_bytes_per_env},
                    "grasps_per_s": world * N_CAND * steps / dev_max,
                    "e2e": {"value": sum(e2e_st_l) / e2e_max, "unit": "env-steps/s", "h2d_bytes_per_step": int(sets[0]["pose7"].nbytes + sets[0]["joints"].nbytes),
