@@ -91,9 +91,10 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
   M->dm = blob.dm;
   rebase_model(M->dm, M->d_blob);
   CU(cudaMalloc(&M->d_counter, 2 * sizeof(unsigned int)));  // [0] work queue head, [1] environments that overflowed a capacity
+  int ncache_max = MGS_MPR_CACHE_MAX;
   auto make_layout = [&](int lanes) {
     layout_compute(&M->L, desc->nq, desc->nv, desc->nu, desc->nbody, desc->njnt, desc->nmocap, desc->ntendon, desc->ncgeom, blob.ncon_max,
-                   blob.nefc_max, desc->npair, blob.dm.nM, lanes);
+                   blob.nefc_max, desc->npair, blob.dm.nM, lanes, ncache_max);
     return (int)(M->L.total * sizeof(real));
   };
   cudaDeviceProp prop;
@@ -111,20 +112,23 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
   const MgsKernelOps *variants[2] = {mgs_kernel_ops_w16(), mgs_kernel_ops_w12()};
   int best_warps = 0;
   // FIRST-PASS CAPACITY of single-object scenes, when the caller left the capacities to the library: if the default contact
-  // capacity leaves room for fewer than MGS_WIDE_BELOW_ENVS warp-environments per SM, smaller ones are tried (24, 20, 16 contacts)
-  // and the first that fits that many is taken.  Measured on the Allegro hand in the fp64 build (its product path): 32 contacts =
+  // capacity leaves room for fewer than MGS_WIDE_BELOW_ENVS warp-environments per SM, smaller ones are tried (24, 20, 16 contacts,
+  // then 16 and 12 with the shared-memory MPR cache cut to 32 pairs - the rest of the pairs use the global cache) and the first
+  // that fits that many is taken.  Measured on the Allegro hand in the fp64 build (its product path): 32 contacts =
   // 90 KB per environment = the environment-per-CTA variant at 0.54 M env-steps/s; 16 contacts = 57 KB = four warp-environments
   // per SM at 0.94 M, no environment of 1,024 over capacity, identical labels (profiles/caps_sweep_r2c_f64_hands.log).  An
   // environment that does exceed its capacity is flagged per candidate as always and re-run on larger capacities by the callers
   // (mgs.env EscalatingSim, tools/label_agreement.py).  MGS_NO_AUTO_CAPS=1 keeps the default capacity.
   const bool auto_caps = ncon_max <= 0 && nefc_max <= 0 && !force_var && !force_wpb && blob.nfreeobj <= 1 && !getenv("MGS_NO_AUTO_CAPS");
   const int default_nc = blob.ncon_max, default_ne = blob.nefc_max;
-  const int try_nc[4] = {default_nc, 24, 20, 16};
-  for (int attempt = 0; attempt < 4; attempt++) {
+  const int ntry = 6, try_nc[ntry] = {default_nc, 24, 20, 16, 16, 12}, try_cache[ntry] = {MGS_MPR_CACHE_MAX, MGS_MPR_CACHE_MAX, MGS_MPR_CACHE_MAX, MGS_MPR_CACHE_MAX, 32, 32};
+  for (int attempt = 0; attempt < ntry; attempt++) {
     if (attempt > 0) {
-      if (!auto_caps || force_wide || try_nc[attempt] >= default_nc) break;
+      if (!auto_caps || force_wide) break;
+      if (try_nc[attempt] >= default_nc) continue;
       blob.ncon_max = try_nc[attempt];
       blob.nefc_max = blob.rows_static + blob.ncon_max * blob.rows_per_contact;
+      ncache_max = try_cache[attempt];
     }
     env_bytes = make_layout(32);
     best_warps = 0;
@@ -148,6 +152,7 @@ extern "C" int mgs_model_create_ex(const MgsModelDesc *desc, int device, int nco
   if (best_warps < MGS_WIDE_BELOW_ENVS && blob.ncon_max != default_nc) {  // no smaller capacity helped: back to the default (wide variant)
     blob.ncon_max = default_nc;
     blob.nefc_max = default_ne;
+    ncache_max = MGS_MPR_CACHE_MAX;
     env_bytes = make_layout(32);
   }
   if (force_wide || (!force_var && best_warps < MGS_WIDE_BELOW_ENVS)) {

@@ -177,9 +177,9 @@ struct Layout {
                                // 4 words per pair - portal vertex pairs or separating axis (words 0-2), hill-climb start vertices (3)
 // `lanes`: threads that share one environment (32 for the warp-per-environment variants, MGS_WIDE for the env-per-CTA one)
 static inline void layout_compute(Layout *L, int nq, int nv, int nu, int nbody, int njnt, int nmocap, int ntendon, int ncgeom,
-                                  int ncon_max, int nefc_max, int npair, int nM, int lanes = 32) {
+                                  int ncon_max, int nefc_max, int npair, int nM, int lanes = 32, int ncache_max = MGS_MPR_CACHE_MAX) {
   int off = 0;
-  const int ncache = npair < MGS_MPR_CACHE_MAX ? npair : MGS_MPR_CACHE_MAX;
+  const int ncache = npair < ncache_max ? npair : ncache_max;  // the pairs beyond it keep their warm start in the global (L2) cache
   L->ncache = ncache;
   // arrays are packed back to back (no vector loads anywhere: word alignment is enough); padding every array to 16 bytes cost
   // ~270 bytes per environment, which is the difference between 10 and 9 resident Robotiq environments per SM
