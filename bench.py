@@ -50,9 +50,9 @@ WORKLOADS = {
     "panda": dict(gripper="panda", caps=(24, 100), objects=N_OBJECTS,
                   desc=f"panda gripper, 8 synthetic convex-hull objects (n_v 16/32/64, ycb recipe), 4096 antipodal candidates per object, one object per step, {SCHED_TXT}"),
     "allegro": dict(gripper="allegro", caps=(0, 0), objects=2, n=1024,
-                    desc=f"configs[3]: allegro hand (16 dof, Newton), synthetic convex-hull objects, 1024 candidates (one GPU-filling wave) per object, one object per step, {SCHED_TXT}"),
+                    desc=f"configs[3]: allegro hand (16 dof, Newton), synthetic convex-hull objects, 1024 candidates per object, one object per step, {SCHED_TXT}"),
     "leap": dict(gripper="leap", caps=(0, 0), objects=2, n=1024,
-                 desc=f"configs[3]: leap hand (16 dof, Newton), synthetic convex-hull objects, 1024 candidates (one GPU-filling wave) per object, one object per step, {SCHED_TXT}"),
+                 desc=f"configs[3]: leap hand (16 dof, Newton), synthetic convex-hull objects, 1024 candidates per object, one object per step, {SCHED_TXT}"),
 }
 MIXED_DESC = (f"configs[2]: vx300 + panda mixed batch, 65536 candidates = 8 synthetic convex-hull objects (n_v 16/32/64) x 2 grippers x 4096, "
               f"bucketed by model, sharded over the ranks in GPU-filling chunks (dynamic hand-out), {SCHED_TXT}")
