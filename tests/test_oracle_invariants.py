@@ -146,3 +146,55 @@ def test_newton_solution_is_kkt_point(panda_cube):
     J, f = s.efc("J"), s.efc("force")
     lhs = s.M @ s.qacc - s.qfrc_smooth
     assert np.allclose(lhs, J.T @ f, atol=1e-6 * max(1.0, np.abs(lhs).max()))
+
+
+REST = """<mujoco><compiler angle="radian" autolimits="true"/>
+<option integrator="implicitfast" timestep="0.001" cone="elliptic" impratio="3" noslip_iterations="2" gravity="0 0 -9.81"/>
+<worldbody><geom name="geom:ground" type="box" size="1 1 0.02" pos="0 0 -0.02"/>
+<body name="b" pos="0 0 0.0199"><freejoint name="j"/>
+<geom type="sphere" size="0.02" mass="{mass}" solref="{solref}" solimp="{solimp}"/></body></worldbody></mujoco>"""
+
+
+def _impedance(solimp, r):
+    d0, dw, width, mid, power = solimp
+    x = min(1.0, abs(r) / width)
+    if power == 1:
+        y = x
+    elif x <= mid:
+        y = x ** power / mid ** (power - 1)
+    else:
+        y = 1 - (1 - x) ** power / (1 - mid) ** (power - 1)
+    return d0 + y * (dw - d0)
+
+
+@pytest.mark.parametrize("mass,solref,solimp", [(0.3, (0.02, 1.0), (0.9, 0.95, 0.001, 0.5, 2.0)), (2.0, (0.02, 1.0), (0.9, 0.95, 0.001, 0.5, 2.0)),
+                                                (0.3, (0.005, 1.0), (0.95, 0.99, 0.001, 0.5, 2.0)), (0.3, (0.02, 0.7), (0.8, 0.9, 0.002, 0.3, 3.0))])
+def test_resting_depth_follows_the_soft_constraint_model(mass, solref, solimp):
+    """A sphere at rest on the ground under gravity: one contact whose normal row is a unit translation, so A = J M^-1 J' = 1 / m =
+    diagApprox exactly and MuJoCo's soft-constraint model (Computation chapter: R = (1 - d) / d * A, aref = -b v - k d r with
+    k = 1 / (dmax^2 timeconst^2 dampratio^2)) has a closed-form equilibrium: a0 + A f = 0 and f = (aref - a0) / (A + R) give
+    r = -(1 - d(r)) g / (d(r)^2 k), independent of the mass.  Pins impedance, regulariser and reference acceleration - and the
+    sphere-box closed form that supplies r - to the documented formulas; the kernel source (fp64 1-lane build) must land on the
+    same depth."""
+    from hostsim import lane1
+    mix = lambda a, b: 0.5 * (a + b)  # geom defaults on the ground: solmix 1 vs 1 -> plain mean of the two geoms' parameters
+    sr = (mix(solref[0], 0.02), mix(solref[1], 1.0))
+    si = tuple(mix(a, b) for a, b in zip(solimp, (0.9, 0.95, 0.001, 0.5, 2.0)))
+    m = compile_mjcf(REST.format(mass=mass, solref="%g %g" % solref, solimp="%g %g %g %g %g" % solimp))
+    assert np.allclose(m.pair_solref[0], sr) and np.allclose(m.pair_solimp[0], si)
+    dmax = si[1]
+    k = 1.0 / (dmax * dmax * max(sr[0], 2e-3) ** 2 * sr[1] ** 2)
+    r = -1e-4
+    for _ in range(200):  # fixed point of r = -(1 - d(r)) g / (d(r)^2 k)
+        d = _impedance(si, r)
+        r = -(1 - d) * 9.81 / (d * d * k)
+    s = OracleSim(m)
+    s.reset()
+    s.step(3000)
+    con = s.contacts()
+    assert len(con) == 1 and np.abs(s.qvel).max() < 1e-9
+    assert np.isclose(con[0, 12], r, rtol=1e-6), (con[0, 12], r)
+    assert np.isclose(s.efc("force")[int(con[0, 17])], mass * 9.81, rtol=1e-9)
+    L = lane1.sim(m, f64=True)
+    st = L.step(L.pack_state(m.qpos0[None], np.zeros((1, 6))), 3000)
+    assert np.isclose(L.unpack_state(st)["qpos"][0, 2] - 0.02, r, rtol=1e-6)
