@@ -48,15 +48,21 @@ XML = r"""
 # 256 holds every contact the pair lists of the two-finger grippers can produce (63 pairs x 4 points)
 ESCALATION_CAPS = (256, 128, 96, 64)
 MAX_CAPS = (ESCALATION_CAPS[0], 0)
+# first rung of the ladder: the library's default capacity of a single-object scene.  A model whose first pass was cut below it (the
+# fp64 hands: 16 / 12 contacts, so that four warp-environments fit an SM) re-runs its few environments over capacity there before
+# the largest capacity is tried for what is still over: a launch of a handful of candidates lasts one rollout whatever its size, and
+# a rollout on 32 contacts is much shorter than one on 128
+MID_CAPS = (32, 0)
 
 
 class EscalatingSim:
-    """Two instances of one model: the default capacities (most environments resident per SM) and, created on first
-    need, the largest ones.  `run(call, n)` evaluates n candidates with `call(sim, index_array_or_None) -> arrays`, then
-    re-runs the candidates whose environment overflowed on the big instance."""
+    """Up to three instances of one model: the first-pass capacities (most environments resident per SM) and, created on first
+    need, the default capacity of a single-object scene (when the first pass was cut below it) and the largest one that fits.
+    `run(call, n)` evaluates n candidates with `call(sim, index_array_or_None) -> arrays`, then re-runs the candidates whose
+    environment overflowed up that ladder until none is left (or the ladder ends: warning)."""
 
     def __init__(self, make_sim):
-        self._make, self._small, self._big = make_sim, None, None
+        self._make, self._small, self._mid, self._big = make_sim, None, None, None
         self.last_overflow = dict(first_pass=0, after_escalation=0)
 
     @property
@@ -81,11 +87,21 @@ class EscalatingSim:
                 raise err if err is not None else RuntimeError("no larger capacity than the first pass's")
         return self._big
 
+    @property
+    def mid(self):
+        """the MID_CAPS instance, or None when the first pass already has that capacity (or the model does not fit it)"""
+        if self._mid is None and self.small.info.ncon_max < MID_CAPS[0]:
+            try:
+                self._mid = self._make(MID_CAPS)
+            except Exception:
+                self._mid = False
+        return self._mid or None
+
     def close(self):
-        for s in (self._small, self._big):
-            if s is not None:
+        for s in (self._small, self._mid, self._big):
+            if s:
                 s.close()
-        self._small = self._big = None
+        self._small = self._mid = self._big = None
 
     def run(self, call, n):
         out = call(self.small, None)
@@ -93,25 +109,33 @@ class EscalatingSim:
         aux = self.small.last_aux(n)
         over = np.nonzero(aux["overflow"])[0]
         self.last_overflow = dict(first_pass=int(len(over)), after_escalation=0)
-        big = None
-        if len(over) and self.small.info.ncon_max < MAX_CAPS[0]:
-            try:
-                big = self.big
-            except Exception:
-                big = None
-        if big is not None:
-            again = call(self.big, over)
+        last = None
+        for rung in ("mid", "big"):
+            if not len(over):
+                break
+            sim = None
+            if rung == "mid":
+                sim = self.mid
+            elif self.small.info.ncon_max < MAX_CAPS[0]:
+                try:
+                    sim = self.big
+                except Exception:
+                    sim = None
+            if sim is None:
+                continue
+            again = call(sim, over)
             again = again if isinstance(again, tuple) else (again,)
             for o, a in zip(out, again):
                 o[over] = a
-            aux2 = self.big.last_aux(len(over))
+            aux2 = sim.last_aux(len(over))
             for k in ("bad", "pos_drift", "rot_drift_deg"):
                 aux[k][over] = aux2[k]
             aux["overflow"][over] = aux2["overflow"]
-            over = over[aux2["overflow"]]
+            over = over[np.asarray(aux2["overflow"], dtype=bool)]
             self.last_overflow["after_escalation"] = int(len(over))
+            last = sim
         if len(over):
-            cap = (self._big or self.small).info.ncon_max
+            cap = (last or self.small).info.ncon_max
             warnings.warn(f"{len(over)} of {n} environments needed more than {cap} contacts: their labels were computed on a "
                           "truncated contact set", RuntimeWarning, stacklevel=3)
         return (out[0] if len(out) == 1 else tuple(out)), aux

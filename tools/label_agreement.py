@@ -55,26 +55,33 @@ def make_oracle(n, only):
 
 
 def run_escalated(G_small, make_big, call):
-    """Labels with NO truncated contact set: candidates whose environment overflowed the default capacities are re-run on the
-    largest ones (what mgs.env's EscalatingSim does).  Returns (arrays..., n_overflow_first, n_overflow_left)."""
+    """Labels with NO truncated contact set: candidates whose environment overflowed the first-pass capacities are re-run up the
+    ladder mgs.env's EscalatingSim climbs - the default capacity of a single-object scene (32 contacts) when the first pass was
+    cut below it, then the largest capacity that fits one CTA's shared memory.  Returns (arrays..., n_overflow_first, n_overflow_left)."""
     out = [np.array(o) for o in call(G_small, None)]
     n = len(out[0])
     over = np.nonzero(G_small.last_aux(n)["overflow"])[0]
-    left = 0
-    if len(over):
+    first = int(len(over))
+    for rung in ((32,), (256, 128, 96, 64)):
+        if not len(over):
+            break
         big = None
-        for nc in (256, 128, 96, 64):  # the largest capacity that fits one CTA's shared memory (mgs.env EscalatingSim does the same)
+        for nc in rung:
+            if nc <= G_small.info.ncon_max:
+                continue
             try:
                 big = make_big(nc)
                 break
             except Exception:
                 continue
+        if big is None:
+            continue
         again = call(big, over)
         for o, a in zip(out, again):
             o[over] = a
-        left = int(big.last_aux(len(over))["overflow"].sum())
+        over = over[np.asarray(big.last_aux(len(over))["overflow"], dtype=bool)]
         big.close()
-    return out, int(len(over)), left
+    return out, first, int(len(over))
 
 
 def measure_one(gripper, kind, seed, n, f64):
