@@ -127,3 +127,47 @@ def test_remove_obj_and_mask_roundtrip():
     env2 = ClutterTableEnv.from_dict(env.to_dict())
     assert int(env2.model.arr["npair"]) == int(m.arr["npair"]) and np.array_equal(env2.model.geom_contype, m.geom_contype)
     assert np.array_equal(env2.model.body_gravcomp, m.body_gravcomp) and np.array_equal(env2.model.pair_geom1, m.pair_geom1)
+
+
+def test_shadow_hand_over_clutter_first_steps_lane1_vs_oracle():
+    """The Shadow hand (spheres, capsules, cylinders, boxes, hulls) closing over a settled two-object scene: kernel source (fp64 1-lane
+    build) vs the oracle over the first 150 steps of the close phase - same contact count at every step, qpos within 1e-6 - with the
+    closed-form pairs (sphere / capsule against box) and MPR pairs both among the contacts."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import clutter_shadow_bench as csb
+    m, info = scenes.build_clutter_scene("shadow", [0, 1])
+    S = OracleSim(m, ground_name="geom:table")
+
+    def ostep(rec, k):
+        S.set_record(rec); S.step(k)
+        return S.get_record()
+    rec = scenes.gen_clutter(m, info, ostep, 7)
+    pose7, joints = csb.make_inputs(scenes, m, info, rec, 8)
+    L = mlib.BatchSim(m, lib=mlib.bind(C.CDLL(lane1.build(True)), prefix="l1_"), prefix="l1_", ground_name="geom:table")
+    nq, nv, nu = m.nq, m.nv, m.nu
+    ty, p1, p2, cg = m.arr["cgeom_type"], m.arr["pair_geom1"], m.arr["pair_geom2"], m.arr["cgeom_geomid"]
+    pairmap = {(int(cg[p1[i]]), int(cg[p2[i]])): i for i in range(len(p1))}
+    kinds = set()
+    for cand in (1, 5):
+        st = rec.copy()
+        b = info["base_qposadr"]
+        st[b:b + 7] = pose7[cand]
+        for k, a in enumerate(info["joint_qposadr"]):
+            st[a] = joints[cand, k]
+        st[nq + 2 * nv:nq + 2 * nv + nu] = info["close_ctrl"]
+        st[nq + 2 * nv + nu:nq + 2 * nv + nu + 7] = pose7[cand]
+        sa = st[None].copy()
+        S.set_record(st)
+        for step in range(150):  # (candidate 5 meets its first manifold decision at a threshold at step 173: DESIGN.md 5)
+            sa, d = L.step(sa, 1, want_diag=True)
+            S.step(1)
+            assert int(d["ncon"][0]) == S.ncon, (cand, step)
+            assert np.abs(sa[0, :nq] - S.qpos).max() < 1e-6, (cand, step)
+            if step % 20 == 0:
+                for c in S.contacts():
+                    p = pairmap[(int(c[13]), int(c[14]))]
+                    kinds.add(tuple(sorted((int(ty[p1[p]]), int(ty[p2[p]])))))
+    GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX, GEOM_MESH = 2, 3, 6, 7
+    assert kinds & {(GEOM_SPHERE, GEOM_BOX), (GEOM_CAPSULE, GEOM_BOX), (GEOM_CAPSULE, GEOM_CAPSULE), (GEOM_SPHERE, GEOM_CAPSULE)}, kinds
+    assert kinds & {(GEOM_BOX, GEOM_MESH), (GEOM_MESH, GEOM_MESH), (GEOM_CAPSULE, GEOM_MESH), (GEOM_BOX, GEOM_BOX)}, kinds
