@@ -293,3 +293,41 @@ def test_cuda_builds_match_the_oracle_on_primitive_pairs(a, b):
         u = G.unpack_state(st)
         assert np.abs(u["qpos"] - ref_q).max() < tol and np.abs(u["qvel"] - ref_v).max() < 1000 * tol, (f64, np.abs(u["qpos"] - ref_q).max(), np.abs(u["qvel"] - ref_v).max())
         G.close()
+
+
+def test_allegro_fingertip_capsules_on_a_cube_kernel_source_vs_oracle():
+    """The closed forms on a real hand: the Allegro hand's four fingertip capsules closing on the box primitive (capsule-box pairs
+    against the grasped object, the ground box and the hand's own link boxes).  Kernel source (fp64 1-lane build) vs the oracle: same
+    contact count at every one of the first 300 steps of the close phase and qpos within 1e-7, capsule-box contacts with the object
+    among them; then the labels of a short rollout."""
+    from hostsim import lane1
+    from mj_grasp_sim_b200 import scenes
+    from mj_grasp_sim_b200.lib import MgsRolloutCfg
+    from oracle.oracle import RolloutCfg, batch
+    m, info, pose7, joints = scenes.workload("allegro", "cube", 0, 6)
+    s, L = OracleSim(m), lane1.sim(m, f64=True)
+    ty, p1, p2, cg = m.arr["cgeom_type"], m.arr["pair_geom1"], m.arr["pair_geom2"], m.arr["cgeom_geomid"]
+    ground = m.names["geom"]["geom:ground"]
+    pairmap = {(int(cg[p1[i]]), int(cg[p2[i]])): i for i in range(len(p1))}
+    cap_on_object = 0
+    for i in (0, 1):
+        s.reset()
+        s.place(pose7[i].astype(np.float64), info["base_qposadr"], joints[i].astype(np.float64), info["joint_qposadr"])
+        s.ctrl[:] = info["close_ctrl"]
+        st = L.pack_state(s.qpos.copy(), s.qvel.copy(), ctrl=s.ctrl.copy(), mocap_pos=s.mocap_pos[0].copy(), mocap_quat=s.mocap_quat[0].copy())
+        for step in range(300):
+            s.step(1)
+            st, d = L.step(st, 1, want_diag=True)
+            assert int(d["ncon"][0]) == s.ncon, (i, step)
+            assert np.abs(L.unpack_state(st)["qpos"][0] - s.qpos).max() < 1e-7, (i, step)
+            if step % 10 == 0:
+                for c in s.contacts():
+                    p = pairmap[(int(c[13]), int(c[14]))]
+                    if {int(ty[p1[p]]), int(ty[p2[p]])} == {3, 6} and min(c[13], c[14]) < ground < max(c[13], c[14]):
+                        cap_on_object += 1
+    assert cap_on_object > 0
+    sched = (600, 200, 30, 1, 0.03, 0.02)
+    lab, steps = L.stability(pose7, joints, info["joint_qposadr"], info["base_qposadr"], info["close_ctrl"], MgsRolloutCfg(*sched))
+    olab, osteps = batch(m, 1, pose7.astype(np.float64), info["base_qposadr"], joints.astype(np.float64), info["joint_qposadr"],
+                         info["close_ctrl"], RolloutCfg(*sched), 4)
+    assert np.array_equal(lab.astype(bool), olab.astype(bool)) and np.array_equal(steps, osteps)
