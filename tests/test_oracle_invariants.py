@@ -198,3 +198,54 @@ def test_resting_depth_follows_the_soft_constraint_model(mass, solref, solimp):
     L = lane1.sim(m, f64=True)
     st = L.step(L.pack_state(m.qpos0[None], np.zeros((1, 6))), 3000)
     assert np.isclose(L.unpack_state(st)["qpos"][0, 2] - 0.02, r, rtol=1e-6)
+
+
+SLIDER = """<mujoco><compiler angle="radian" autolimits="true"/>
+<option integrator="implicitfast" timestep="0.001" cone="elliptic" noslip_iterations="{ns}" gravity="0 0 -9.81"/>
+<worldbody><body name="b" pos="0 0 0"><joint name="j" type="slide" axis="0 0 1" range="-0.05 0.1" frictionloss="{fl}" solreflimit="{sr}" solimplimit="{si}"/>
+<geom type="sphere" size="0.02" mass="{mass}" contype="0" conaffinity="0"/></body></worldbody></mujoco>"""
+
+
+@pytest.mark.parametrize("mass,solref,solimp", [(0.3, (0.02, 1.0), (0.9, 0.95, 0.001, 0.5, 2.0)), (2.0, (0.01, 0.8), (0.8, 0.97, 0.002, 0.4, 3.0))])
+def test_joint_limit_rests_at_the_closed_form_violation(mass, solref, solimp):
+    """A mass on a vertical slide joint resting on its lower limit: the limit row is a unit vector, A = 1 / m = dof_invweight0, so the
+    violation obeys the same closed form as the resting contact, r = -(1 - d(r)) g / (d(r)^2 k) - the CT_LIMIT branch of the row
+    builder, its impedance and its reference acceleration, in the oracle and in the kernel source."""
+    from hostsim import lane1
+    m = compile_mjcf(SLIDER.format(ns=0, fl=0, sr="%g %g" % solref, si="%g %g %g %g %g" % solimp, mass=mass))
+    k = 1.0 / (solimp[1] ** 2 * max(solref[0], 2e-3) ** 2 * solref[1] ** 2)
+    r = -1e-4
+    for _ in range(300):
+        d = _impedance(solimp, r)
+        r = -(1 - d) * 9.81 / (d * d * k)
+    s = OracleSim(m)
+    s.reset()
+    s.step(6000)
+    assert s.nefc == 1 and abs(s.qvel[0]) < 1e-10 and np.isclose(s.qpos[0] + 0.05, r, rtol=1e-8)
+    L = lane1.sim(m, f64=True)
+    st = L.step(L.pack_state(m.qpos0[None], np.zeros((1, 1))), 6000)
+    assert np.isclose(L.unpack_state(st)["qpos"][0, 0] + 0.05, r, rtol=1e-8)
+
+
+def test_dry_friction_threshold_and_sliding_acceleration():
+    """frictionloss on a loaded slide joint: below the threshold (m g < f) the noslip pass holds the joint exactly (without it the soft
+    row creeps, as MuJoCo's does); above it the joint accelerates with (m g - f) / m exactly - CT_FRICTION_DOF rows in the Newton cost
+    (linear zones) and in the noslip sweep, oracle and kernel source."""
+    from hostsim import lane1
+    mass, g = 0.3, 9.81
+    for ns, fl, acc, vmax in ((2, 5.0, 0.0, 1e-12), (0, 5.0, None, 5e-2), (2, 1.0, -(mass * g - 1.0) / mass, None), (0, 1.0, -(mass * g - 1.0) / mass, None)):
+        m = compile_mjcf(SLIDER.format(ns=ns, fl=fl, sr="0.02 1", si="0.9 0.95 0.001 0.5 2", mass=mass))
+        s, L = OracleSim(m), lane1.sim(m, f64=True)
+        s.reset()
+        st = L.pack_state(m.qpos0[None], np.zeros((1, 1)))
+        s.step(20); st = L.step(st, 20)
+        v0, w0 = s.qvel[0], L.unpack_state(st)["qvel"][0, 0]
+        s.step(20); st = L.step(st, 20)
+        v1, w1 = s.qvel[0], L.unpack_state(st)["qvel"][0, 0]
+        assert abs(v1 - w1) < 1e-12
+        if acc is not None:
+            assert np.isclose((v1 - v0) / 0.02, acc, atol=1e-9) and np.isclose((w1 - w0) / 0.02, acc, atol=1e-9)
+        if vmax is not None:
+            assert abs(v1) < vmax
+        if ns == 0 and fl == 5.0:
+            assert v1 < -1e-3  # the soft friction row alone lets the held joint creep
