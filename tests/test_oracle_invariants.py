@@ -249,3 +249,54 @@ def test_dry_friction_threshold_and_sliding_acceleration():
             assert abs(v1) < vmax
         if ns == 0 and fl == 5.0:
             assert v1 < -1e-3  # the soft friction row alone lets the held joint creep
+
+
+ACT = """<mujoco><compiler angle="radian" autolimits="true"/>
+<option integrator="implicitfast" timestep="0.001" cone="elliptic" gravity="0 0 -9.81"/>
+<worldbody><body name="b" pos="0 0 0"><joint name="j" type="slide" axis="0 0 1" stiffness="{stiff}" damping="5"/>
+<geom type="sphere" size="0.02" mass="0.5" contype="0" conaffinity="0"/></body></worldbody>
+<actuator><position name="a" joint="j" kp="{kp}" kv="{kv}" ctrlrange="-1 1" forcerange="{fr}"/></actuator></mujoco>"""
+
+
+@pytest.mark.parametrize("stiff,kp,fr", [(0, 1000, "-20 20"), (200, 0, "-20 20"), (50, 1000, "-20 20"), (0, 1000, "-3 3")])
+def test_position_actuator_spring_and_force_clamp_statics(stiff, kp, fr):
+    """A 0.5 kg mass on a vertical slide joint with a position servo (kp, kv), a joint spring and damping 5: it settles where
+    kp (ctrl - q) - stiffness q = m g; with the actuator force clamped to 3 N < m g it falls at the terminal velocity
+    (m g - 3) / damping instead.  Actuator gain / bias, forcerange, passive forces and the implicitfast derivative terms, oracle and
+    kernel source."""
+    from hostsim import lane1
+    m = compile_mjcf(ACT.format(stiff=stiff, kp=kp, kv=10 if kp else 0, fr=fr))
+    mg, ctrl = 0.5 * 9.81, 0.04 if kp else 0.0
+    s, L = OracleSim(m), lane1.sim(m, f64=True)
+    s.reset()
+    s.ctrl[:] = ctrl
+    s.step(5000)
+    st = L.step(L.pack_state(m.qpos0[None], np.zeros((1, 1)), ctrl=np.array([[ctrl]])), 5000)
+    u = L.unpack_state(st)
+    if fr == "-3 3":
+        assert np.isclose(s.qvel[0], -(mg - 3.0) / 5.0, rtol=1e-9) and np.isclose(u["qvel"][0, 0], -(mg - 3.0) / 5.0, rtol=1e-9)
+    else:
+        q = (kp * ctrl - mg) / (kp + stiff)
+        assert np.isclose(s.qpos[0], q, rtol=1e-8) and abs(s.qvel[0]) < 1e-9
+        assert np.isclose(u["qpos"][0, 0], q, rtol=1e-8)
+
+
+@pytest.mark.parametrize("solref,solimp", [((0.02, 1.0), (0.9, 0.95, 0.001, 0.5, 2.0)), ((0.01, 1.0), (0.95, 0.99, 0.001, 0.5, 2.0))])
+def test_weld_sags_by_the_closed_form_under_gravity(solref, solimp):
+    """A body welded to a fixed mocap body under gravity: the translational weld rows at the centre of mass are unit vectors with
+    A = 1 / m, so the sag is the soft-constraint closed form again (equality rows: two-sided quadratic cost)."""
+    from hostsim import lane1
+    m = compile_mjcf(WELD.replace('gravity="0 0 0"', 'gravity="0 0 -9.81"').replace('<weld body1="mocap" body2="b"/>',
+                     '<weld body1="mocap" body2="b" solref="%g %g" solimp="%g %g %g %g %g"/>' % (solref + solimp)))
+    k = 1.0 / (solimp[1] ** 2 * solref[0] ** 2 * solref[1] ** 2)
+    r = -1e-4
+    for _ in range(300):
+        d = _impedance(solimp, r)
+        r = -(1 - d) * 9.81 / (d * d * k)
+    s = OracleSim(m)
+    s.reset()
+    s.step(8000)
+    assert np.isclose(s.qpos[2], r, rtol=1e-6) and np.abs(s.qvel).max() < 1e-8
+    L = lane1.sim(m, f64=True)
+    st = L.step(L.pack_state(m.qpos0[None], np.zeros((1, 6)), mocap_pos=np.zeros((1, 3)), mocap_quat=np.array([[1.0, 0, 0, 0]])), 8000)
+    assert np.isclose(L.unpack_state(st)["qpos"][0, 2], r, rtol=1e-6)
