@@ -300,3 +300,35 @@ def test_weld_sags_by_the_closed_form_under_gravity(solref, solimp):
     L = lane1.sim(m, f64=True)
     st = L.step(L.pack_state(m.qpos0[None], np.zeros((1, 6)), mocap_pos=np.zeros((1, 3)), mocap_quat=np.array([[1.0, 0, 0, 0]])), 8000)
     assert np.isclose(L.unpack_state(st)["qpos"][0, 2], r, rtol=1e-6)
+
+
+INCLINE = """<mujoco><compiler angle="radian" autolimits="true"/>
+<option integrator="implicitfast" timestep="0.001" cone="elliptic" impratio="{imp}" noslip_iterations="2" gravity="{gx} 0 {gz}"/>
+<worldbody><geom name="geom:ground" type="box" size="50 50 0.02" pos="0 0 -0.02" friction="{mu} 0.005 0.0001"/>
+<body name="b" pos="0 0 0.0039"><freejoint name="j"/>
+<geom type="box" size="0.1 0.08 0.004" mass="0.4" friction="0.1 0.005 0.0001" condim="{cd}"/></body></worldbody></mujoco>"""
+
+
+@pytest.mark.parametrize("imp,mu,cd", [(1, 0.5, 3), (3, 1.0, 4), (3, 0.2, 3), (10, 0.5, 3)])
+def test_coulomb_threshold_on_an_incline(imp, mu, cd):
+    """A flat box on an incline (gravity tilted by theta; friction = max of the two geoms'): with tan(theta) = 0.97 mu it does not
+    move (elliptic cone + noslip: < 1 um in 0.5 s), with 1.03 mu it slides by x = g cos(theta) (tan(theta) - mu) t^2 / 2 to 1 % -
+    whatever impratio and condim are.  Friction mixing, the cone's mu scaling and the noslip pass against Coulomb's law; the kernel
+    source (fp64 1-lane build) slides the same distance."""
+    from hostsim import lane1
+    g, T = 9.81, 0.5
+    for f in (0.97, 1.03):
+        th = np.arctan(mu * f)
+        m = compile_mjcf(INCLINE.format(imp=imp, gx=g * np.sin(th), gz=-g * np.cos(th), mu=mu, cd=cd))
+        s = OracleSim(m)
+        s.reset()
+        s.step(int(T / 1e-3))
+        assert s.ncon == 4
+        if f < 1:
+            assert abs(s.qpos[0]) < 1e-6 and abs(s.qvel[0]) < 1e-5
+        else:
+            x = 0.5 * g * np.cos(th) * (np.tan(th) - mu) * T * T
+            assert np.isclose(s.qpos[0], x, rtol=1e-2), (s.qpos[0], x)
+            L = lane1.sim(m, f64=True)
+            st = L.step(L.pack_state(m.qpos0[None], np.zeros((1, 6))), int(T / 1e-3))
+            assert np.isclose(L.unpack_state(st)["qpos"][0, 0], s.qpos[0], rtol=1e-6)
