@@ -332,3 +332,19 @@ def test_coulomb_threshold_on_an_incline(imp, mu, cd):
             L = lane1.sim(m, f64=True)
             st = L.step(L.pack_state(m.qpos0[None], np.zeros((1, 6))), int(T / 1e-3))
             assert np.isclose(L.unpack_state(st)["qpos"][0, 0], s.qpos[0], rtol=1e-6)
+
+
+def test_resting_box_manifold_is_the_four_corners_with_equal_loads():
+    """Face-on-face manifold of the convex path: a box at rest on the ground box gets four contacts at the corners of its footprint
+    (reference face clipped against the incident face), each carrying m g / 4, normal along the ground's face normal."""
+    m = compile_mjcf(INCLINE.format(imp=3, gx=0.0, gz=-9.81, mu=0.5, cd=3))
+    s = OracleSim(m)
+    s.reset()
+    s.step(3000)
+    con = s.contacts()
+    assert len(con) == 4 and np.abs(s.qvel).max() < 1e-8
+    corners = sorted((round(float(c[0]), 6), round(float(c[1]), 6)) for c in con)
+    assert corners == [(-0.1, -0.08), (-0.1, 0.08), (0.1, -0.08), (0.1, 0.08)]
+    assert np.allclose(np.abs(con[:, 3:6]), [[0, 0, 1]] * 4, atol=1e-9)
+    f = s.efc("force")[con[:, 17].astype(int)]
+    assert np.allclose(f, 0.4 * 9.81 / 4, rtol=1e-6) and np.allclose(con[:, 12], con[0, 12], rtol=1e-6) and con[0, 12] < 0
