@@ -195,9 +195,10 @@ def test_resting_depth_follows_the_soft_constraint_model(mass, solref, solimp):
     assert len(con) == 1 and np.abs(s.qvel).max() < 1e-9
     assert np.isclose(con[0, 12], r, rtol=1e-6), (con[0, 12], r)
     assert np.isclose(s.efc("force")[int(con[0, 17])], mass * 9.81, rtol=1e-9)
-    L = lane1.sim(m, f64=True)
-    st = L.step(L.pack_state(m.qpos0[None], np.zeros((1, 6))), 3000)
-    assert np.isclose(L.unpack_state(st)["qpos"][0, 2] - 0.02, r, rtol=1e-6)
+    for f64, tol in ((True, 1e-6), (False, 1e-4)):  # the fp32 build of the kernel source too (measured 1.4e-5)
+        L = lane1.sim(m, f64=f64)
+        st = L.step(L.pack_state(m.qpos0[None], np.zeros((1, 6))), 3000)
+        assert np.isclose(L.unpack_state(st)["qpos"][0, 2] - 0.02, r, rtol=tol)
 
 
 SLIDER = """<mujoco><compiler angle="radian" autolimits="true"/>
@@ -304,7 +305,7 @@ def test_weld_sags_by_the_closed_form_under_gravity(solref, solimp):
 
 INCLINE = """<mujoco><compiler angle="radian" autolimits="true"/>
 <option integrator="implicitfast" timestep="0.001" cone="elliptic" impratio="{imp}" noslip_iterations="2" gravity="{gx} 0 {gz}"/>
-<worldbody><geom name="geom:ground" type="box" size="50 50 0.02" pos="0 0 -0.02" friction="{mu} 0.005 0.0001"/>
+<worldbody><geom name="geom:ground" type="box" size="5 5 0.02" pos="0 0 -0.02" friction="{mu} 0.005 0.0001"/>
 <body name="b" pos="0 0 0.0039"><freejoint name="j"/>
 <geom type="box" size="0.1 0.08 0.004" mass="0.4" friction="0.1 0.005 0.0001" condim="{cd}"/></body></worldbody></mujoco>"""
 
@@ -324,9 +325,16 @@ def test_coulomb_threshold_on_an_incline(imp, mu, cd):
         s.reset()
         s.step(int(T / 1e-3))
         assert s.ncon == 4
+        # the fp32 build of the kernel source: same verdict, its slide corresponds to a friction coefficient within 1 % (measured 0.5 %).  The ground is 10 m wide, not
+        # 100 m: against a 100 m box the fp32 MPR depth is noisy by ~0.1 mm (vertex coordinates of 50 m carry 4 um of rounding each)
+        # and the box near its friction limit slips in bursts - found with this very test; DESIGN.md 9
+        L32 = lane1.sim(m, f64=False)
+        x32 = L32.unpack_state(L32.step(L32.pack_state(m.qpos0[None], np.zeros((1, 6))), int(T / 1e-3)))["qpos"][0, 0]
         if f < 1:
-            assert abs(s.qpos[0]) < 1e-6 and abs(s.qvel[0]) < 1e-5
+            assert abs(s.qpos[0]) < 1e-6 and abs(s.qvel[0]) < 1e-5 and abs(x32) < 2e-6
         else:
+            mu_eff32 = np.tan(th) - 2 * x32 / (g * np.cos(th) * T * T)  # what friction coefficient the fp32 slide corresponds to
+            assert abs(mu_eff32 / mu - 1) < 1e-2, mu_eff32
             x = 0.5 * g * np.cos(th) * (np.tan(th) - mu) * T * T
             assert np.isclose(s.qpos[0], x, rtol=1e-2), (s.qpos[0], x)
             L = lane1.sim(m, f64=True)
