@@ -356,3 +356,42 @@ def test_resting_box_manifold_is_the_four_corners_with_equal_loads():
     assert np.allclose(np.abs(con[:, 3:6]), [[0, 0, 1]] * 4, atol=1e-9)
     f = s.efc("force")[con[:, 17].astype(int)]
     assert np.allclose(f, 0.4 * 9.81 / 4, rtol=1e-6) and np.allclose(con[:, 12], con[0, 12], rtol=1e-6) and con[0, 12] < 0
+
+
+DOUBLE_PENDULUM = """<mujoco><compiler angle="radian" autolimits="true"/>
+<option integrator="implicitfast" timestep="0.001" cone="elliptic" gravity="0 0 -9.81"/>
+<worldbody><body name="a" pos="0 0 0"><joint name="h1" type="hinge" axis="0 1 0"/>
+<geom type="sphere" size="0.03" mass="0.7" pos="0 0 -0.4" contype="0" conaffinity="0"/>
+<body name="b" pos="0 0 -0.4"><joint name="h2" type="hinge" axis="0 1 0"/>
+<geom type="box" size="0.02 0.02 0.1" mass="0.3" pos="0 0 -0.15" contype="0" conaffinity="0"/></body></body></worldbody></mujoco>"""
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_double_pendulum_normal_mode_periods(mode):
+    """Small oscillations of a two-link pendulum (a sphere on a massless arm, a box hanging from it) started in a normal mode: the
+    period is 2 pi / omega with omega^2 an eigenvalue of M^-1 K, M and K written out by hand from the masses, offsets and the closed-form
+    inertias of a sphere and a box.  Geom inertia, body frames, hinge kinematics, CRBA, the gravity part of RNE and the integrator,
+    in the oracle and the kernel source, to 2e-5."""
+    from hostsim import lane1
+    m1, l1, r, m2, c2, g = 0.7, 0.4, 0.03, 0.3, 0.15, 9.81
+    I1, I2 = 0.4 * m1 * r * r, m2 / 3.0 * (0.02 ** 2 + 0.1 ** 2)
+    M = np.array([[m1 * l1 ** 2 + I1 + m2 * (l1 + c2) ** 2 + I2, m2 * (l1 + c2) * c2 + I2], [m2 * (l1 + c2) * c2 + I2, m2 * c2 ** 2 + I2]])
+    K = np.array([[m1 * g * l1 + m2 * g * (l1 + c2), m2 * g * c2], [m2 * g * c2, m2 * g * c2]])
+    vals, vecs = np.linalg.eig(np.linalg.solve(M, K))
+    order = np.argsort(vals.real)
+    w, v = np.sqrt(vals.real[order[mode]]), vecs[:, order[mode]].real
+    v = v / np.abs(v).max() * 0.01
+    model = compile_mjcf(DOUBLE_PENDULUM)
+    s, L = OracleSim(model), lane1.sim(model, f64=True)
+    s.reset()
+    s.qpos[:] = v
+    st = L.pack_state(v[None], np.zeros((1, 2)))
+    n = int(6 * 2 * np.pi / w / 1e-3)
+    qs, ql = [], []
+    for _ in range(n):
+        s.step(1)
+        st = L.step(st, 1)
+        qs.append(s.qpos[0]); ql.append(L.unpack_state(st)["qpos"][0, 0])
+    for q in (np.array(qs), np.array(ql)):
+        zc = [k + q[k] / (q[k] - q[k + 1]) for k in range(len(q) - 1) if q[k] > 0 >= q[k + 1]]
+        assert len(zc) >= 5 and abs(np.mean(np.diff(zc)) * 1e-3 / (2 * np.pi / w) - 1) < 2e-5
