@@ -251,6 +251,13 @@ def compile_mjcf(xml: str, assets: dict | None = None, massprops: dict | None = 
     B["name"].append("world"); B["parent"].append(0); B["pos"].append(np.zeros(3)); B["quat"].append(np.array([1., 0, 0, 0]))
     B["mocap"].append(False); B["gravcomp"].append(0.0); B["inertial"].append(None); B["cls"].append("main")
 
+    def quat_of(attrs, what):
+        """orientation of a body / geom / inertial: `quat` only - the other MJCF spellings are refused loudly, not read as identity"""
+        for k in ("euler", "axisangle", "xyaxes", "zaxis"):
+            if k in attrs:
+                raise NotImplementedError(f"{what}: orientation given as '{k}' (this compiler reads 'quat' only; the six gripper templates use nothing else)")
+        return quat_norm(_f(attrs.get("quat"), 4, [1, 0, 0, 0]))
+
     def add_geom(g, bid, childclass):
         cls = g.get("class", childclass or "main")
         a = dfl.resolve(cls, ["geom"])
@@ -261,7 +268,7 @@ def compile_mjcf(xml: str, assets: dict | None = None, massprops: dict | None = 
         if "fromto" in a:
             raise NotImplementedError("geom fromto")
         G["name"].append(a.get("name")); G["type"].append(gtype); G["body"].append(bid)
-        G["pos"].append(_f(a.get("pos"), 3, [0, 0, 0])); G["quat"].append(quat_norm(_f(a.get("quat"), 4, [1, 0, 0, 0])))
+        G["pos"].append(_f(a.get("pos"), 3, [0, 0, 0])); G["quat"].append(quat_of(a, "geom"))
         G["size"].append(_f(a.get("size"), 3, [0, 0, 0])); G["mesh"].append(a.get("mesh"))
         G["contype"].append(int(a.get("contype", 1))); G["conaffinity"].append(int(a.get("conaffinity", 1)))
         G["condim"].append(int(a.get("condim", 3))); G["priority"].append(int(a.get("priority", 0)))
@@ -296,7 +303,7 @@ def compile_mjcf(xml: str, assets: dict | None = None, massprops: dict | None = 
         bid = len(B["name"])
         cc = node.get("childclass", childclass)
         B["name"].append(node.get("name")); B["parent"].append(parent)
-        B["pos"].append(_f(node.get("pos"), 3, [0, 0, 0])); B["quat"].append(quat_norm(_f(node.get("quat"), 4, [1, 0, 0, 0])))
+        B["pos"].append(_f(node.get("pos"), 3, [0, 0, 0])); B["quat"].append(quat_of(node.attrib, "body"))
         B["mocap"].append(node.get("mocap") == "true"); B["gravcomp"].append(float(node.get("gravcomp", 0)))
         B["cls"].append(cc)
         inert = node.find("inertial")
@@ -309,7 +316,7 @@ def compile_mjcf(xml: str, assets: dict | None = None, massprops: dict | None = 
                     Q[:, 2] = -Q[:, 2]
                 iq, di = mat_to_quat(Q), w
             else:
-                iq = quat_norm(_f(inert.get("quat"), 4, [1, 0, 0, 0]))
+                iq = quat_of(inert.attrib, "inertial")
                 di = _f(inert.get("diaginertia"), 3, [0, 0, 0])
             B["inertial"].append({"mass": float(inert.get("mass")), "pos": _f(inert.get("pos"), 3, [0, 0, 0]),
                                   "quat": iq, "diag": di})

@@ -1,5 +1,6 @@
 """Model compiler: dimensions, id ordering, contact mixing."""
 import numpy as np
+import pytest
 
 from mj_grasp_sim_b200 import scenes
 from mj_grasp_sim_b200.compiler import mesh as meshlib
@@ -95,3 +96,44 @@ def test_pose_processing_matches_se3pose_semantics():
     assert p.dtype == np.float32
     assert np.allclose(p[0], [0, 0, -0.102, 0.70710677, 0, 0, 0.70710677], atol=1e-7)
     assert np.allclose(p[1, :3], [0.01, 0.02, 0.03 - 0.102], atol=1e-7)
+
+
+PRIM = """<mujoco><compiler angle="radian"/><worldbody><body name="b" pos="0.1 0.2 0.3"><freejoint/>
+<geom type="{t}" size="{s}" density="850" pos="0.01 -0.02 0.03" quat="{q}"/></body></worldbody></mujoco>"""
+
+
+@pytest.mark.parametrize("gtype,size", [("sphere", (0.03,)), ("box", (0.02, 0.03, 0.05)), ("cylinder", (0.02, 0.04)), ("capsule", (0.015, 0.035))])
+def test_primitive_geom_mass_properties_match_closed_forms(gtype, size):
+    """Mass, centre of mass and the full inertia tensor of a body made of one rotated primitive geom against the textbook closed forms
+    (capsule = cylinder + two hemispheres, each (83 / 320) m r^2 about its own centre of mass, 3 r / 8 from its flat face)."""
+    from mj_grasp_sim_b200.compiler.mjcf import quat_to_mat
+    q = np.array([0.8, 0.3, -0.4, 0.33]); q /= np.linalg.norm(q)
+    m = compile_mjcf(PRIM.format(t=gtype, s=" ".join("%g" % x for x in size), q=" ".join("%.17g" % x for x in q)))
+    rho = 850.0
+    if gtype == "sphere":
+        r, = size
+        mass = rho * 4 / 3 * np.pi * r ** 3
+        I = np.full(3, 0.4 * mass * r * r)
+    elif gtype == "box":
+        a, b, c = size
+        mass = rho * 8 * a * b * c
+        I = mass / 3 * np.array([b * b + c * c, a * a + c * c, a * a + b * b])
+    elif gtype == "cylinder":
+        r, h = size
+        mass = rho * np.pi * r * r * 2 * h
+        I = np.array([mass * (3 * r * r + 4 * h * h) / 12] * 2 + [0.5 * mass * r * r])
+    else:
+        r, h = size
+        mc, ms = rho * np.pi * r * r * 2 * h, rho * 4 / 3 * np.pi * r ** 3
+        mass = mc + ms
+        side = mc * (3 * r * r + 4 * h * h) / 12 + 2 * (83 / 320 * (ms / 2) * r * r + (ms / 2) * (h + 3 * r / 8) ** 2)
+        I = np.array([side, side, 0.5 * mc * r * r + 0.4 * ms * r * r])
+    assert np.isclose(m.body_mass[1], mass, rtol=1e-12) and np.allclose(m.body_ipos[1], [0.01, -0.02, 0.03], atol=1e-15)
+    Rg, Ri = quat_to_mat(q), quat_to_mat(m.body_iquat[1])
+    assert np.allclose(Ri @ np.diag(m.body_inertia[1]) @ Ri.T, Rg @ np.diag(I) @ Rg.T, rtol=1e-10, atol=1e-16)
+
+
+def test_unsupported_orientation_spellings_are_refused():
+    for attr in ('euler="0.1 0.2 0.3"', 'axisangle="0 0 1 0.3"', 'zaxis="0 1 0"', 'xyaxes="1 0 0 0 1 0"'):
+        with pytest.raises(NotImplementedError):
+            compile_mjcf(PRIM.format(t="box", s="0.02 0.03 0.05", q="1 0 0 0").replace('quat="1 0 0 0"', attr))
